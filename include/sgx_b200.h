@@ -1,0 +1,184 @@
+/*
+ * sgx_b200.h -- C ABI of libsgx_b200.so, the B200-native (sm_100a) engine for the hot path of the
+ * `spectrograms` crate (jmg049/Spectrograms v2.1.0): stft() / StftPlan / SpectrogramPlanner plans
+ * (linear | mel | ERB | LogHz  x  power | magnitude | dB) / mfcc_from_log_mel, in f32 and f64.
+ *
+ * The reference exposes no C ABI; its seam for this path is the plan API. Every entry point
+ * below names the reference item it replaces (paths relative to the reference checkout; a bare :N is
+ * src/spectrogram.rs:N). A Rust `gpu` feature would bind these with `extern "C"`.
+ *
+ * Conventions (mirroring the reference):
+ *   - Errors: every call returns sgx_status; the four non-OK codes are the four SpectrogramError variants
+ *     (src/error.rs:13-28). sgx_last_error_message() returns the thread-local Display string of the last error.
+ *   - Ownership: the caller owns every buffer; nothing is retained after a call returns (for device pointers: after
+ *     the work queued on `stream` completes). A plan owns its device tables and scratch.
+ *   - Threading: a plan is `&mut self` -- one call at a time per plan; distinct plans are independent.
+ *   - Layout: outputs are row-major (rows, n_frames) with frames contiguous (:248, :1433), clips outermost.
+ *     Complex values are interleaved (re, im) like num_complex::Complex<T>.
+ *   - Pointers may be host or device pointers (detected with cudaPointerGetAttributes). Device pointers run
+ *     asynchronously on `stream`; host pointers are staged through pinned chunks, computed, copied back, and the
+ *     call returns after the results are in host memory.
+ *   - There is no CPU fallback: without a CUDA device every compute call fails with SGX_BACKEND_ERROR.
+ */
+#ifndef SGX_B200_H
+#define SGX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* SpectrogramError (src/error.rs:13-28) */
+typedef enum {
+    SGX_OK = 0,
+    SGX_INVALID_INPUT = 1,       /* InvalidInput(String) */
+    SGX_DIMENSION_MISMATCH = 2,  /* DimensionMismatch{expected, got} */
+    SGX_BACKEND_ERROR = 3,       /* FftBackendError{backend: "cuda", msg} */
+    SGX_INTERNAL_ERROR = 4       /* InternalError(String) */
+} sgx_status;
+
+/* Sample (src/sample.rs:23-86): the two sealed implementors */
+typedef enum { SGX_F32 = 0, SGX_F64 = 1 } sgx_dtype;
+
+/* WindowType (src/window.rs:19-50) */
+typedef enum {
+    SGX_WIN_RECTANGULAR = 0, SGX_WIN_HANNING = 1, SGX_WIN_HAMMING = 2, SGX_WIN_BLACKMAN = 3,
+    SGX_WIN_KAISER = 4,   /* window_param = beta */
+    SGX_WIN_GAUSSIAN = 5, /* window_param = std (samples) */
+    SGX_WIN_CUSTOM = 6    /* custom_window[custom_window_len] */
+} sgx_window;
+
+/* frequency scales: LinearHz / Mel / Erb / LogHz marker types (MappingKind :1639-1656; Cqt is out of scope) */
+typedef enum { SGX_MAP_LINEAR = 0, SGX_MAP_MEL = 1, SGX_MAP_ERB = 2, SGX_MAP_LOGHZ = 3 } sgx_mapping;
+
+/* AmpScaleSpec implementors Power / Magnitude / Decibels (:1986-2037) */
+typedef enum { SGX_AMP_POWER = 0, SGX_AMP_MAGNITUDE = 1, SGX_AMP_DECIBELS = 2 } sgx_amp;
+
+/* MelNorm (:3708-3734) and ErbSpacing (src/erb.rs:17-25) */
+typedef enum { SGX_MELNORM_NONE = 0, SGX_MELNORM_SLANEY = 1, SGX_MELNORM_L1 = 2, SGX_MELNORM_L2 = 3 } sgx_mel_norm;
+typedef enum { SGX_ERB_LINEAR = 0, SGX_ERB_APPLE_TR35 = 1 } sgx_erb_spacing;
+
+/* what a plan produces */
+typedef enum {
+    SGX_OUT_SPECTROGRAM = 0,  /* SpectrogramPlan::compute  -> (n_bins, n_frames) of T             (:240-294)   */
+    SGX_OUT_COMPLEX_STFT = 1, /* StftPlan::compute / stft() -> (n_fft/2+1, n_frames) of Complex<T> (:1424-1458) */
+    SGX_OUT_MFCC = 2          /* mfcc(): mel dB plan fused with mfcc_from_log_mel -> (n_mfcc[-1], n_frames)
+                                 (src/mfcc.rs:359-379, :224-273) */
+} sgx_output;
+
+/*
+ * One flat description of a plan = StftParams (:3452-3506) + SpectrogramParams (:4108-4140) + the scale-specific
+ * params MelParams (:3744-3920) / ErbParams (src/erb.rs:30-43) / LogHzParams (:3955-3975) + Option<LogParams>
+ * (:4052-4100) + MfccParams (src/mfcc.rs:21-39). Zero-initialise, then fill what applies.
+ */
+typedef struct {
+    sgx_dtype dtype;
+    size_t n_fft;               /* NonZeroUsize */
+    size_t hop_size;            /* NonZeroUsize, <= n_fft (:3485) */
+    int centre;                 /* zero padding of n_fft/2 both sides (:1236-1237) */
+    sgx_window window;
+    double window_param;
+    const double *custom_window;
+    size_t custom_window_len;   /* must equal n_fft (:3490-3497) */
+    double sample_rate_hz;      /* finite, > 0 (:4130) */
+
+    sgx_mapping mapping;
+    size_t n_bands;             /* n_mels / n_filters / n_bins; ignored for SGX_MAP_LINEAR */
+    double f_min, f_max;
+    sgx_mel_norm mel_norm;
+    sgx_erb_spacing erb_spacing;
+
+    sgx_amp amp;
+    int has_floor_db;           /* Option<&LogParams>: 0 = None. Decibels with None yields raw power (:2052-2058, :2075) */
+    double floor_db;
+
+    sgx_output output;
+    size_t n_mfcc;              /* SGX_OUT_MFCC only */
+    int include_c0;
+    size_t lifter;
+
+    int device;                 /* CUDA ordinal; -1 = current device */
+} sgx_plan_desc;
+
+typedef struct sgx_plan sgx_plan;
+
+/* Display string of the last error raised on this thread ("Invalid input: ...", "Dimension mismatch: expected N,
+ * got M", "cuda -- FFT backend error: ...", "Internal error: ..."), src/error.rs:17-27. Never NULL. */
+const char *sgx_last_error_message(void);
+
+/* expected/got of the last SGX_DIMENSION_MISMATCH on this thread (src/error.rs:21) */
+void sgx_last_dimension_mismatch(size_t *expected, size_t *got);
+
+/* Library / build information: "sgx_b200 <version> sm_100a". */
+const char *sgx_version(void);
+
+/*
+ * SpectrogramPlanner::{linear,mel,erb,log_hz}_plan::<A,T> (:893-1102) and StftPlan::<T>::new (:1204-1228).
+ * Validates like StftParams::new, SpectrogramParams::new, MelParams/ErbParams/LogHzParams::new, the planner's
+ * f_max <= Nyquist checks (:954-959, :1016-1022, :1078-1084) and LogParams::new; builds window, twiddles,
+ * filterbank, DCT basis in f64 on the host exactly as the reference does and uploads them once.
+ */
+sgx_status sgx_plan_create(const sgx_plan_desc *desc, sgx_plan **out_plan);
+sgx_status sgx_plan_destroy(sgx_plan *plan);
+
+/* SpectrogramPlan::output_shape (:512-519) / StftPlan::output_shape (:1596-1602) -- frame_count (:1230-1250). */
+sgx_status sgx_plan_output_shape(const sgx_plan *plan, size_t n_samples, size_t *n_rows, size_t *n_frames);
+
+/* Axes: FrequencyMapping::frequencies_hz (:1909-1945) into freqs[n_bins]; build_time_axis_seconds (:2128-2139)
+ * into times[n_frames]. Either pointer may be NULL. For SGX_OUT_MFCC the frequency axis is the mel axis. */
+sgx_status sgx_plan_axes(const sgx_plan *plan, size_t n_frames, double *freqs, double *times);
+
+/* make_window::<T> (:2159-2235): writes n_fft values of the plan's dtype to host memory. */
+sgx_status sgx_plan_window(const sgx_plan *plan, void *out_host);
+
+/* Inspection of the frequency mapping: dense row-major (n_bins, n_fft/2+1) f64 copy of the SparseMatrix (:43-118)
+ * or ERB response matrix (src/erb.rs:261); *nnz = stored non-zeros (sparse mappings) or n_bins*out_len (dense). */
+sgx_status sgx_plan_filterbank(const sgx_plan *plan, double *dense_out_host, size_t *nnz);
+
+/* Name of the CUDA kernel family the plan dispatches to (e.g. "r2c_fused_generic", "r2c_fused_n400"). */
+const char *sgx_plan_kernel_name(const sgx_plan *plan);
+
+/* Number of kernel launches issued by the last compute call on this plan. */
+size_t sgx_plan_last_launch_count(const sgx_plan *plan);
+
+/* Force the generic kernel family (1) or allow specialised kernels (0, default). Test hook. */
+sgx_status sgx_plan_force_generic(sgx_plan *plan, int force);
+
+/*
+ * The batched entry point: for c in 0..n_clips { plan.compute_into(&samples[c], &mut out[c]) }  (:414-477,
+ * :1548-1580; the reference has no batch API -- batching is a user loop, src/lib.rs:228-235).
+ *   samples : [n_clips][clip_stride] of T, n_samples valid per clip (n_samples >= 1, NonEmptySlice)
+ *   out     : [n_clips][out_rows][out_cols] of T (Complex<T> for SGX_OUT_COMPLEX_STFT), clip pitch out_clip_stride
+ *             elements (0 = out_rows*out_cols)
+ * out_rows/out_cols are validated like compute_into: rows first, then columns (:423-434) -> SGX_DIMENSION_MISMATCH.
+ * n_clips = 1 with host pointers reproduces the reference call exactly.
+ */
+sgx_status sgx_plan_compute_batch(sgx_plan *plan, const void *samples, size_t n_clips, size_t n_samples,
+                                  size_t clip_stride, void *out, size_t out_rows, size_t out_cols,
+                                  size_t out_clip_stride, void *cuda_stream);
+
+/* SpectrogramPlan::compute_frame (:335-372) / StftPlan::compute_frame_simple (:1500-1507): one frame -> out[rows].
+ * Like the reference, frame_idx is not range checked: past the end it reads zero padding. */
+sgx_status sgx_plan_compute_frame(sgx_plan *plan, const void *samples, size_t n_samples, size_t frame_idx,
+                                  void *out, void *cuda_stream);
+
+/*
+ * mfcc_from_log_mel::<T> (src/mfcc.rs:224-273): unnormalised DCT-II over n_mels (:278-292), lifter (:297-316),
+ * optional c0 drop (:262-267). log_mel: [n_clips][n_mels][n_frames]; out: [n_clips][rows][n_frames] with
+ * rows = n_mfcc - (include_c0 || n_mfcc == 1 ? 0 : 1). n_mfcc > n_mels -> SGX_INVALID_INPUT (:231-233).
+ */
+sgx_status sgx_mfcc_from_log_mel(sgx_dtype dtype, const void *log_mel, size_t n_clips, size_t n_mels,
+                                 size_t n_frames, size_t n_mfcc, int include_c0, size_t lifter, void *out,
+                                 int device, void *cuda_stream);
+
+/* free fn fft() / rfft helpers (:4490-4520): one unnormalised R2C of n_in <= n_fft samples (zero padded), no window.
+ * out: n_fft/2+1 Complex<T>. n_in > n_fft -> SGX_INVALID_INPUT "Input length (..) exceeds FFT size (..)". */
+sgx_status sgx_rfft(sgx_dtype dtype, const void *samples, size_t n_in, size_t n_fft, void *out, int device,
+                    void *cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGX_B200_H */

@@ -1,0 +1,90 @@
+// epilogue.cuh -- the fused back half of every kernel family: power tile in shared memory ->
+// frequency mapping -> amplitude scaling -> (DCT-II + lifter) -> bin-major coalesced store.
+//
+// Reference semantics restated here (bare :N = src/spectrogram.rs:N):
+//   FrequencyMapping::apply :1822-1881, SparseMatrix::multiply_vec :102-117 (ascending columns, acc += T(w)*x without
+//   FMA), ErbFilterbank::apply_to_power_spectrum src/erb.rs:384-398, AmplitudeScaling::apply_in_place :2068-2080,
+//   column write data[[row, frame]] :285-287, mfcc_from_log_mel src/mfcc.rs:224-273.
+//
+// Thread mapping: the frame index is the fastest-varying index across lanes, so every global store is a run of
+// consecutive frames of one output row (the reference layout is (rows, n_frames) with frames contiguous), and every
+// shared-memory read of the tile is lane-stride `tile_stride` (odd -> conflict free). Filterbank weights are
+// warp-uniform and come through the read-only path.
+#pragma once
+
+#include "kparams.cuh"
+
+namespace sgx {
+
+// P: power tile, P[f * p.tile_stride + k], f < nf valid frames (rows beyond nf are not read)
+// scratch: second tile region with at least FT * tile_stride elements (used for the log-mel tile when output == MFCC)
+template <typename T>
+__device__ __forceinline__ void epilogue_from_power(const KParams &p, const T *__restrict__ P, T *__restrict__ scratch,
+                                                    int clip, long long f0, int nf) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int FT = p.FT;
+    const T eps = static_cast<T>(p.eps);
+    T *out = static_cast<T *>(p.out) + static_cast<long long>(clip) * p.out_clip_stride + (f0 - p.out_frame_origin);
+    const bool to_mfcc = (p.output == SGX_OUT_MFCC);
+    const int ts = p.tile_stride;
+
+    // rows x frames, frames fastest
+    const int total = p.n_bins * FT;
+    for (int idx = tid; idx < total; idx += nthr) {
+        const int row = idx / FT;
+        const int f = idx - row * FT;
+        if (f >= nf) continue;
+        const T *pf = P + f * ts;
+        T acc;
+        if (p.mapping == SGX_MAP_LINEAR) {
+            acc = pf[row];
+        } else if (p.mapping == SGX_MAP_ERB) {
+            const T *w = static_cast<const T *>(p.dense) + static_cast<long long>(row) * p.out_len;
+            acc = T(0);
+            for (int k = 0; k < p.out_len; ++k) acc = t_add_rn(acc, t_mul_rn(__ldg(w + k), pf[k]));
+        } else {
+            const T *val = static_cast<const T *>(p.val);
+            const int e0 = __ldg(p.row_ptr + row), e1 = __ldg(p.row_ptr + row + 1);
+            acc = T(0);
+            for (int e = e0; e < e1; ++e) acc = t_add_rn(acc, t_mul_rn(__ldg(val + e), pf[__ldg(p.col + e)]));
+        }
+        acc = amp_scale<T>(acc, p.amp, p.apply_db, eps);
+        if (to_mfcc) scratch[f * ts + row] = acc;
+        else out[static_cast<long long>(row) * p.out_row_stride + f] = acc;
+    }
+    if (!to_mfcc) return;
+    __syncthreads();
+    // DCT-II over the mel axis, keep n_mfcc rows, lifter, optional c0 drop
+    const T *dct = static_cast<const T *>(p.dct);
+    const T *lift = static_cast<const T *>(p.lifter);
+    const int rows = p.n_mfcc - p.mfcc_row0;
+    for (int idx = tid; idx < rows * FT; idx += nthr) {
+        const int r = idx / FT;
+        const int f = idx - r * FT;
+        if (f >= nf) continue;
+        const int c = r + p.mfcc_row0;
+        const T *mf = scratch + f * ts;
+        const T *b = dct + static_cast<long long>(c) * p.n_bins;
+        T acc = T(0);
+        for (int i = 0; i < p.n_bins; ++i) acc = t_fma(mf[i], __ldg(b + i), acc);   // val.mul_add(basis, acc)
+        out[static_cast<long long>(r) * p.out_row_stride + f] = acc * __ldg(lift + c);
+    }
+}
+
+// S: complex spectrum tile, S[f * p.frame_stride + k]; StftPlan::compute column copy (:1440-1442)
+template <typename T>
+__device__ __forceinline__ void epilogue_complex(const KParams &p, const typename Cplx<T>::type *__restrict__ S, int clip,
+                                                 long long f0, int nf) {
+    using C = typename Cplx<T>::type;
+    const int FT = p.FT;
+    C *out = static_cast<C *>(p.out) + static_cast<long long>(clip) * p.out_clip_stride + (f0 - p.out_frame_origin);
+    const int total = p.out_len * FT;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const int k = idx / FT;
+        const int f = idx - k * FT;
+        if (f >= nf) continue;
+        out[static_cast<long long>(k) * p.out_row_stride + f] = S[f * p.frame_stride + k];
+    }
+}
+
+}  // namespace sgx

@@ -1,0 +1,95 @@
+// kparams.cuh -- kernel parameter block and small device helpers shared by all kernel families.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "../../include/sgx_b200.h"
+
+namespace sgx {
+
+constexpr int kMaxStages = 24;
+
+// Everything a fused STFT -> power -> mapping -> scaling (-> DCT) kernel needs. Passed by value (__grid_constant__).
+struct KParams {
+    // ---- input: [n_clips][clip_stride] samples, n_samples valid per clip
+    const void *samples;
+    long long n_samples;
+    long long clip_stride;
+    int n_clips;
+    // ---- which frames: [frame_begin, frame_begin + frames_todo), tiled FT frames per CTA
+    long long frame_begin;
+    long long frames_todo;
+    int tiles_per_clip;
+    int FT;
+    // ---- output: element (clip, row, frame) at out[clip*out_clip_stride + row*out_row_stride + (frame - frame_begin_out)]
+    void *out;
+    long long out_row_stride;
+    long long out_clip_stride;
+    long long out_frame_origin;
+    // ---- STFT (StftPlan fields, src/spectrogram.rs:1173-1187)
+    int n_fft, hop, pad, out_len;
+    int L;        // complex FFT length: n_fft/2 (even n_fft, packed real input) or n_fft (odd)
+    int even;
+    int n_stages;
+    int radix[kMaxStages];
+    const void *window;   // T[n_fft]            make_window cast to T (:2232)
+    const void *tw;       // complex T[L]        W_L^k
+    const void *post;     // complex T[L+1]      W_{n_fft}^k (even n_fft only)
+    // ---- frequency mapping (MappingKind :1639-1656)
+    int mapping;          // sgx_mapping
+    int n_bins;
+    const int *row_ptr;   // CSR (mel / loghz)
+    const int *col;
+    const void *val;      // T[nnz]              T::from_f64(value) (:113)
+    const void *dense;    // T[n_bins][out_len]  (erb)
+    // ---- amplitude scaling (AmplitudeScaling :2043-2081)
+    int amp;              // sgx_amp
+    int apply_db;         // amp == Decibels && db_floor.is_some()
+    double eps;           // 10^(floor_db/10), cast to T in the kernel (:2028)
+    // ---- output kind
+    int output;           // sgx_output
+    int n_mfcc;           // DCT rows computed
+    int mfcc_row0;        // 1 when c0 is dropped (!include_c0 && n_mfcc > 1), else 0
+    const void *dct;      // T[n_mfcc][n_bins]
+    const void *lifter;   // T[n_mfcc]
+    // ---- shared-memory geometry chosen by the host
+    int buf_elems;        // complex elements per ping-pong buffer
+    int frame_stride;     // complex elements between frames in a buffer (>= L+1)
+    int tile_stride;      // T elements between frames in the power / mel tile
+};
+
+template <typename T> struct Cplx;
+template <> struct Cplx<float> { using type = float2; };
+template <> struct Cplx<double> { using type = double2; };
+
+template <typename T> __device__ __forceinline__ typename Cplx<T>::type mk(T a, T b) {
+    typename Cplx<T>::type r; r.x = a; r.y = b; return r;
+}
+template <typename C> __device__ __forceinline__ C cmul(C a, C b) {
+    C r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r;
+}
+template <typename C> __device__ __forceinline__ C cadd(C a, C b) { C r; r.x = a.x + b.x; r.y = a.y + b.y; return r; }
+template <typename C> __device__ __forceinline__ C csub(C a, C b) { C r; r.x = a.x - b.x; r.y = a.y - b.y; return r; }
+
+__device__ __forceinline__ float t_sqrt(float v) { return sqrtf(v); }
+__device__ __forceinline__ double t_sqrt(double v) { return sqrt(v); }
+__device__ __forceinline__ float t_log10(float v) { return log10f(v); }
+__device__ __forceinline__ double t_log10(double v) { return log10(v); }
+__device__ __forceinline__ float t_max(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ double t_max(double a, double b) { return fmax(a, b); }
+__device__ __forceinline__ float t_fma(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ double t_fma(double a, double b, double c) { return fma(a, b, c); }
+// products/sums that must not be contracted into an FMA (the reference writes `acc += w * x`, :113)
+__device__ __forceinline__ float t_mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double t_mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float t_add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double t_add_rn(double a, double b) { return __dadd_rn(a, b); }
+
+// AmpScale::apply_from_power + apply_db_in_place (:1986-2037, :2068-2080)
+template <typename T> __device__ __forceinline__ T amp_scale(T v, int amp, int apply_db, T eps) {
+    if (amp == 1) v = t_sqrt(v);
+    if (apply_db) v = T(10) * t_log10(t_max(v, eps));
+    return v;
+}
+
+}  // namespace sgx

@@ -1,0 +1,18 @@
+// launch.hpp -- host-callable launchers of the kernel families (defined in the kernel_*.cu files).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "../../include/sgx_b200.h"
+#include "kparams.cuh"
+
+namespace sgx {
+
+// r2c_fused_generic: any n_fft (kernel_generic.cu)
+cudaError_t launch_generic(const KParams &p, bool f64, size_t smem_bytes, cudaStream_t stream);
+
+// standalone mfcc_from_log_mel (kernel_mfcc.cu): log_mel [n_clips][n_mels][n_frames] -> out [n_clips][rows][n_frames]
+cudaError_t launch_mfcc(bool f64, const void *log_mel, void *out, long long n_clips, int n_mels, long long n_frames,
+                        int n_mfcc, int row0, const void *dct, const void *lifter, cudaStream_t stream);
+
+}  // namespace sgx

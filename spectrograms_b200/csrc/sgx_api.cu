@@ -1,0 +1,553 @@
+// sgx_api.cu -- the C ABI (include/sgx_b200.h): plan objects, validation, table upload, dispatch, host staging.
+// No torch types, no CPU compute path: without a CUDA device every compute call fails with SGX_BACKEND_ERROR.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/sgx_b200.h"
+#include "kparams.cuh"
+#include "launch.hpp"
+#include "tables.hpp"
+
+using namespace sgx;
+
+// ------------------------------------------------------------------------------------------------ errors
+namespace {
+
+thread_local std::string g_err_msg = "";
+thread_local size_t g_exp = 0, g_got = 0;
+
+sgx_status set_error(const Error &e) {
+    switch (e.code) {
+        case SGX_INVALID_INPUT: g_err_msg = "Invalid input: " + e.msg; break;
+        case SGX_DIMENSION_MISMATCH:
+            g_exp = e.expected; g_got = e.got;
+            g_err_msg = "Dimension mismatch: expected " + std::to_string(e.expected) + ", got " + std::to_string(e.got);
+            break;
+        case SGX_BACKEND_ERROR: g_err_msg = "cuda -- FFT backend error: " + e.msg; break;
+        default: g_err_msg = "Internal error: " + e.msg; break;
+    }
+    return e.code;
+}
+
+[[noreturn]] void invalid(const std::string &m) { throw Error{SGX_INVALID_INPUT, m}; }
+[[noreturn]] void backend(const std::string &m) { throw Error{SGX_BACKEND_ERROR, m}; }
+[[noreturn]] void mismatch(size_t expected, size_t got) { throw Error{SGX_DIMENSION_MISMATCH, "", expected, got}; }
+
+void ck(cudaError_t e, const char *what) {
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        backend(std::string(what) + ": " + cudaGetErrorString(e));
+    }
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        ck(cudaGetDevice(&prev), "cudaGetDevice");
+        if (dev != prev) ck(cudaSetDevice(dev), "cudaSetDevice");
+        else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+template <typename F> sgx_status guarded(F &&f) {
+    try {
+        f();
+        return SGX_OK;
+    } catch (const Error &e) {
+        return set_error(e);
+    } catch (const std::bad_alloc &) {
+        return set_error(Error{SGX_INTERNAL_ERROR, "out of host memory"});
+    } catch (const std::exception &e) {
+        return set_error(Error{SGX_INTERNAL_ERROR, e.what()});
+    }
+}
+
+enum class PtrKind { Host, Device };
+PtrKind ptr_kind(const void *p) {
+    cudaPointerAttributes a;
+    const cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return PtrKind::Host; }
+    return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? PtrKind::Device : PtrKind::Host;
+}
+
+template <typename T> void *upload_as(const std::vector<double> &src) {
+    if (src.empty()) return nullptr;
+    std::vector<T> tmp(src.size());
+    for (size_t i = 0; i < src.size(); ++i) tmp[i] = static_cast<T>(src[i]);   // T::from_f64
+    void *d = nullptr;
+    ck(cudaMalloc(&d, tmp.size() * sizeof(T)), "cudaMalloc(table)");
+    ck(cudaMemcpy(d, tmp.data(), tmp.size() * sizeof(T), cudaMemcpyHostToDevice), "cudaMemcpy(table)");
+    return d;
+}
+void *upload(const std::vector<double> &src, bool f64) { return f64 ? upload_as<double>(src) : upload_as<float>(src); }
+int *upload_int(const std::vector<int> &src) {
+    if (src.empty()) return nullptr;
+    int *d = nullptr;
+    ck(cudaMalloc(&d, src.size() * sizeof(int)), "cudaMalloc(index)");
+    ck(cudaMemcpy(d, src.data(), src.size() * sizeof(int), cudaMemcpyHostToDevice), "cudaMemcpy(index)");
+    return d;
+}
+
+constexpr long double kPiL = 3.14159265358979323846264338327950288L;
+// interleaved (cos, sin) of -2*pi*k/n, k = 0..count-1, evaluated in extended precision
+std::vector<double> twiddle_table(size_t n, size_t count) {
+    std::vector<double> t(2 * count);
+    for (size_t k = 0; k < count; ++k) {
+        const long double a = -2.0L * kPiL * static_cast<long double>(k % n) / static_cast<long double>(n);
+        t[2 * k] = static_cast<double>(cosl(a));
+        t[2 * k + 1] = static_cast<double>(sinl(a));
+    }
+    return t;
+}
+
+constexpr int kStagingSlots = 3;
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ plan
+struct sgx_plan {
+    sgx_plan_desc desc{};
+    std::vector<double> custom;
+    HostTables tab;
+    int device = 0;
+    bool f64 = false;
+    size_t esize = 4;
+    size_t rows = 0;                 // output rows
+    // FFT factorisation
+    int L = 0, even = 0;
+    std::vector<int> radix;
+    // device tables
+    void *d_window = nullptr, *d_tw = nullptr, *d_post = nullptr, *d_val = nullptr, *d_dense = nullptr;
+    void *d_dct = nullptr, *d_lifter = nullptr;
+    int *d_row_ptr = nullptr, *d_col = nullptr;
+    // generic-family geometry
+    int FT = 1, buf_elems = 0, frame_stride = 0, tile_stride = 0;
+    size_t smem_bytes = 0;
+    // bookkeeping
+    bool force_generic = false;
+    bool on_device = false;
+    size_t last_launches = 0;
+    std::string kernel_name = "r2c_fused_generic";
+    // staging for host-pointer calls
+    struct Slot { void *d_in = nullptr; void *d_out = nullptr; size_t in_cap = 0, out_cap = 0; cudaStream_t s = nullptr; } slot[kStagingSlots];
+
+    ~sgx_plan() {
+        if (!on_device) return;
+        int prev = -1;
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != device) cudaSetDevice(device); else prev = -1;
+        for (void *p : {d_window, d_tw, d_post, d_val, d_dense, d_dct, d_lifter}) if (p) cudaFree(p);
+        if (d_row_ptr) cudaFree(d_row_ptr);
+        if (d_col) cudaFree(d_col);
+        for (auto &s : slot) {
+            if (s.d_in) cudaFree(s.d_in);
+            if (s.d_out) cudaFree(s.d_out);
+            if (s.s) cudaStreamDestroy(s.s);
+        }
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+namespace {
+
+void factorise(sgx_plan &pl) {
+    const size_t n = pl.desc.n_fft;
+    pl.even = (n % 2 == 0) ? 1 : 0;
+    size_t L = pl.even ? n / 2 : n;
+    if (L > (1u << 24)) backend("n_fft too large for the CUDA plan");
+    pl.L = static_cast<int>(L);
+    size_t rem = L;
+    pl.radix.clear();
+    while (rem % 4 == 0) { pl.radix.push_back(4); rem /= 4; }
+    while (rem % 2 == 0) { pl.radix.push_back(2); rem /= 2; }
+    while (rem % 3 == 0) { pl.radix.push_back(3); rem /= 3; }
+    while (rem % 5 == 0) { pl.radix.push_back(5); rem /= 5; }
+    if (rem > 1) pl.radix.insert(pl.radix.begin(), static_cast<int>(rem));   // cofactor stage (primes >= 7), evaluated directly
+    if (static_cast<int>(pl.radix.size()) > kMaxStages) backend("too many FFT stages");
+}
+
+void choose_generic_geometry(sgx_plan &pl) {
+    const size_t es = pl.esize;
+    const size_t out_len = pl.tab.out_len;
+    size_t fs = static_cast<size_t>(pl.L) + 1;
+    if (fs % 2 == 0) fs += 1;                                  // odd complex stride -> conflict-free frame-major reads
+    size_t ts = std::max(out_len, pl.tab.n_bins);
+    if (ts % 2 == 0) ts += 1;
+    const size_t per_frame_cplx = std::max(fs, (ts + 1) / 2);  // complex elements per frame per buffer
+    const size_t per_frame_bytes = 2 * per_frame_cplx * 2 * es;   // two ping-pong buffers
+    size_t ft = (110 * 1024) / per_frame_bytes;
+    if (ft < 2) ft = (200 * 1024) / per_frame_bytes;
+    if (ft < 1) backend("n_fft too large for the CUDA plan (one frame exceeds shared memory)");
+    if (ft > 32) ft = 32;
+    pl.FT = static_cast<int>(ft);
+    pl.frame_stride = static_cast<int>(per_frame_cplx >= fs ? per_frame_cplx : fs);
+    pl.tile_stride = static_cast<int>(ts);
+    pl.buf_elems = static_cast<int>(per_frame_cplx * ft);
+    pl.frame_stride = static_cast<int>(fs);
+    pl.smem_bytes = per_frame_bytes * ft;
+}
+
+// Resolve the device and upload the per-plan tables once. Host-only queries (shape, axes, window, filterbank) work
+// without a GPU; anything that computes does not.
+void ensure_device(sgx_plan &pl) {
+    if (pl.on_device) return;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        backend("no CUDA device available (this library has no CPU fallback)");
+    }
+    int dev = pl.device;
+    if (dev < 0) ck(cudaGetDevice(&dev), "cudaGetDevice");
+    if (dev >= ndev) invalid("device ordinal out of range");
+    pl.device = dev;
+    DeviceGuard g(dev);
+    pl.d_window = upload(pl.tab.window, pl.f64);
+    pl.d_tw = upload(twiddle_table(static_cast<size_t>(pl.L), static_cast<size_t>(pl.L)), pl.f64);
+    if (pl.even) pl.d_post = upload(twiddle_table(pl.desc.n_fft, static_cast<size_t>(pl.L) + 1), pl.f64);
+    pl.d_row_ptr = upload_int(pl.tab.row_ptr);
+    pl.d_col = upload_int(pl.tab.col);
+    pl.d_val = upload(pl.tab.val, pl.f64);
+    pl.d_dense = upload(pl.tab.dense, pl.f64);
+    pl.d_dct = upload(pl.tab.dct, pl.f64);
+    pl.d_lifter = upload(pl.tab.lifter, pl.f64);
+    pl.on_device = true;
+}
+
+void fill_params(const sgx_plan &pl, KParams &p) {
+    std::memset(&p, 0, sizeof p);
+    const sgx_plan_desc &d = pl.desc;
+    p.n_fft = static_cast<int>(d.n_fft);
+    p.hop = static_cast<int>(d.hop_size);
+    p.pad = d.centre ? static_cast<int>(d.n_fft / 2) : 0;
+    p.out_len = static_cast<int>(pl.tab.out_len);
+    p.L = pl.L;
+    p.even = pl.even;
+    p.n_stages = static_cast<int>(pl.radix.size());
+    for (size_t i = 0; i < pl.radix.size(); ++i) p.radix[i] = pl.radix[i];
+    p.window = pl.d_window; p.tw = pl.d_tw; p.post = pl.d_post;
+    p.mapping = d.mapping;
+    p.n_bins = static_cast<int>(pl.tab.n_bins);
+    p.row_ptr = pl.d_row_ptr; p.col = pl.d_col; p.val = pl.d_val; p.dense = pl.d_dense;
+    p.amp = d.amp;
+    p.apply_db = (d.amp == SGX_AMP_DECIBELS && d.has_floor_db) ? 1 : 0;     // quirk F7: Decibels + None = raw power
+    p.eps = d.has_floor_db ? std::pow(10.0, d.floor_db / 10.0) : 0.0;
+    p.output = d.output;
+    p.n_mfcc = static_cast<int>(d.n_mfcc);
+    p.mfcc_row0 = (d.output == SGX_OUT_MFCC && !d.include_c0 && d.n_mfcc > 1) ? 1 : 0;
+    p.dct = pl.d_dct; p.lifter = pl.d_lifter;
+    p.FT = pl.FT; p.buf_elems = pl.buf_elems; p.frame_stride = pl.frame_stride; p.tile_stride = pl.tile_stride;
+}
+
+// run frames [frame_begin, frame_begin+frames_todo) of n_clips device-resident clips
+void run_device(sgx_plan &pl, const void *d_samples, size_t n_clips, size_t n_samples, size_t clip_stride, void *d_out,
+                long long out_row_stride, long long out_clip_stride, long long frame_begin, long long frames_todo,
+                cudaStream_t stream, long long pad_override = -1) {
+    KParams p;
+    fill_params(pl, p);
+    if (pad_override >= 0) p.pad = static_cast<int>(pad_override);
+    p.samples = d_samples;
+    p.n_samples = static_cast<long long>(n_samples);
+    p.clip_stride = static_cast<long long>(clip_stride);
+    p.frame_begin = frame_begin;
+    p.frames_todo = frames_todo;
+    p.out = d_out;
+    p.out_row_stride = out_row_stride;
+    p.out_clip_stride = out_clip_stride;
+    p.out_frame_origin = frame_begin;
+    p.tiles_per_clip = static_cast<int>((frames_todo + p.FT - 1) / p.FT);
+    // the grid is limited to 2^31-1 CTAs: split very large batches
+    const long long max_clips = std::max<long long>(1, 2000000000LL / std::max(1, p.tiles_per_clip));
+    for (size_t c0 = 0; c0 < n_clips; c0 += static_cast<size_t>(max_clips)) {
+        const size_t nc = std::min<size_t>(static_cast<size_t>(max_clips), n_clips - c0);
+        KParams q = p;
+        q.n_clips = static_cast<int>(nc);
+        q.samples = static_cast<const char *>(d_samples) + c0 * clip_stride * pl.esize;
+        q.out = static_cast<char *>(d_out) + c0 * static_cast<size_t>(out_clip_stride) * pl.esize *
+                                                 (pl.desc.output == SGX_OUT_COMPLEX_STFT ? 2 : 1);
+        ck(launch_generic(q, pl.f64, pl.smem_bytes, stream), "kernel launch (r2c_fused_generic)");
+        pl.last_launches += 1;
+    }
+}
+
+void ensure_slot(sgx_plan::Slot &s, size_t in_bytes, size_t out_bytes) {
+    if (!s.s) ck(cudaStreamCreateWithFlags(&s.s, cudaStreamNonBlocking), "cudaStreamCreate");
+    if (s.in_cap < in_bytes) {
+        if (s.d_in) { ck(cudaStreamSynchronize(s.s), "sync"); cudaFree(s.d_in); s.d_in = nullptr; }
+        ck(cudaMalloc(&s.d_in, in_bytes), "cudaMalloc(staging in)");
+        s.in_cap = in_bytes;
+    }
+    if (s.out_cap < out_bytes) {
+        if (s.d_out) { ck(cudaStreamSynchronize(s.s), "sync"); cudaFree(s.d_out); s.d_out = nullptr; }
+        ck(cudaMalloc(&s.d_out, out_bytes), "cudaMalloc(staging out)");
+        s.out_cap = out_bytes;
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ C ABI
+extern "C" {
+
+const char *sgx_last_error_message(void) { return g_err_msg.c_str(); }
+void sgx_last_dimension_mismatch(size_t *expected, size_t *got) {
+    if (expected) *expected = g_exp;
+    if (got) *got = g_got;
+}
+const char *sgx_version(void) { return "sgx_b200 0.1.0 sm_100a"; }
+
+sgx_status sgx_plan_create(const sgx_plan_desc *desc, sgx_plan **out_plan) {
+    return guarded([&] {
+        if (!desc || !out_plan) invalid("null argument");
+        *out_plan = nullptr;
+        validate_desc(*desc);
+        std::unique_ptr<sgx_plan> pl(new sgx_plan());
+        pl->desc = *desc;
+        if (desc->window == SGX_WIN_CUSTOM) {
+            pl->custom.assign(desc->custom_window, desc->custom_window + desc->custom_window_len);
+            pl->desc.custom_window = pl->custom.data();
+        } else {
+            pl->desc.custom_window = nullptr;
+            pl->desc.custom_window_len = 0;
+        }
+        pl->f64 = desc->dtype == SGX_F64;
+        pl->esize = pl->f64 ? 8 : 4;
+        build_tables(pl->desc, pl->tab);
+        pl->rows = desc->output == SGX_OUT_COMPLEX_STFT ? pl->tab.out_len
+                 : desc->output == SGX_OUT_MFCC ? desc->n_mfcc - ((!desc->include_c0 && desc->n_mfcc > 1) ? 1 : 0)
+                                                : pl->tab.n_bins;
+        factorise(*pl);
+        choose_generic_geometry(*pl);
+
+        pl->device = desc->device;   // device tables are uploaded on first use (ensure_device)
+        *out_plan = pl.release();
+    });
+}
+
+sgx_status sgx_plan_destroy(sgx_plan *plan) {
+    return guarded([&] { delete plan; });
+}
+
+sgx_status sgx_plan_output_shape(const sgx_plan *plan, size_t n_samples, size_t *n_rows, size_t *n_frames) {
+    return guarded([&] {
+        if (!plan) invalid("null plan");
+        if (n_samples == 0) invalid("signal length must be non-zero");
+        if (n_rows) *n_rows = plan->rows;
+        if (n_frames) *n_frames = frame_count(n_samples, plan->desc.n_fft, plan->desc.hop_size, plan->desc.centre != 0);
+    });
+}
+
+sgx_status sgx_plan_axes(const sgx_plan *plan, size_t n_frames, double *freqs, double *times) {
+    return guarded([&] {
+        if (!plan) invalid("null plan");
+        if (freqs) std::memcpy(freqs, plan->tab.freq_axis.data(), sizeof(double) * plan->tab.freq_axis.size());
+        if (times) {
+            // frame_period_seconds = hop / sr (:4268-4271); times[i] = i * dt (:2128-2139)
+            const double dt = static_cast<double>(plan->desc.hop_size) / plan->desc.sample_rate_hz;
+            for (size_t i = 0; i < n_frames; ++i) times[i] = static_cast<double>(i) * dt;
+        }
+    });
+}
+
+sgx_status sgx_plan_window(const sgx_plan *plan, void *out_host) {
+    return guarded([&] {
+        if (!plan || !out_host) invalid("null argument");
+        const size_t n = plan->desc.n_fft;
+        if (plan->f64) for (size_t i = 0; i < n; ++i) static_cast<double *>(out_host)[i] = plan->tab.window[i];
+        else for (size_t i = 0; i < n; ++i) static_cast<float *>(out_host)[i] = static_cast<float>(plan->tab.window[i]);
+    });
+}
+
+sgx_status sgx_plan_filterbank(const sgx_plan *plan, double *dense_out, size_t *nnz) {
+    return guarded([&] {
+        if (!plan) invalid("null plan");
+        const HostTables &t = plan->tab;
+        const size_t nb = t.n_bins, ol = t.out_len;
+        if (nnz) *nnz = plan->desc.mapping == SGX_MAP_ERB ? nb * ol : plan->desc.mapping == SGX_MAP_LINEAR ? ol : t.val.size();
+        if (!dense_out) return;
+        std::fill(dense_out, dense_out + nb * ol, 0.0);
+        if (plan->desc.mapping == SGX_MAP_LINEAR) {
+            for (size_t r = 0; r < nb; ++r) dense_out[r * ol + r] = 1.0;
+        } else if (plan->desc.mapping == SGX_MAP_ERB) {
+            std::memcpy(dense_out, t.dense.data(), sizeof(double) * nb * ol);
+        } else {
+            for (size_t r = 0; r < nb; ++r)
+                for (int e = t.row_ptr[r]; e < t.row_ptr[r + 1]; ++e) dense_out[r * ol + t.col[e]] = t.val[e];
+        }
+    });
+}
+
+const char *sgx_plan_kernel_name(const sgx_plan *plan) { return plan ? plan->kernel_name.c_str() : ""; }
+size_t sgx_plan_last_launch_count(const sgx_plan *plan) { return plan ? plan->last_launches : 0; }
+sgx_status sgx_plan_force_generic(sgx_plan *plan, int force) {
+    return guarded([&] {
+        if (!plan) invalid("null plan");
+        plan->force_generic = force != 0;
+    });
+}
+
+sgx_status sgx_plan_compute_batch(sgx_plan *plan, const void *samples, size_t n_clips, size_t n_samples,
+                                  size_t clip_stride, void *out, size_t out_rows, size_t out_cols,
+                                  size_t out_clip_stride, void *cuda_stream) {
+    return guarded([&] {
+        if (!plan || !samples || !out) invalid("null argument");
+        if (n_samples == 0) invalid("samples must be non-empty");                 // NonEmptySlice
+        if (n_clips == 0) invalid("n_clips must be non-zero");
+        if (clip_stride < n_samples) invalid("clip_stride must be >= n_samples");
+        sgx_plan &pl = *plan;
+        const size_t n_frames = frame_count(n_samples, pl.desc.n_fft, pl.desc.hop_size, pl.desc.centre != 0);
+        if (out_rows != pl.rows) mismatch(pl.rows, out_rows);                     // rows first (:423-428)
+        if (out_cols != n_frames) mismatch(n_frames, out_cols);                   // then columns (:429-434)
+        if (out_clip_stride == 0) out_clip_stride = out_rows * out_cols;
+        if (out_clip_stride < out_rows * out_cols) invalid("out_clip_stride must be >= out_rows*out_cols");
+        ensure_device(pl);
+        DeviceGuard g(pl.device);
+        pl.last_launches = 0;
+        const size_t oes = pl.esize * (pl.desc.output == SGX_OUT_COMPLEX_STFT ? 2 : 1);
+        const PtrKind ki = ptr_kind(samples), ko = ptr_kind(out);
+        if (ki != ko) invalid("samples and out must both be host pointers or both be device pointers");
+        if (ki == PtrKind::Device) {
+            run_device(pl, samples, n_clips, n_samples, clip_stride, out, static_cast<long long>(n_frames),
+                       static_cast<long long>(out_clip_stride), 0, static_cast<long long>(n_frames),
+                       static_cast<cudaStream_t>(cuda_stream));
+            return;
+        }
+        // host pointers: chunk the clips, pipeline H2D / compute / D2H over kStagingSlots private streams
+        const size_t in_clip_bytes = n_samples * pl.esize;
+        const size_t out_clip_bytes = out_rows * out_cols * oes;
+        size_t chunk = std::max<size_t>(1, (size_t(64) << 20) / std::max(in_clip_bytes, out_clip_bytes));
+        chunk = std::min(chunk, n_clips);
+        int si = 0;
+        for (size_t c0 = 0; c0 < n_clips; c0 += chunk, si = (si + 1) % kStagingSlots) {
+            const size_t nc = std::min(chunk, n_clips - c0);
+            sgx_plan::Slot &s = pl.slot[si];
+            ensure_slot(s, chunk * in_clip_bytes, chunk * out_clip_bytes);
+            ck(cudaMemcpy2DAsync(s.d_in, in_clip_bytes, static_cast<const char *>(samples) + c0 * clip_stride * pl.esize,
+                                 clip_stride * pl.esize, in_clip_bytes, nc, cudaMemcpyHostToDevice, s.s), "H2D copy");
+            const size_t saved = pl.last_launches;
+            run_device(pl, s.d_in, nc, n_samples, n_samples, s.d_out, static_cast<long long>(n_frames),
+                       static_cast<long long>(out_rows * out_cols), 0, static_cast<long long>(n_frames), s.s);
+            (void)saved;
+            ck(cudaMemcpy2DAsync(static_cast<char *>(out) + c0 * out_clip_stride * oes, out_clip_stride * oes, s.d_out,
+                                 out_clip_bytes, out_clip_bytes, nc, cudaMemcpyDeviceToHost, s.s), "D2H copy");
+        }
+        for (auto &s : pl.slot) if (s.s) ck(cudaStreamSynchronize(s.s), "cudaStreamSynchronize");
+    });
+}
+
+sgx_status sgx_plan_compute_frame(sgx_plan *plan, const void *samples, size_t n_samples, size_t frame_idx, void *out,
+                                  void *cuda_stream) {
+    return guarded([&] {
+        if (!plan || !samples || !out) invalid("null argument");
+        if (n_samples == 0) invalid("samples must be non-empty");
+        sgx_plan &pl = *plan;
+        if (frame_idx > (size_t(1) << 62) / pl.desc.hop_size) invalid("frame index overflow");     // checked_mul (:1262-1264)
+        ensure_device(pl);
+        DeviceGuard g(pl.device);
+        pl.last_launches = 0;
+        const size_t oes = pl.esize * (pl.desc.output == SGX_OUT_COMPLEX_STFT ? 2 : 1);
+        const PtrKind ki = ptr_kind(samples), ko = ptr_kind(out);
+        if (ki != ko) invalid("samples and out must both be host pointers or both be device pointers");
+        if (ki == PtrKind::Device) {
+            run_device(pl, samples, 1, n_samples, n_samples, out, 1, static_cast<long long>(pl.rows),
+                       static_cast<long long>(frame_idx), 1, static_cast<cudaStream_t>(cuda_stream));
+            return;
+        }
+        // host pointers: stage only the span [lo, hi) of samples this frame touches and shift the padding so that
+        // kernel index (0*hop - pad' + i) addresses the staged span; everything outside it is zero padding anyway.
+        sgx_plan::Slot &s = pl.slot[0];
+        const long long pad = pl.desc.centre ? static_cast<long long>(pl.desc.n_fft / 2) : 0;
+        const long long lo_raw = static_cast<long long>(frame_idx * pl.desc.hop_size) - pad;
+        const long long lo = std::min<long long>(std::max<long long>(lo_raw, 0), static_cast<long long>(n_samples));
+        const long long hi = std::min<long long>(std::max<long long>(lo_raw + static_cast<long long>(pl.desc.n_fft), lo),
+                                                 static_cast<long long>(n_samples));
+        const size_t span = static_cast<size_t>(hi - lo);
+        ensure_slot(s, std::max<size_t>(span, 1) * pl.esize, pl.rows * oes);
+        if (span) ck(cudaMemcpyAsync(s.d_in, static_cast<const char *>(samples) + static_cast<size_t>(lo) * pl.esize,
+                                     span * pl.esize, cudaMemcpyHostToDevice, s.s), "H2D copy");
+        run_device(pl, s.d_in, 1, span, std::max<size_t>(span, 1), s.d_out, 1, static_cast<long long>(pl.rows), 0, 1, s.s,
+                   /*pad_override=*/lo - lo_raw);
+        ck(cudaMemcpyAsync(out, s.d_out, pl.rows * oes, cudaMemcpyDeviceToHost, s.s), "D2H copy");
+        ck(cudaStreamSynchronize(s.s), "cudaStreamSynchronize");
+    });
+}
+
+sgx_status sgx_mfcc_from_log_mel(sgx_dtype dtype, const void *log_mel, size_t n_clips, size_t n_mels, size_t n_frames,
+                                 size_t n_mfcc, int include_c0, size_t lifter, void *out, int device, void *cuda_stream) {
+    return guarded([&] {
+        if (!log_mel || !out) invalid("null argument");
+        if (dtype != SGX_F32 && dtype != SGX_F64) invalid("dtype must be f32 or f64");
+        if (n_mfcc == 0) invalid("n_mfcc must be non-zero");
+        if (n_mfcc > n_mels) invalid("n_mfcc must be <= n_mels");                 // src/mfcc.rs:231-233
+        if (n_clips == 0 || n_frames == 0) invalid("empty log-mel spectrogram");
+        const bool f64 = dtype == SGX_F64;
+        const size_t es = f64 ? 8 : 4;
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+            cudaGetLastError();
+            backend("no CUDA device available (this library has no CPU fallback)");
+        }
+        int dev = device;
+        if (dev < 0) ck(cudaGetDevice(&dev), "cudaGetDevice");
+        DeviceGuard g(dev);
+        std::vector<double> basis, lift;
+        build_dct(n_mfcc, n_mels, lifter, basis, lift);
+        const int row0 = (!include_c0 && n_mfcc > 1) ? 1 : 0;
+        const size_t rows = n_mfcc - row0;
+        void *d_dct = upload(basis, f64), *d_lift = upload(lift, f64);
+        const PtrKind ki = ptr_kind(log_mel), ko = ptr_kind(out);
+        cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+        auto cleanup = [&] { cudaFree(d_dct); cudaFree(d_lift); };
+        try {
+            if (ki != ko) invalid("log_mel and out must both be host pointers or both be device pointers");
+            if (ki == PtrKind::Device) {
+                ck(launch_mfcc(f64, log_mel, out, static_cast<long long>(n_clips), static_cast<int>(n_mels),
+                               static_cast<long long>(n_frames), static_cast<int>(n_mfcc), row0, d_dct, d_lift, st), "kernel launch (dct2_lifter)");
+                ck(cudaStreamSynchronize(st), "cudaStreamSynchronize");   // tables are freed below
+            } else {
+                void *d_in = nullptr, *d_out = nullptr;
+                const size_t ib = n_clips * n_mels * n_frames * es, ob = n_clips * rows * n_frames * es;
+                ck(cudaMalloc(&d_in, ib), "cudaMalloc");
+                if (cudaMalloc(&d_out, ob) != cudaSuccess) { cudaFree(d_in); backend("cudaMalloc failed"); }
+                cudaError_t e = cudaMemcpyAsync(d_in, log_mel, ib, cudaMemcpyHostToDevice, st);
+                if (e == cudaSuccess) e = launch_mfcc(f64, d_in, d_out, static_cast<long long>(n_clips), static_cast<int>(n_mels),
+                                                      static_cast<long long>(n_frames), static_cast<int>(n_mfcc), row0, d_dct, d_lift, st);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, ob, cudaMemcpyDeviceToHost, st);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+                cudaFree(d_in); cudaFree(d_out);
+                ck(e, "mfcc_from_log_mel");
+            }
+        } catch (...) { cleanup(); throw; }
+        cleanup();
+    });
+}
+
+sgx_status sgx_rfft(sgx_dtype dtype, const void *samples, size_t n_in, size_t n_fft, void *out, int device, void *cuda_stream) {
+    sgx_plan *pl = nullptr;
+    sgx_status st = guarded([&] {
+        if (!samples || !out) invalid("null argument");
+        if (n_fft == 0) invalid("n_fft must be set");
+        if (n_in == 0) invalid("samples must be non-empty");
+        if (n_in > n_fft) {                                                        // :4494-4500
+            char buf[128];
+            std::snprintf(buf, sizeof buf, "Input length (%zu) exceeds FFT size (%zu)", n_in, n_fft);
+            invalid(buf);
+        }
+    });
+    if (st != SGX_OK) return st;
+    sgx_plan_desc d;
+    std::memset(&d, 0, sizeof d);
+    d.dtype = dtype; d.n_fft = n_fft; d.hop_size = n_fft; d.centre = 0; d.window = SGX_WIN_RECTANGULAR;
+    d.sample_rate_hz = 1.0; d.mapping = SGX_MAP_LINEAR; d.amp = SGX_AMP_POWER; d.output = SGX_OUT_COMPLEX_STFT; d.device = device;
+    st = sgx_plan_create(&d, &pl);
+    if (st != SGX_OK) return st;
+    st = sgx_plan_compute_frame(pl, samples, n_in, 0, out, cuda_stream);
+    if (st == SGX_OK && ptr_kind(out) == PtrKind::Device) cudaStreamSynchronize(static_cast<cudaStream_t>(cuda_stream));
+    sgx_plan_destroy(pl);
+    return st;
+}
+
+}  // extern "C"
