@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py -- log-mel frames/s of the fused STFT -> |X|^2 -> mel -> dB path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--workload whisper|music|mfcc|multichannel] [--impl reference]
+
+One "step" = one pass of the hot path over one batch of synthetic clips. The default workload is BASELINE.json
+configs[1] (Whisper-style log-mel: 1024 clips x 30 s @16 kHz, n_fft 400, hop 160, 128 mels, f32); each rank owns a
+full batch (weak scaling, clips shard with no data-path collective -- SURVEY.md section 8e).
+
+Printed JSON (rank 0, one line):
+  value      whole-job frames/s with inputs resident in HBM (CUDA events, max over ranks)
+  e2e        same metric through the C ABI with pinned HOST buffers (H2D + kernel + D2H inside the timed region)
+  roofline   algorithmic HBM bytes per launch / average launch duration vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the oracle's restatement of the reference algorithm on the host cores (bounded sample), rank 0, N=1
+  clocks     SM clock / throttle reasons sampled during the timed region
+
+--impl reference times the reference's CPU algorithm (the oracle port: the Rust crate cannot be built here -- no
+cargo, un-vendored realfft/rustfft) with one plan per host thread on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (n_clips, seconds, sr, n_fft, hop, dtype, kind)
+    "whisper": dict(n_clips=1024, n_samples=480000, sr=16000.0, n_fft=400, hop=160, dtype="float32", kind="mel_db",
+                    label="configs[1] whisper log-mel: 1024 clips x 30 s @16 kHz, n_fft=400 hop=160 128 mels dB f32"),
+    "music": dict(n_clips=512, n_samples=661500, sr=22050.0, n_fft=2048, hop=512, dtype="float32", kind="mel_db",
+                  label="configs[2] music mel-dB per-GPU shard: 512 clips x 30 s @22.05 kHz, n_fft=2048 hop=512 128 mels dB f32"),
+    "mfcc": dict(n_clips=1024, n_samples=160000, sr=16000.0, n_fft=400, hop=160, dtype="float32", kind="mfcc",
+                 label="configs[3] MFCC per-GPU shard: 1024 clips x 10 s @16 kHz, n_fft=400 hop=160 128 mels -> 40 MFCC f32"),
+    "multichannel": dict(n_clips=64, n_samples=2880000, sr=48000.0, n_fft=4096, hop=1024, dtype="float64", kind="linear_mag",
+                         label="configs[4] multichannel STFT magnitude: 64 ch x 60 s @48 kHz, n_fft=4096 hop=1024 f64"),
+}
+
+
+def frames_of(w):
+    pad = w["n_fft"] // 2
+    return (w["n_samples"] + 2 * pad - w["n_fft"]) // w["hop"] + 1
+
+
+def out_rows(w):
+    return {"mel_db": 128, "mfcc": 40, "linear_mag": w["n_fft"] // 2 + 1}[w["kind"]]
+
+
+def algorithmic_bytes(w):
+    """read every input sample once + write every output element once."""
+    es = 4 if w["dtype"] == "float32" else 8
+    return w["n_clips"] * (w["n_samples"] * es + out_rows(w) * frames_of(w) * es)
+
+
+def make_plan(w, device=None):
+    import spectrograms_b200 as sg
+    params = sg.SpectrogramParams(sg.StftParams(w["n_fft"], w["hop"], sg.WindowType.hanning(), True), w["sr"])
+    if w["kind"] == "mel_db":
+        return sg.SpectrogramPlanner(device).mel_plan(params, sg.MelParams(128, 0.0, w["sr"] / 2), sg.LogParams(-80.0), "db", w["dtype"])
+    if w["kind"] == "mfcc":
+        return sg.MfccPlan(params.stft, w["sr"], 128, sg.MfccParams(40), w["dtype"], device)
+    return sg.SpectrogramPlanner(device).linear_plan(params, None, "magnitude", w["dtype"])
+
+
+def oracle_desc(w):
+    import oracle
+    kw = dict(dtype="f32" if w["dtype"] == "float32" else "f64", n_fft=w["n_fft"], hop=w["hop"], sample_rate=w["sr"])
+    if w["kind"] in ("mel_db", "mfcc"):
+        kw.update(mapping="mel", n_bands=128, f_min=0.0, f_max=w["sr"] / 2, amp="db", floor_db=-80.0)
+    else:
+        kw.update(amp="magnitude")
+    return oracle.Desc(**kw)
+
+
+class ClockSampler:
+    """Samples SM clock + throttle reasons during the timed region (pynvml; nvidia-smi as a fallback)."""
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run_nvml(self):
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+                 0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+        while not self._stop.is_set():
+            self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+            try:
+                r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+            except Exception:
+                r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            for bit, nm in names.items():
+                if r & bit:
+                    self.reasons.add(nm)
+            time.sleep(0.002)
+
+    def _run(self):
+        try:
+            self._run_nvml()
+        except Exception:
+            import subprocess
+            while not self._stop.is_set():
+                try:
+                    o = subprocess.run(["nvidia-smi", f"--id={self.index}", "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+                                        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
+                                        "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                    self.samples.append(int(o[0])); self.max_mhz = int(o[1])
+                    for nm, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), o[2:]):
+                        if v.strip().lower().startswith("active"):
+                            self.reasons.add(nm)
+                except Exception:
+                    break
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=10)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def cpu_baseline(w, sample_clips, threads, faithful=True, reps=2):
+    """The oracle's one-plan-per-thread batch driver on a bounded sample of the workload; best of `reps`."""
+    import oracle
+    d = oracle_desc(w)
+    rng = np.random.default_rng(0)
+    clips = rng.standard_normal((sample_clips, w["n_samples"])).astype(np.float32 if w["dtype"] == "float32" else np.float64)
+    mf = dict(n_mfcc=40, include_c0=True, lifter=22, faithful=faithful) if w["kind"] == "mfcc" else None
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        oracle.compute_batch(d, clips, threads, mfcc=mf)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return sample_clips * frames_of(w) / best, best
+
+
+def run_reference(args, w, rank, world):
+    """--impl reference: the reference's CPU algorithm (oracle port) with all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    import oracle
+    cores = os.cpu_count() or 1
+    sample = max(cores, min(w["n_clips"], args.ref_clips))
+    d = oracle_desc(w)
+    clips = np.random.default_rng(0).standard_normal((sample, w["n_samples"])).astype(np.float32 if w["dtype"] == "float32" else np.float64)
+    mf = dict(n_mfcc=40, include_c0=True, lifter=22, faithful=True) if w["kind"] == "mfcc" else None
+    for _ in range(args.warmup):
+        oracle.compute_batch(d, clips, cores, mfcc=mf)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle.compute_batch(d, clips, cores, mfcc=mf)
+    dt = time.perf_counter() - t0
+    value = args.steps * sample * frames_of(w) / dt
+    line = {
+        "impl": "reference", "metric": "log-mel frames/sec", "value": value, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32" if w["dtype"] == "float32" else "f64", "data": "synthetic (seeded white noise)",
+        "config": {"workload": w["label"], "sample": f"{sample} clips per step"},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} of {w['n_clips']} clips per step, one plan per thread (oracle/oracle.c restatement of the reference; "
+                                   "the Rust crate cannot be built here: no cargo, un-vendored realfft/rustfft)"},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="whisper", choices=sorted(WORKLOADS))
+    ap.add_argument("--clips", type=int, default=0, help="override clips per GPU (0 = the workload's size)")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer end-to-end leg (0 = min(steps, 10))")
+    ap.add_argument("--cpu-clips", type=int, default=256, help="bounded CPU-baseline sample (clips)")
+    ap.add_argument("--ref-clips", type=int, default=64, help="--impl reference: clips per step")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--generic", action="store_true", help="force the generic kernel family")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3        # timing rule: W >= 3
+
+    w = dict(WORKLOADS[args.workload])
+    if args.clips:
+        w["n_clips"] = args.clips
+        w["label"] += f" [clips overridden to {args.clips}]"
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, w, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    tdt = torch.float32 if w["dtype"] == "float32" else torch.float64
+    plan = make_plan(w, local_rank)
+    if args.generic:
+        plan.force_generic(True)
+    n_frames = frames_of(w)
+    rows = out_rows(w)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    clips = torch.randn((w["n_clips"], w["n_samples"]), generator=g, device=dev, dtype=tdt)   # resident in HBM
+    out = torch.empty((w["n_clips"], rows, n_frames), device=dev, dtype=tdt)
+    frames_per_step = w["n_clips"] * n_frames
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        plan.compute_batch(clips, out)
+    launches_per_step = plan.last_launch_count()
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    with ClockSampler(local_rank) as cs:
+        barrier()
+        ev[0].record()
+        for i in range(args.steps):
+            plan.compute_batch(clips, out)
+            ev[i + 1].record()
+        barrier()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    kernel_ms = float(np.mean(per_launch_ms)) / max(1, launches_per_step)
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = world * frames_per_step * args.steps / (total_ms_max * 1e-3)
+
+    # ---- end to end through the C ABI with pinned host buffers (H2D + kernel + D2H inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        es = 4 if w["dtype"] == "float32" else 8
+        h_in = torch.empty((w["n_clips"], w["n_samples"]), dtype=tdt, pin_memory=True)
+        h_in.copy_(clips)
+        h_out = torch.empty((w["n_clips"], rows, n_frames), dtype=tdt, pin_memory=True)
+        hin, hout = h_in.numpy(), h_out.numpy()
+        ksteps = args.e2e_steps or min(args.steps, 10)
+        for _ in range(2):
+            plan.compute_batch(hin, hout)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ksteps):
+            plan.compute_batch(hin, hout)           # returns after the results are in host memory
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        te = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * frames_per_step * ksteps / float(te.item()), "unit": "frames/s",
+               "h2d_bytes_per_step": w["n_clips"] * w["n_samples"] * es, "d2h_bytes_per_step": w["n_clips"] * rows * n_frames * es,
+               "steps": ksteps, "ms_per_step": 1e3 * float(te.item()) / ksteps,
+               "check": "host result equals device result: %s" % bool(torch.equal(h_out[:4].to(dev), out[:4]))}
+        del h_in, h_out
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant (only) kernel
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    alg_bytes = algorithmic_bytes(w)
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(args.workload, {}).get(plan.kernel_name())
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "kernel": plan.kernel_name(), "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src}
+
+    cpu = None
+    if not args.no_cpu and world == 1:
+        cores = os.cpu_count() or 1
+        sample = min(w["n_clips"], args.cpu_clips)
+        v, secs = cpu_baseline(w, sample, cores)
+        cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
+               "sample": f"{sample} of {w['n_clips']} clips, one plan per thread, best of 2 ({secs:.2f} s wall)"}
+
+    line = {
+        "metric": "log-mel frames/sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if w["dtype"] == "float32" else "f64", "data": "synthetic (seeded white noise, generated on device)",
+        "config": {"workload": w["label"], "clips_per_gpu": w["n_clips"], "frames_per_clip": n_frames, "sharding": f"clips x{world}, no collective",
+                   "l2": f"inputs per step {w['n_clips'] * w['n_samples'] * (4 if w['dtype'] == 'float32' else 8) / 1e9:.2f} GB > 126 MB L2 (no flush needed)"},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+        "clocks": cs.summary(),
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
