@@ -87,4 +87,50 @@ __device__ __forceinline__ void epilogue_complex(const KParams &p, const typenam
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Variant for kernel families whose tile is "frames fastest": P[k * 32 + f], exactly 32 frames per tile, lane = frame.
+// One warp owns one output row at a time, so every filterbank weight / column index / DCT coefficient is warp-uniform
+// and every store is a 128-byte run of one output row. scratch: [row * 32 + f], >= n_bins * 32 elements (MFCC only).
+template <typename T>
+__device__ __forceinline__ void epilogue_lane_frames(const KParams &p, const T *__restrict__ P, T *__restrict__ scratch,
+                                                     int clip, long long f0, int nf) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const T eps = static_cast<T>(p.eps);
+    T *out = static_cast<T *>(p.out) + static_cast<long long>(clip) * p.out_clip_stride + (f0 - p.out_frame_origin) + lane;
+    const bool to_mfcc = (p.output == SGX_OUT_MFCC);
+    const bool live = lane < nf;
+    const T *pl = P + lane;
+    for (int row = warp; row < p.n_bins; row += nwarps) {
+        T acc;
+        if (p.mapping == SGX_MAP_LINEAR) {
+            acc = pl[row * 32];
+        } else if (p.mapping == SGX_MAP_ERB) {
+            const T *w = static_cast<const T *>(p.dense) + static_cast<long long>(row) * p.out_len;
+            acc = T(0);
+            for (int k = 0; k < p.out_len; ++k) acc = t_add_rn(acc, t_mul_rn(__ldg(w + k), pl[k * 32]));
+        } else {
+            const T *val = static_cast<const T *>(p.val);
+            const int e0 = __ldg(p.row_ptr + row), e1 = __ldg(p.row_ptr + row + 1);
+            acc = T(0);
+            for (int e = e0; e < e1; ++e) acc = t_add_rn(acc, t_mul_rn(__ldg(val + e), pl[__ldg(p.col + e) * 32]));
+        }
+        acc = amp_scale<T>(acc, p.amp, p.apply_db, eps);
+        if (to_mfcc) scratch[row * 32 + lane] = acc;
+        else if (live) out[static_cast<long long>(row) * p.out_row_stride] = acc;
+    }
+    if (!to_mfcc) return;
+    __syncthreads();
+    const T *dct = static_cast<const T *>(p.dct);
+    const T *lift = static_cast<const T *>(p.lifter);
+    const int rows = p.n_mfcc - p.mfcc_row0;
+    const T *ml = scratch + lane;
+    for (int r = warp; r < rows; r += nwarps) {
+        const int c = r + p.mfcc_row0;
+        const T *b = dct + static_cast<long long>(c) * p.n_bins;
+        T acc = T(0);
+        for (int i = 0; i < p.n_bins; ++i) acc = t_fma(ml[i * 32], __ldg(b + i), acc);
+        if (live) out[static_cast<long long>(r) * p.out_row_stride] = acc * __ldg(lift + c);
+    }
+}
+
 }  // namespace sgx

@@ -1,0 +1,150 @@
+// fft400_core.cuh -- register-level core of the n_fft = 400 / hop = 160 f32 kernel family ("r2c_fused_n400").
+//
+// Real-input DFT of N = 400 = 20 x 20 in two register passes with ONE shared-memory exchange and no separate
+// real-FFT post pass:
+//
+//   n = 20*n1 + n2,  k = k1 + 20*k2
+//   pass 1 (over n1, for each n2):  Y[k1][n2] = sum_n1 x[20 n1 + n2] W20^(n1 k1)          real input -> only k1 = 0..10
+//                                   two columns n2 = 2t, 2t+1 share one complex 20-point DFT (2-for-1 inside one frame,
+//                                   so no cross-frame mixing of rounding noise)
+//   pass 2 (over n2, for each k1):  X[k1 + 20 k2] = sum_n2 (Y[k1][n2] W400^(n2 k1)) W20^(n2 k2),   k1 = 0..10
+//                                   outputs k2 >= 10 are the conjugates of bins 400 - k: every output is a wanted bin,
+//                                   so bins 0..200 come out of 11 butterflies with nothing left to untangle.
+//
+// The 20-point DFT is a Good-Thomas 4 x 5 prime-factor butterfly: no internal twiddles, 224 flops-ish instructions,
+// pure register renaming. Everything here is __host__ __device__ so tests/test_fft400_core.py can run the exact task
+// functions on the CPU (the build container has no GPU) against the oracle before a kernel ever launches.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#ifndef SGX_HD
+#define SGX_HD __host__ __device__ __forceinline__
+#endif
+
+namespace sgx {
+namespace f400 {
+
+constexpr int kN = 400, kHop = 160, kBins = 201;
+constexpr int kFT = 32;                 // frames per tile = lanes of a warp
+constexpr int kWarps = 11;              // pass 1 uses 10 (t = 0..9), pass 2 uses 11 (k1 = 0..10)
+constexpr int kThreads = kWarps * 32;
+
+// shared-memory layouts (in 4-byte words)
+//   signal tile : sample u of the tile (u = 0 <-> sample f0*160 - pad) lives at u + 2*(u/160). The 2-word pad per hop
+//                 makes the frame stride 162 == 2 (mod 32): lanes = frames read 8-byte pairs from 16 distinct bank pairs.
+//   Y exchange  : Y[f][k1][n2] complex at 444 f + 40 k1 + 2 n2 ; 444/4 odd -> 16-byte accesses with lanes = frames are
+//                 conflict free both when pass 1 writes and when pass 2 reads.
+//   power tile  : P[bin][f] at 32 bin + f (frames fastest: conflict free for lanes = frames, and it is already the
+//                 (rows, frames) orientation of the output).
+constexpr int kSigBlocks = 34;                         // ceil((31*160 + 400) / 160)
+constexpr int kSigBlockStride = 162;
+constexpr int kSigWords = kSigBlocks * kSigBlockStride;   // 5508
+constexpr int kTileSamples = (kFT - 1) * kHop + kN;       // 5360
+constexpr int kYFrameStride = 444;
+constexpr int kYWords = kFT * kYFrameStride;              // 14208
+constexpr int kPWords = kBins * kFT;                      // 6432
+
+// per-plan constants, passed by value as a kernel parameter (constant bank; indices are warp-uniform)
+struct Consts {
+    float win[kN];          // window cast to f32 (make_window, src/spectrogram.rs:2232)
+    float2 tw2[11][20];     // s(k1) * W400^(n2 k1), s = 1 for k1 in {0, 10}, 0.5 otherwise (folds the 2-for-1 halving)
+};
+
+SGX_HD int sig_word(int u) { return u + 2 * (u / kHop); }
+
+SGX_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+SGX_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+
+// in-place 4-point DFT (forward): (a,b,c,d) <- (X0,X1,X2,X3)
+SGX_HD void dft4(float2 &a, float2 &b, float2 &c, float2 &d) {
+    const float2 t0 = cadd(a, c), t1 = csub(a, c), t2 = cadd(b, d), t3 = csub(b, d);
+    a = cadd(t0, t2);
+    c = csub(t0, t2);
+    b = make_float2(t1.x + t3.y, t1.y - t3.x);
+    d = make_float2(t1.x - t3.y, t1.y + t3.x);
+}
+
+// in-place 5-point DFT (forward): (a0..a4) <- (X0..X4)
+SGX_HD void dft5(float2 &a0, float2 &a1, float2 &a2, float2 &a3, float2 &a4) {
+    constexpr float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;
+    constexpr float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;
+    const float2 p1 = cadd(a1, a4), m1 = csub(a1, a4), p2 = cadd(a2, a3), m2 = csub(a2, a3);
+    const float2 e1 = make_float2(a0.x + c1 * p1.x + c2 * p2.x, a0.y + c1 * p1.y + c2 * p2.y);
+    const float2 e2 = make_float2(a0.x + c2 * p1.x + c1 * p2.x, a0.y + c2 * p1.y + c1 * p2.y);
+    const float2 u1 = make_float2(s1 * m1.x + s2 * m2.x, s1 * m1.y + s2 * m2.y);
+    const float2 u2 = make_float2(s2 * m1.x - s1 * m2.x, s2 * m1.y - s1 * m2.y);
+    a0 = make_float2(a0.x + p1.x + p2.x, a0.y + p1.y + p2.y);
+    a1 = make_float2(e1.x + u1.y, e1.y - u1.x);   // e1 - i u1
+    a4 = make_float2(e1.x - u1.y, e1.y + u1.x);   // e1 + i u1
+    a2 = make_float2(e2.x + u2.y, e2.y - u2.x);   // e2 - i u2
+    a3 = make_float2(e2.x - u2.y, e2.y + u2.x);   // e2 + i u2
+}
+
+// Good-Thomas 20 = 4 x 5: input sample n sits in v[n]; afterwards output bin k sits in v[reg_of_bin(k)].
+SGX_HD constexpr int reg_of_bin(int k) { return (5 * (k % 4) + 4 * (k % 5)) % 20; }
+
+SGX_HD void dft20(float2 (&v)[20]) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a)   // 5-point DFTs over b on n = 5a + 4b (mod 20)
+        dft5(v[(5 * a) % 20], v[(5 * a + 4) % 20], v[(5 * a + 8) % 20], v[(5 * a + 12) % 20], v[(5 * a + 16) % 20]);
+#pragma unroll
+    for (int d = 0; d < 5; ++d)   // 4-point DFTs over a on the same registers
+        dft4(v[(4 * d) % 20], v[(5 + 4 * d) % 20], v[(10 + 4 * d) % 20], v[(15 + 4 * d) % 20]);
+}
+
+// ---- pass 1, one task = (frame f of the tile, column pair t): columns n2 = 2t and 2t+1
+SGX_HD void pass1_task(const float *__restrict__ sig, float *__restrict__ ybuf, const Consts &c, int f, int t) {
+    float2 v[20];
+    const float *s = sig + kSigBlockStride * f + 2 * t;
+#pragma unroll
+    for (int n1 = 0; n1 < 20; ++n1) {
+        const float2 x = *reinterpret_cast<const float2 *>(s + 20 * n1 + 2 * (n1 / 8));
+        const float wa = c.win[20 * n1 + 2 * t], wb = c.win[20 * n1 + 2 * t + 1];
+        v[n1] = make_float2(x.x * wa, x.y * wb);      // sample * window[i] (src/spectrogram.rs:1319)
+    }
+    dft20(v);
+    float *y = ybuf + kYFrameStride * f + 4 * t;      // complex index 2t -> word 4t
+    // k1 = 0 and k1 = 10: both column spectra are real there
+    {
+        const float2 z0 = v[reg_of_bin(0)], z10 = v[reg_of_bin(10)];
+        *reinterpret_cast<float4 *>(y) = make_float4(z0.x, 0.f, z0.y, 0.f);
+        *reinterpret_cast<float4 *>(y + 40 * 10) = make_float4(z10.x, 0.f, z10.y, 0.f);
+    }
+#pragma unroll
+    for (int k1 = 1; k1 < 10; ++k1) {
+        const float2 A = v[reg_of_bin(k1)], B = v[reg_of_bin(20 - k1)];
+        // 2*Ya = A + conj(B) ; 2*Yb = (A - conj(B)) / i   (the 1/2 lives in tw2)
+        *reinterpret_cast<float4 *>(y + 40 * k1) = make_float4(A.x + B.x, A.y - B.y, A.y + B.y, B.x - A.x);
+    }
+}
+
+// ---- pass 2, one task = (frame f, k1): writes |X[bin]|^2 for the bins this butterfly owns
+SGX_HD void pass2_task(const float *__restrict__ ybuf, float *__restrict__ ptile, const Consts &c, int f, int k1) {
+    float2 v[20];
+    const float *y = ybuf + kYFrameStride * f + 40 * k1;
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+        const float4 q = *reinterpret_cast<const float4 *>(y + 4 * j);
+        const float2 w0 = c.tw2[k1][2 * j], w1 = c.tw2[k1][2 * j + 1];
+        v[2 * j] = make_float2(q.x * w0.x - q.y * w0.y, q.x * w0.y + q.y * w0.x);
+        v[2 * j + 1] = make_float2(q.z * w1.x - q.w * w1.y, q.z * w1.y + q.w * w1.x);
+    }
+    dft20(v);
+    float *p = ptile + f;
+#pragma unroll
+    for (int k2 = 0; k2 < 20; ++k2) {
+        const float2 X = v[reg_of_bin(k2)];
+        const float pw = X.x * X.x + X.y * X.y;       // norm_sqr (src/spectrogram.rs:1332-1334)
+        if (k2 < 10) {
+            p[kFT * (k1 + 20 * k2)] = pw;             // bin k1 + 20 k2
+        } else if (k2 == 10) {
+            if (k1 != 10) p[kFT * (200 - k1)] = pw;   // bin 400 - (k1 + 200); k1 = 10 would repeat bin 190
+        } else {
+            if (k1 != 0 && k1 != 10) p[kFT * (400 - k1 - 20 * k2)] = pw;   // k1 = 0 / 10: conjugate duplicates
+        }
+    }
+}
+
+}  // namespace f400
+}  // namespace sgx

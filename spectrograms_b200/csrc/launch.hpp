@@ -11,6 +11,12 @@ namespace sgx {
 // r2c_fused_generic: any n_fft (kernel_generic.cu)
 cudaError_t launch_generic(const KParams &p, bool f64, size_t smem_bytes, cudaStream_t stream);
 
+// r2c_fused_n400: n_fft = 400, hop = 160, f32, any spectrogram / MFCC output (kernel_fast400.cu).
+// p.buf_elems is reused as the "8-byte aligned input" flag; window_f32 is the host copy of the plan window.
+cudaError_t launch_fast400(const KParams &p, const float *window_f32, cudaStream_t stream);
+size_t fast400_smem_bytes();
+int fast400_max_scratch_rows();
+
 // standalone mfcc_from_log_mel (kernel_mfcc.cu): log_mel [n_clips][n_mels][n_frames] -> out [n_clips][rows][n_frames]
 cudaError_t launch_mfcc(bool f64, const void *log_mel, void *out, long long n_clips, int n_mels, long long n_frames,
                         int n_mfcc, int row0, const void *dct, const void *lifter, cudaStream_t stream);

@@ -133,6 +133,8 @@ struct sgx_plan {
     bool on_device = false;
     size_t last_launches = 0;
     std::string kernel_name = "r2c_fused_generic";
+    bool fast400 = false;            // eligible for r2c_fused_n400
+    std::vector<float> window_f32;
     // staging for host-pointer calls
     struct Slot { void *d_in = nullptr; void *d_out = nullptr; size_t in_cap = 0, out_cap = 0; cudaStream_t s = nullptr; } slot[kStagingSlots];
 
@@ -168,6 +170,17 @@ void factorise(sgx_plan &pl) {
     while (rem % 5 == 0) { pl.radix.push_back(5); rem /= 5; }
     if (rem > 1) pl.radix.insert(pl.radix.begin(), static_cast<int>(rem));   // cofactor stage (primes >= 7), evaluated directly
     if (static_cast<int>(pl.radix.size()) > kMaxStages) backend("too many FFT stages");
+}
+
+void select_family(sgx_plan &pl) {
+    const sgx_plan_desc &d = pl.desc;
+    pl.fast400 = !pl.f64 && d.n_fft == 400 && d.hop_size == 160 && d.output != SGX_OUT_COMPLEX_STFT &&
+                 (d.output != SGX_OUT_MFCC || static_cast<int>(pl.tab.n_bins) <= fast400_max_scratch_rows());
+    if (pl.fast400) {
+        pl.window_f32.resize(d.n_fft);
+        for (size_t i = 0; i < d.n_fft; ++i) pl.window_f32[i] = static_cast<float>(pl.tab.window[i]);
+    }
+    pl.kernel_name = pl.fast400 ? "r2c_fused_n400" : "r2c_fused_generic";
 }
 
 void choose_generic_geometry(sgx_plan &pl) {
@@ -258,7 +271,8 @@ void run_device(sgx_plan &pl, const void *d_samples, size_t n_clips, size_t n_sa
     p.out_row_stride = out_row_stride;
     p.out_clip_stride = out_clip_stride;
     p.out_frame_origin = frame_begin;
-    p.tiles_per_clip = static_cast<int>((frames_todo + p.FT - 1) / p.FT);
+    const int tile_frames = (pl.fast400 && !pl.force_generic) ? 32 : p.FT;
+    p.tiles_per_clip = static_cast<int>((frames_todo + tile_frames - 1) / tile_frames);
     // the grid is limited to 2^31-1 CTAs: split very large batches
     const long long max_clips = std::max<long long>(1, 2000000000LL / std::max(1, p.tiles_per_clip));
     for (size_t c0 = 0; c0 < n_clips; c0 += static_cast<size_t>(max_clips)) {
@@ -268,7 +282,13 @@ void run_device(sgx_plan &pl, const void *d_samples, size_t n_clips, size_t n_sa
         q.samples = static_cast<const char *>(d_samples) + c0 * clip_stride * pl.esize;
         q.out = static_cast<char *>(d_out) + c0 * static_cast<size_t>(out_clip_stride) * pl.esize *
                                                  (pl.desc.output == SGX_OUT_COMPLEX_STFT ? 2 : 1);
-        ck(launch_generic(q, pl.f64, pl.smem_bytes, stream), "kernel launch (r2c_fused_generic)");
+        if (pl.fast400 && !pl.force_generic) {
+            // 8-byte vector loads need an 8-byte aligned base and an even clip stride
+            q.buf_elems = (reinterpret_cast<uintptr_t>(q.samples) % 8 == 0 && clip_stride % 2 == 0) ? 1 : 0;
+            ck(launch_fast400(q, pl.window_f32.data(), stream), "kernel launch (r2c_fused_n400)");
+        } else {
+            ck(launch_generic(q, pl.f64, pl.smem_bytes, stream), "kernel launch (r2c_fused_generic)");
+        }
         pl.last_launches += 1;
     }
 }
@@ -321,6 +341,7 @@ sgx_status sgx_plan_create(const sgx_plan_desc *desc, sgx_plan **out_plan) {
                                                 : pl->tab.n_bins;
         factorise(*pl);
         choose_generic_geometry(*pl);
+        select_family(*pl);
 
         pl->device = desc->device;   // device tables are uploaded on first use (ensure_device)
         *out_plan = pl.release();
@@ -380,7 +401,10 @@ sgx_status sgx_plan_filterbank(const sgx_plan *plan, double *dense_out, size_t *
     });
 }
 
-const char *sgx_plan_kernel_name(const sgx_plan *plan) { return plan ? plan->kernel_name.c_str() : ""; }
+const char *sgx_plan_kernel_name(const sgx_plan *plan) {
+    if (!plan) return "";
+    return (plan->force_generic || !plan->fast400) ? "r2c_fused_generic" : plan->kernel_name.c_str();
+}
 size_t sgx_plan_last_launch_count(const sgx_plan *plan) { return plan ? plan->last_launches : 0; }
 sgx_status sgx_plan_force_generic(sgx_plan *plan, int force) {
     return guarded([&] {
