@@ -119,9 +119,9 @@ SGX_HD void pass1_task(const float *__restrict__ sig, float *__restrict__ ybuf, 
     }
 }
 
-// ---- pass 2, one task = (frame f, k1): writes |X[bin]|^2 for the bins this butterfly owns
-SGX_HD void pass2_task(const float *__restrict__ ybuf, float *__restrict__ ptile, const Consts &c, int f, int k1) {
-    float2 v[20];
+// ---- pass 2, one task = (frame f, k1), in two halves so that a barrier can sit between "every Y value has been
+// read" and "the power tile (which may alias the Y buffer) is written".
+SGX_HD void pass2_load(const float *__restrict__ ybuf, const Consts &c, int f, int k1, float2 (&v)[20]) {
     const float *y = ybuf + kYFrameStride * f + 40 * k1;
 #pragma unroll
     for (int j = 0; j < 10; ++j) {
@@ -130,6 +130,10 @@ SGX_HD void pass2_task(const float *__restrict__ ybuf, float *__restrict__ ptile
         v[2 * j] = make_float2(q.x * w0.x - q.y * w0.y, q.x * w0.y + q.y * w0.x);
         v[2 * j + 1] = make_float2(q.z * w1.x - q.w * w1.y, q.z * w1.y + q.w * w1.x);
     }
+}
+
+// writes |X[bin]|^2 for the bins this butterfly owns into P[bin][f]
+SGX_HD void pass2_finish(float2 (&v)[20], float *__restrict__ ptile, int f, int k1) {
     dft20(v);
     float *p = ptile + f;
 #pragma unroll
@@ -144,6 +148,12 @@ SGX_HD void pass2_task(const float *__restrict__ ybuf, float *__restrict__ ptile
             if (k1 != 0 && k1 != 10) p[kFT * (400 - k1 - 20 * k2)] = pw;   // k1 = 0 / 10: conjugate duplicates
         }
     }
+}
+
+SGX_HD void pass2_task(const float *__restrict__ ybuf, float *__restrict__ ptile, const Consts &c, int f, int k1) {
+    float2 v[20];
+    pass2_load(ybuf, c, f, k1, v);
+    pass2_finish(v, ptile, f, k1);
 }
 
 }  // namespace f400

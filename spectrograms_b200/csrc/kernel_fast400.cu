@@ -1,14 +1,17 @@
 // kernel_fast400.cu -- "r2c_fused_n400": the Whisper-shaped family, n_fft = 400, hop = 160, f32 (BASELINE configs[1]
-// and configs[3]). One CTA = one tile of 32 consecutive frames of one clip, 11 warps, lane = frame:
+// and configs[3]). Persistent CTAs (2 per SM), 11 warps, lane = frame; each CTA walks tiles of 32 consecutive frames:
 //
-//   load    5360 samples (31*160 + 400) -> padded signal tile; zero fill outside the clip gives the centre padding
-//           (src/spectrogram.rs:1309-1320) with no per-tap branch
-//   pass 1  warps 0..9 : window multiply + 20-point real-pair DFT in registers   (fft400_core.cuh)
-//   ----    one shared-memory exchange (Y[k1][n2], 11 x 20 complex per frame)
-//   pass 2  warps 0..10: twiddle + 20-point DFT in registers -> |X|^2 straight into the power tile P[bin][frame]
-//   epilogue mapping -> sqrt / dB -> (DCT-II + lifter) -> 128-byte row stores     (epilogue.cuh, lane = frame)
+//   prefetch  cp.async (LDGSTS, 8-byte, zero-fill) of the NEXT tile's 5360 samples into the other signal buffer --
+//             overlaps everything below; out-of-clip bytes are zero filled, which is the reference's centre padding
+//             (src/spectrogram.rs:1309-1320) with no per-tap branch
+//   pass 1    warps 0..9 : window multiply + 20-point real-pair DFT in registers        (fft400_core.cuh)
+//   ----      one shared-memory exchange (Y[k1][n2], 11 x 20 complex per frame)
+//   pass 2    warps 0..10: twiddle + 20-point DFT in registers -> |X|^2 into the power tile P[bin][frame]
+//             (P aliases the Y buffer: a barrier separates the last Y read from the first P write)
+//   epilogue  sparse filterbank rows from a shared-memory table -> sqrt / dB -> 128-byte row stores; other mappings and
+//             the fused DCT-II take the general lane = frame epilogue (epilogue.cuh)
 //
-// Every shared-memory access in the two passes is conflict free by construction of the layouts (fft400_core.cuh);
+// Every shared-memory access of the two passes is conflict free by construction of the layouts (fft400_core.cuh);
 // window and twiddles come from the constant bank (kernel parameter) with warp-uniform indices.
 #include "epilogue.cuh"
 #include "fft400_core.cuh"
@@ -25,53 +28,223 @@ namespace {
 
 using namespace f400;
 
+constexpr int kMaxNnz = 1536;      // sparse-table capacity in shared memory (padded weights)
+constexpr int kMaxRows = 256;      // rows incl. padding to whole quads
+constexpr int kQInfoInts = (kWarps + 1 + kMaxRows / 4 + 3) & ~3;
+
+__device__ __forceinline__ void cp_async8(float *dst_smem, const float *src, int src_bytes) {
+    const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(dst_smem));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+// stage one tile's samples [s0, s0 + 5360) of a clip into a padded signal buffer
+__device__ __forceinline__ void load_tile(float *sig, const float *x, long long s0, long long n, bool vec_ok, int tid) {
+    if (vec_ok && s0 >= 0 && s0 + kTileSamples <= n) {
+        // interior tile (all but the first / last tile of a clip): no bounds logic at all
+        const float *src = x + s0;
+#pragma unroll
+        for (int i = 0; i < (kTileSamples / 2 + kThreads - 1) / kThreads; ++i) {
+            const int j = tid + i * kThreads;
+            if (j < kTileSamples / 2) cp_async8(sig + 2 * j + 2 * (j / (kHop / 2)), src + 2 * j, 8);
+        }
+    } else if (vec_ok) {
+        for (int j = tid; j < kTileSamples / 2; j += kThreads) {
+            const long long s = s0 + 2 * j;
+            const long long avail = n - s;                // samples available from s on
+            const int bytes = (s < 0 || avail <= 0) ? 0 : (avail >= 2 ? 8 : 4);
+            cp_async8(sig + 2 * j + 2 * (j / (kHop / 2)), bytes ? x + s : x, bytes);
+        }
+    } else {
+        for (int j = tid; j < kTileSamples / 2; j += kThreads) {
+            const long long s = s0 + 2 * j;
+            float2 v;
+            v.x = (s >= 0 && s < n) ? __ldg(x + s) : 0.f;
+            v.y = (s + 1 >= 0 && s + 1 < n) ? __ldg(x + s + 1) : 0.f;
+            *reinterpret_cast<float2 *>(sig + 2 * j + 2 * (j / (kHop / 2))) = v;
+        }
+    }
+}
+
+// lg2.approx.ftz: the argument is clamped to eps > 0 first, so the denormal fix-up of __log2f is dead weight
+__device__ __forceinline__ float fast_lg2(float v) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ float lds_f32(unsigned a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float4 lds_v4(unsigned a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+
+// Sparse filterbank rows (mel triangles, loghz interpolation pairs: every row's columns are contiguous), "quad"
+// schedule: one warp step = 4 rows x 32 frames. Lane (s, j) = (lane >> 3, lane & 7) owns row s of the quad and, in
+// sub-step q = 0..3, frame 8*((s + q) & 3) + j -- so the four row groups always read four different 8-bank groups of
+// P[bin][frame] (conflict free), each lane carries four independent accumulators (ILP 4), the row's weights and
+// bookkeeping are loaded once for four outputs, and every store is four 32-byte runs. Rows are sorted by column count
+// on the host, so a quad is nearly homogeneous; the per-lane predicate e < cnt keeps the exact reference arithmetic:
+// ascending columns, acc += T(w) * x with separate rounding (SparseMatrix::multiply_vec, src/spectrogram.rs:102-117).
+// AMP: 0 power, 1 magnitude, 2 dB.
+template <int AMP>
+__device__ __forceinline__ float finish_value(float acc, float eps) {
+    if (AMP == 1) acc = sqrtf(acc);
+    if (AMP == 2) acc = 3.01029995663981195f * fast_lg2(fmaxf(acc, eps));
+    return acc;
+}
+
+template <int AMP>
+__device__ __forceinline__ void sparse_quads_epilogue(const KParams &p, const float *ptile, const int4 *s_quads, const int *s_qinfo,
+                                                      float *out_clip_frame, int nf, int warp, int lane) {
+    const float eps = static_cast<float>(p.eps);
+    const int s = lane >> 3, j = lane & 7;
+    int fr[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) fr[q] = 8 * ((s + q) & 3) + j;
+    const unsigned pbase = smem_u32(ptile);
+    const unsigned qbase = smem_u32(s_quads);
+    const unsigned ors4 = 4u * static_cast<unsigned>(p.out_row_stride);
+    char *ob = reinterpret_cast<char *>(out_clip_frame);
+    const int q0 = s_qinfo[warp], q1 = s_qinfo[warp + 1];
+#pragma unroll 1
+    for (int qi = q0; qi < q1; ++qi) {
+        const float4 rf = lds_v4(qbase + 16u * (4 * qi + s));      // {byte offset of P[c0], cnt, weights address, row}
+        const int maxc = s_qinfo[kWarps + 1 + qi];
+        const int cnt = __float_as_int(rf.y);
+        const unsigned pa = pbase + __float_as_uint(rf.x) + 4u * j;
+        unsigned wa = __float_as_uint(rf.z);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        unsigned pe = pa;
+#pragma unroll 1
+        for (int e = 0; e < maxc; ++e, wa += 4, pe += kFT * 4) {
+            const float w = lds_f32(wa);
+            const float x0 = lds_f32(pe + 32u * ((s + 0) & 3)), x1 = lds_f32(pe + 32u * ((s + 1) & 3));
+            const float x2 = lds_f32(pe + 32u * ((s + 2) & 3)), x3 = lds_f32(pe + 32u * ((s + 3) & 3));
+            if (e < cnt) {
+                a0 = __fadd_rn(a0, __fmul_rn(w, x0));
+                a1 = __fadd_rn(a1, __fmul_rn(w, x1));
+                a2 = __fadd_rn(a2, __fmul_rn(w, x2));
+                a3 = __fadd_rn(a3, __fmul_rn(w, x3));
+            }
+        }
+        const int row = __float_as_int(rf.w);
+        if (row >= 0) {
+            char *orow = ob + static_cast<size_t>(static_cast<unsigned>(row)) * ors4;
+            const float v0 = finish_value<AMP>(a0, eps), v1 = finish_value<AMP>(a1, eps);
+            const float v2 = finish_value<AMP>(a2, eps), v3 = finish_value<AMP>(a3, eps);
+            if (fr[0] < nf) *reinterpret_cast<float *>(orow + 4 * fr[0]) = v0;
+            if (fr[1] < nf) *reinterpret_cast<float *>(orow + 4 * fr[1]) = v1;
+            if (fr[2] < nf) *reinterpret_cast<float *>(orow + 4 * fr[2]) = v2;
+            if (fr[3] < nf) *reinterpret_cast<float *>(orow + 4 * fr[3]) = v3;
+        }
+    }
+}
+
+// SPARSE: mel / loghz rows served from the shared-memory table; otherwise the general epilogue.
+template <bool SPARSE>
 __global__ void __launch_bounds__(kThreads, 2) k_r2c_fused_n400(const __grid_constant__ F400Params P) {
     extern __shared__ __align__(16) float smem[];
-    float *sig = smem;
-    float *ybuf = sig + kSigWords;
-    float *ptile = ybuf + kYWords;
+    float *sig0 = smem;
+    float *sig1 = sig0 + kSigWords;
+    float *ybuf = sig1 + kSigWords;
+    float *ptile = ybuf;                       // aliases the Y exchange buffer
+    float *scratch = ybuf + kPWords;           // log-mel tile of the MFCC path (rows * 32 <= kYWords - kPWords)
+    int4 *s_quads = reinterpret_cast<int4 *>(ybuf + kYWords);        // [4 * n_quads] {byte offset of P[c0], cnt, weights address, row}
+    int *s_qinfo = reinterpret_cast<int *>(s_quads + kMaxRows);      // [kWarps + 1] quad ranges per warp, then [n_quads] max cnt
+    float *s_w = reinterpret_cast<float *>(s_qinfo + kQInfoInts);    // weights, rows padded to multiples of 4
     const KParams &p = P.k;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int clip = blockIdx.x / p.tiles_per_clip;
-    const int tile = blockIdx.x - clip * p.tiles_per_clip;
-    const long long f0 = p.frame_begin + static_cast<long long>(tile) * kFT;
-    const long long rem = p.frame_begin + p.frames_todo - f0;
-    const int nf = rem < kFT ? static_cast<int>(rem) : kFT;
+    const bool vec_ok = p.buf_elems != 0;
 
-    // ---- load the signal tile (8-byte units; p.buf_elems != 0 means the base is 8-byte aligned and the stride even)
-    const float *x = static_cast<const float *>(p.samples) + static_cast<long long>(clip) * p.clip_stride;
-    const long long s0 = f0 * kHop - p.pad;
-    const long long n = p.n_samples;
-    for (int j = tid; j < kTileSamples / 2; j += kThreads) {
-        const long long s = s0 + 2 * j;
-        float2 v;
-        if (p.buf_elems && s >= 0 && s + 1 < n) {
-            v = __ldg(reinterpret_cast<const float2 *>(x + s));
-        } else {
-            v.x = (s >= 0 && s < n) ? __ldg(x + s) : 0.f;
-            v.y = (s + 1 >= 0 && s + 1 < n) ? __ldg(x + s + 1) : 0.f;
+    if (SPARSE) {
+        // p.dense carries the host-built schedule blob: int n_quads; int qrange[kWarps + 1]; int maxcnt[n_quads];
+        // (16-byte aligned) int4 {c0, cnt, padded weight offset, row or -1}[4 * n_quads]
+        const int *blob = reinterpret_cast<const int *>(p.dense);
+        const int nq = __ldg(blob);
+        const int hdr = (1 + kWarps + 1 + nq + 3) & ~3;
+        const int4 *quads = reinterpret_cast<const int4 *>(blob + hdr);
+        const float *val = static_cast<const float *>(p.val);
+        const unsigned wbase = smem_u32(s_w);
+        for (int i = tid; i < kWarps + 1 + nq; i += kThreads) s_qinfo[i] = __ldg(blob + 1 + i);
+        for (int i = tid; i < 4 * nq; i += kThreads) {
+            const int4 e = __ldg(quads + i);
+            s_quads[i] = make_int4(e.x * (kFT * 4), e.y, static_cast<int>(wbase + 4u * e.z), e.w);
+            if (e.w >= 0) {
+                const int e0 = __ldg(p.row_ptr + e.w);
+                for (int k = 0; k < ((e.y + 3) & ~3); ++k) s_w[e.z + k] = k < e.y ? __ldg(val + e0 + k) : 0.f;
+            }
         }
-        *reinterpret_cast<float2 *>(sig + 2 * j + 2 * (j / (kHop / 2))) = v;
     }
-    __syncthreads();
 
-    if (warp < 10) pass1_task(sig, ybuf, P.c, lane, warp);
-    __syncthreads();
+    // persistent walk over tiles t = blockIdx.x, += gridDim.x; (clip, tile) advance by carry instead of dividing
+    const int tpc = p.tiles_per_clip;
+    const int step_clip = static_cast<int>(gridDim.x / tpc), step_tile = static_cast<int>(gridDim.x % tpc);
+    int clip = static_cast<int>(blockIdx.x / tpc), tile = static_cast<int>(blockIdx.x % tpc);
+    const float *xbase = static_cast<const float *>(p.samples);
+    int buf = 0;
+    if (clip < p.n_clips)
+        load_tile(sig0, xbase + static_cast<long long>(clip) * p.clip_stride,
+                  (p.frame_begin + static_cast<long long>(tile) * kFT) * kHop - p.pad, p.n_samples, vec_ok, tid);
+    for (; clip < p.n_clips; buf ^= 1) {
+        const long long f0 = p.frame_begin + static_cast<long long>(tile) * kFT;
+        const long long rem = p.frame_begin + p.frames_todo - f0;
+        const int nf = rem < kFT ? static_cast<int>(rem) : kFT;
+        float *sig = buf ? sig1 : sig0;
+        const int cur_clip = clip;
 
-    pass2_task(ybuf, ptile, P.c, lane, warp);
-    __syncthreads();
+        cp_async_commit_wait_all();
+        __syncthreads();                       // tile t has landed; everyone is done with the previous tile's P
 
-    // Y exchange buffer is dead now: scratch for the log-mel tile of the MFCC path (n_bins * 32 <= kYWords checked on host)
-    epilogue_lane_frames<float>(p, ptile, ybuf, clip, f0, nf);
+        clip += step_clip;                     // next tile of this CTA
+        tile += step_tile;
+        if (tile >= tpc) { tile -= tpc; ++clip; }
+        if (clip < p.n_clips)                  // prefetch it into the other buffer
+            load_tile(buf ? sig0 : sig1, xbase + static_cast<long long>(clip) * p.clip_stride,
+                      (p.frame_begin + static_cast<long long>(tile) * kFT) * kHop - p.pad, p.n_samples, vec_ok, tid);
+
+        if (warp < 10) pass1_task(sig, ybuf, P.c, lane, warp);
+        __syncthreads();
+
+        float2 v[20];
+        pass2_load(ybuf, P.c, lane, warp, v);
+        __syncthreads();                       // every Y value is in registers: P may overwrite the buffer
+        pass2_finish(v, ptile, lane, warp);
+        __syncthreads();
+
+        if (SPARSE && p.output != SGX_OUT_MFCC) {
+            float *ocf = static_cast<float *>(p.out) + static_cast<long long>(cur_clip) * p.out_clip_stride + (f0 - p.out_frame_origin);
+            if (p.apply_db) sparse_quads_epilogue<2>(p, ptile, s_quads, s_qinfo, ocf, nf, warp, lane);
+            else if (p.amp == SGX_AMP_MAGNITUDE) sparse_quads_epilogue<1>(p, ptile, s_quads, s_qinfo, ocf, nf, warp, lane);
+            else sparse_quads_epilogue<0>(p, ptile, s_quads, s_qinfo, ocf, nf, warp, lane);
+        } else {
+            epilogue_lane_frames<float>(p, ptile, scratch, cur_clip, f0, nf);
+        }
+    }
 }
 
 }  // namespace
 
-size_t fast400_smem_bytes() { return sizeof(float) * (f400::kSigWords + f400::kYWords + f400::kPWords); }
-int fast400_max_scratch_rows() { return f400::kYWords / 32; }
+size_t fast400_smem_bytes() {
+    return sizeof(float) * (2 * f400::kSigWords + f400::kYWords) + sizeof(int4) * kMaxRows + sizeof(int) * kQInfoInts +
+           sizeof(float) * (kMaxNnz + 64);
+}
+int fast400_max_scratch_rows() { return (f400::kYWords - f400::kPWords) / 32; }
+int fast400_max_sparse_rows() { return kMaxRows; }
+int fast400_max_sparse_nnz() { return kMaxNnz; }
+int fast400_warps() { return f400::kWarps; }
 
-cudaError_t launch_fast400(const KParams &p, const float *window_f32, cudaStream_t stream) {
+
+cudaError_t launch_fast400(const KParams &p, const float *window_f32, bool sparse_table, int sm_count, cudaStream_t stream) {
     static_assert(sizeof(F400Params) <= 4096, "kernel parameter block must fit the classic 4 KiB limit");
     F400Params P;
     P.k = p;
@@ -86,13 +259,20 @@ cudaError_t launch_fast400(const KParams &p, const float *window_f32, cudaStream
             P.c.tw2[k1][n2] = make_float2(static_cast<float>(s * static_cast<double>(cosl(a))),
                                           static_cast<float>(s * static_cast<double>(sinl(a))));
         }
-    const long long grid = static_cast<long long>(p.n_clips) * P.k.tiles_per_clip;
-    if (grid <= 0) return cudaSuccess;
-    if (grid > 2147483647LL) return cudaErrorInvalidConfiguration;
+    const long long total = static_cast<long long>(p.n_clips) * P.k.tiles_per_clip;
+    if (total <= 0) return cudaSuccess;
+    const long long grid = std::min<long long>(total, 2LL * sm_count);     // persistent: 2 CTAs per SM
     const size_t smem = fast400_smem_bytes();
-    cudaError_t e = cudaFuncSetAttribute(k_r2c_fused_n400, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess) return e;
-    k_r2c_fused_n400<<<static_cast<unsigned>(grid), f400::kThreads, smem, stream>>>(P);
+    cudaError_t e;
+    if (sparse_table) {
+        e = cudaFuncSetAttribute(k_r2c_fused_n400<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return e;
+        k_r2c_fused_n400<true><<<static_cast<unsigned>(grid), f400::kThreads, smem, stream>>>(P);
+    } else {
+        e = cudaFuncSetAttribute(k_r2c_fused_n400<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return e;
+        k_r2c_fused_n400<false><<<static_cast<unsigned>(grid), f400::kThreads, smem, stream>>>(P);
+    }
     return cudaGetLastError();
 }
 

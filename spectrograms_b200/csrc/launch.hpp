@@ -1,6 +1,8 @@
 // launch.hpp -- host-callable launchers of the kernel families (defined in the kernel_*.cu files).
 #pragma once
 
+#include <algorithm>
+
 #include <cuda_runtime.h>
 
 #include "../../include/sgx_b200.h"
@@ -13,9 +15,14 @@ cudaError_t launch_generic(const KParams &p, bool f64, size_t smem_bytes, cudaSt
 
 // r2c_fused_n400: n_fft = 400, hop = 160, f32, any spectrogram / MFCC output (kernel_fast400.cu).
 // p.buf_elems is reused as the "8-byte aligned input" flag; window_f32 is the host copy of the plan window.
-cudaError_t launch_fast400(const KParams &p, const float *window_f32, cudaStream_t stream);
+// sparse_table: serve mel / loghz rows from a shared-memory copy of the CSR table (needs rows <= max_sparse_rows and
+// nnz <= max_sparse_nnz); sm_count sizes the persistent grid (2 CTAs per SM).
+cudaError_t launch_fast400(const KParams &p, const float *window_f32, bool sparse_table, int sm_count, cudaStream_t stream);
 size_t fast400_smem_bytes();
 int fast400_max_scratch_rows();
+int fast400_max_sparse_rows();
+int fast400_max_sparse_nnz();
+int fast400_warps();
 
 // standalone mfcc_from_log_mel (kernel_mfcc.cu): log_mel [n_clips][n_mels][n_frames] -> out [n_clips][rows][n_frames]
 cudaError_t launch_mfcc(bool f64, const void *log_mel, void *out, long long n_clips, int n_mels, long long n_frames,

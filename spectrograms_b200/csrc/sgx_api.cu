@@ -1,5 +1,6 @@
 // sgx_api.cu -- the C ABI (include/sgx_b200.h): plan objects, validation, table upload, dispatch, host staging.
 // No torch types, no CPU compute path: without a CUDA device every compute call fails with SGX_BACKEND_ERROR.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -124,7 +125,8 @@ struct sgx_plan {
     // device tables
     void *d_window = nullptr, *d_tw = nullptr, *d_post = nullptr, *d_val = nullptr, *d_dense = nullptr;
     void *d_dct = nullptr, *d_lifter = nullptr;
-    int *d_row_ptr = nullptr, *d_col = nullptr;
+    int *d_row_ptr = nullptr, *d_col = nullptr, *d_wofs = nullptr;
+    std::vector<int> wofs;           // padded weight offset per row (fast sparse table)
     // generic-family geometry
     int FT = 1, buf_elems = 0, frame_stride = 0, tile_stride = 0;
     size_t smem_bytes = 0;
@@ -134,6 +136,8 @@ struct sgx_plan {
     size_t last_launches = 0;
     std::string kernel_name = "r2c_fused_generic";
     bool fast400 = false;            // eligible for r2c_fused_n400
+    bool fast400_sparse = false;     // ... with the shared-memory sparse table
+    int sm_count = 148;
     std::vector<float> window_f32;
     // staging for host-pointer calls
     struct Slot { void *d_in = nullptr; void *d_out = nullptr; size_t in_cap = 0, out_cap = 0; cudaStream_t s = nullptr; } slot[kStagingSlots];
@@ -145,6 +149,7 @@ struct sgx_plan {
         for (void *p : {d_window, d_tw, d_post, d_val, d_dense, d_dct, d_lifter}) if (p) cudaFree(p);
         if (d_row_ptr) cudaFree(d_row_ptr);
         if (d_col) cudaFree(d_col);
+        if (d_wofs) cudaFree(d_wofs);
         for (auto &s : slot) {
             if (s.d_in) cudaFree(s.d_in);
             if (s.d_out) cudaFree(s.d_out);
@@ -180,6 +185,68 @@ void select_family(sgx_plan &pl) {
         pl.window_f32.resize(d.n_fft);
         for (size_t i = 0; i < d.n_fft; ++i) pl.window_f32[i] = static_cast<float>(pl.tab.window[i]);
     }
+    const bool csr = d.mapping == SGX_MAP_MEL || d.mapping == SGX_MAP_LOGHZ;
+    // The shared-memory sparse schedule needs rows with contiguous columns (mel triangles, loghz pairs). Rows are sorted
+    // by column count, grouped four at a time ("quads", padded with row = -1), and the quads are dealt to the kernel's
+    // warps longest-first onto the least loaded warp. Blob: int n_quads; int qrange[W + 1]; int maxcnt[n_quads];
+    // pad to 16 bytes; int4 {c0, cnt, padded weight offset, row}[4 * n_quads] in warp order.
+    bool contiguous = csr;
+    int padded = 0;
+    pl.wofs.clear();
+    if (csr) {
+        const int W = fast400_warps();
+        const size_t nb = pl.tab.n_bins;
+        std::vector<int> cnt(nb), wo(nb);
+        for (size_t r = 0; r < nb; ++r) {
+            const int e0 = pl.tab.row_ptr[r], e1 = pl.tab.row_ptr[r + 1];
+            for (int e = e0 + 1; e < e1; ++e) contiguous = contiguous && pl.tab.col[e] == pl.tab.col[e - 1] + 1;
+            cnt[r] = e1 - e0;
+            wo[r] = padded;
+            padded += (e1 - e0 + 3) & ~3;
+        }
+        std::vector<int> order(nb);
+        for (size_t r = 0; r < nb; ++r) order[r] = static_cast<int>(r);
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cnt[a] > cnt[b]; });
+        while (order.size() % 4) order.push_back(-1);
+        const int nq = static_cast<int>(order.size() / 4);
+        std::vector<int> qmax(nq, 0);
+        for (int q = 0; q < nq; ++q)
+            for (int k = 0; k < 4; ++k)
+                if (order[4 * q + k] >= 0) qmax[q] = std::max(qmax[q], cnt[order[4 * q + k]]);
+        std::vector<std::vector<int>> per_warp(W);
+        std::vector<long> load(W, 0);
+        for (int q = 0; q < nq; ++q) {          // quads are already in descending cost order
+            int best = 0;
+            for (int w = 1; w < W; ++w) if (load[w] < load[best]) best = w;
+            per_warp[best].push_back(q);
+            load[best] += 26 + 16 * qmax[q];
+        }
+        const int hdr = (1 + W + 1 + nq + 3) & ~3;
+        std::vector<int> blob(static_cast<size_t>(hdr) + 16 * static_cast<size_t>(nq), 0);
+        blob[0] = nq;
+        int idx = 0;
+        for (int w = 0; w < W; ++w) {
+            blob[1 + w] = idx;
+            for (int q : per_warp[w]) {
+                blob[1 + W + 1 + idx] = qmax[q];
+                for (int k = 0; k < 4; ++k) {
+                    const int r = order[4 * q + k];
+                    int *e = &blob[static_cast<size_t>(hdr) + 4 * (4 * static_cast<size_t>(idx) + k)];
+                    e[0] = (r >= 0 && cnt[r]) ? pl.tab.col[pl.tab.row_ptr[r]] : 0;
+                    e[1] = r >= 0 ? cnt[r] : 0;
+                    e[2] = r >= 0 ? wo[r] : 0;
+                    e[3] = r;
+                }
+                ++idx;
+            }
+        }
+        blob[1 + W] = idx;
+        pl.wofs = blob;
+        padded = std::max(padded, 4);
+        if (static_cast<int>(order.size()) > fast400_max_sparse_rows()) contiguous = false;
+    }
+    pl.fast400_sparse = pl.fast400 && csr && contiguous && static_cast<int>(pl.tab.n_bins) <= fast400_max_sparse_rows() &&
+                        padded <= fast400_max_sparse_nnz();
     pl.kernel_name = pl.fast400 ? "r2c_fused_n400" : "r2c_fused_generic";
 }
 
@@ -223,10 +290,14 @@ void ensure_device(sgx_plan &pl) {
     if (pl.even) pl.d_post = upload(twiddle_table(pl.desc.n_fft, static_cast<size_t>(pl.L) + 1), pl.f64);
     pl.d_row_ptr = upload_int(pl.tab.row_ptr);
     pl.d_col = upload_int(pl.tab.col);
+    pl.d_wofs = upload_int(pl.wofs);
     pl.d_val = upload(pl.tab.val, pl.f64);
     pl.d_dense = upload(pl.tab.dense, pl.f64);
     pl.d_dct = upload(pl.tab.dct, pl.f64);
     pl.d_lifter = upload(pl.tab.lifter, pl.f64);
+    cudaDeviceProp prop;
+    ck(cudaGetDeviceProperties(&prop, dev), "cudaGetDeviceProperties");
+    pl.sm_count = prop.multiProcessorCount;
     pl.on_device = true;
 }
 
@@ -285,7 +356,8 @@ void run_device(sgx_plan &pl, const void *d_samples, size_t n_clips, size_t n_sa
         if (pl.fast400 && !pl.force_generic) {
             // 8-byte vector loads need an 8-byte aligned base and an even clip stride
             q.buf_elems = (reinterpret_cast<uintptr_t>(q.samples) % 8 == 0 && clip_stride % 2 == 0) ? 1 : 0;
-            ck(launch_fast400(q, pl.window_f32.data(), stream), "kernel launch (r2c_fused_n400)");
+            if (pl.fast400_sparse) q.dense = pl.d_wofs;      // sparse mappings do not use `dense`: carries the weight offsets
+            ck(launch_fast400(q, pl.window_f32.data(), pl.fast400_sparse, pl.sm_count, stream), "kernel launch (r2c_fused_n400)");
         } else {
             ck(launch_generic(q, pl.f64, pl.smem_bytes, stream), "kernel launch (r2c_fused_generic)");
         }
