@@ -91,15 +91,16 @@ __device__ __forceinline__ void epilogue_complex(const KParams &p, const typenam
 // Variant for kernel families whose tile is "frames fastest": P[k * 32 + f], exactly 32 frames per tile, lane = frame.
 // One warp owns one output row at a time, so every filterbank weight / column index / DCT coefficient is warp-uniform
 // and every store is a 128-byte run of one output row. scratch: [row * 32 + f], >= n_bins * 32 elements (MFCC only).
+// lane_col: the column of this lane's frame inside a tile row (identity unless the family permutes frames in a row).
 template <typename T>
 __device__ __forceinline__ void epilogue_lane_frames(const KParams &p, const T *__restrict__ P, T *__restrict__ scratch,
-                                                     int clip, long long f0, int nf) {
+                                                     int clip, long long f0, int nf, int lane_col) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const T eps = static_cast<T>(p.eps);
     T *out = static_cast<T *>(p.out) + static_cast<long long>(clip) * p.out_clip_stride + (f0 - p.out_frame_origin) + lane;
     const bool to_mfcc = (p.output == SGX_OUT_MFCC);
     const bool live = lane < nf;
-    const T *pl = P + lane;
+    const T *pl = P + lane_col;
     for (int row = warp; row < p.n_bins; row += nwarps) {
         T acc;
         if (p.mapping == SGX_MAP_LINEAR) {

@@ -35,8 +35,9 @@ constexpr int kThreads = kWarps * 32;
 //                 makes the frame stride 162 == 2 (mod 32): lanes = frames read 8-byte pairs from 16 distinct bank pairs.
 //   Y exchange  : Y[f][k1][n2] complex at 444 f + 40 k1 + 2 n2 ; 444/4 odd -> 16-byte accesses with lanes = frames are
 //                 conflict free both when pass 1 writes and when pass 2 reads.
-//   power tile  : P[bin][f] at 32 bin + f (frames fastest: conflict free for lanes = frames, and it is already the
-//                 (rows, frames) orientation of the output).
+//   power tile  : P[bin][frame_col(f)] at 32 bin + frame_col(f): frames fastest (conflict free for lanes = frames, and
+//                 already the (rows, frames) orientation of the output), with the frame order permuted inside a row so
+//                 that one 16-byte read returns frames j, j+8, j+16, j+24 (what one epilogue lane owns).
 constexpr int kSigBlocks = 34;                         // ceil((31*160 + 400) / 160)
 constexpr int kSigBlockStride = 162;
 constexpr int kSigWords = kSigBlocks * kSigBlockStride;   // 5508
@@ -52,6 +53,7 @@ struct Consts {
 };
 
 SGX_HD int sig_word(int u) { return u + 2 * (u / kHop); }
+SGX_HD int frame_col(int f) { return ((f & 7) << 2) | (f >> 3); }
 
 SGX_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 SGX_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
@@ -135,7 +137,7 @@ SGX_HD void pass2_load(const float *__restrict__ ybuf, const Consts &c, int f, i
 // writes |X[bin]|^2 for the bins this butterfly owns into P[bin][f]
 SGX_HD void pass2_finish(float2 (&v)[20], float *__restrict__ ptile, int f, int k1) {
     dft20(v);
-    float *p = ptile + f;
+    float *p = ptile + frame_col(f);
 #pragma unroll
     for (int k2 = 0; k2 < 20; ++k2) {
         const float2 X = v[reg_of_bin(k2)];

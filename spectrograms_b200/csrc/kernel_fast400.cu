@@ -1,8 +1,8 @@
 // kernel_fast400.cu -- "r2c_fused_n400": the Whisper-shaped family, n_fft = 400, hop = 160, f32 (BASELINE configs[1]
 // and configs[3]). Persistent CTAs (2 per SM), 11 warps, lane = frame; each CTA walks tiles of 32 consecutive frames:
 //
-//   prefetch  cp.async (LDGSTS, 8-byte, zero-fill) of the NEXT tile's 5360 samples into the other signal buffer --
-//             overlaps everything below; out-of-clip bytes are zero filled, which is the reference's centre padding
+//   prefetch  cp.async (LDGSTS, 8-byte, zero-fill) of the NEXT tile's 5360 samples into the other signal buffer, issued
+//             by warp 10 (which has no pass-1 role) -- overlaps everything below; out-of-clip bytes are zero filled, which is the reference's centre padding
 //             (src/spectrogram.rs:1309-1320) with no per-tap branch
 //   pass 1    warps 0..9 : window multiply + 20-point real-pair DFT in registers        (fft400_core.cuh)
 //   ----      one shared-memory exchange (Y[k1][n2], 11 x 20 complex per frame)
@@ -41,24 +41,22 @@ __device__ __forceinline__ void cp_async_commit_wait_all() {
 }
 
 // stage one tile's samples [s0, s0 + 5360) of a clip into a padded signal buffer
-__device__ __forceinline__ void load_tile(float *sig, const float *x, long long s0, long long n, bool vec_ok, int tid) {
+// (tid, nthr): the threads taking part -- the whole CTA for the first tile, one warp for the prefetches
+__device__ __forceinline__ void load_tile(float *sig, const float *x, long long s0, long long n, bool vec_ok, int tid, int nthr) {
     if (vec_ok && s0 >= 0 && s0 + kTileSamples <= n) {
         // interior tile (all but the first / last tile of a clip): no bounds logic at all
         const float *src = x + s0;
-#pragma unroll
-        for (int i = 0; i < (kTileSamples / 2 + kThreads - 1) / kThreads; ++i) {
-            const int j = tid + i * kThreads;
-            if (j < kTileSamples / 2) cp_async8(sig + 2 * j + 2 * (j / (kHop / 2)), src + 2 * j, 8);
-        }
+#pragma unroll 4
+        for (int j = tid; j < kTileSamples / 2; j += nthr) cp_async8(sig + 2 * j + 2 * (j / (kHop / 2)), src + 2 * j, 8);
     } else if (vec_ok) {
-        for (int j = tid; j < kTileSamples / 2; j += kThreads) {
+        for (int j = tid; j < kTileSamples / 2; j += nthr) {
             const long long s = s0 + 2 * j;
             const long long avail = n - s;                // samples available from s on
             const int bytes = (s < 0 || avail <= 0) ? 0 : (avail >= 2 ? 8 : 4);
             cp_async8(sig + 2 * j + 2 * (j / (kHop / 2)), bytes ? x + s : x, bytes);
         }
     } else {
-        for (int j = tid; j < kTileSamples / 2; j += kThreads) {
+        for (int j = tid; j < kTileSamples / 2; j += nthr) {
             const long long s = s0 + 2 * j;
             float2 v;
             v.x = (s >= 0 && s < n) ? __ldg(x + s) : 0.f;
@@ -88,10 +86,10 @@ __device__ __forceinline__ float4 lds_v4(unsigned a) {
 }
 
 // Sparse filterbank rows (mel triangles, loghz interpolation pairs: every row's columns are contiguous), "quad"
-// schedule: one warp step = 4 rows x 32 frames. Lane (s, j) = (lane >> 3, lane & 7) owns row s of the quad and, in
-// sub-step q = 0..3, frame 8*((s + q) & 3) + j -- so the four row groups always read four different 8-bank groups of
-// P[bin][frame] (conflict free), each lane carries four independent accumulators (ILP 4), the row's weights and
-// bookkeeping are loaded once for four outputs, and every store is four 32-byte runs. Rows are sorted by column count
+// schedule: one warp step = 4 rows x 32 frames. Lane (s, j) = (lane >> 3, lane & 7) owns row s of the quad and frames
+// j, j+8, j+16, j+24, which the permuted power tile hands over in ONE 16-byte read per column (4 wavefronts per warp
+// instruction = the minimum for 512 bytes). Each lane carries four independent accumulators (ILP 4), the row's weights
+// and bookkeeping are loaded once for four outputs, and every store instruction writes four 32-byte runs. Rows are sorted by column count
 // on the host, so a quad is nearly homogeneous; the per-lane predicate e < cnt keeps the exact reference arithmetic:
 // ascending columns, acc += T(w) * x with separate rounding (SparseMatrix::multiply_vec, src/spectrogram.rs:102-117).
 // AMP: 0 power, 1 magnitude, 2 dB.
@@ -107,33 +105,28 @@ __device__ __forceinline__ void sparse_quads_epilogue(const KParams &p, const fl
                                                       float *out_clip_frame, int nf, int warp, int lane) {
     const float eps = static_cast<float>(p.eps);
     const int s = lane >> 3, j = lane & 7;
-    int fr[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) fr[q] = 8 * ((s + q) & 3) + j;
-    const unsigned pbase = smem_u32(ptile);
+    const unsigned pbase = smem_u32(ptile) + 16u * j;             // columns 4j..4j+3 = frames j, j+8, j+16, j+24
     const unsigned qbase = smem_u32(s_quads);
     const unsigned ors4 = 4u * static_cast<unsigned>(p.out_row_stride);
-    char *ob = reinterpret_cast<char *>(out_clip_frame);
+    char *ob = reinterpret_cast<char *>(out_clip_frame) + 4 * j;
     const int q0 = s_qinfo[warp], q1 = s_qinfo[warp + 1];
 #pragma unroll 1
     for (int qi = q0; qi < q1; ++qi) {
         const float4 rf = lds_v4(qbase + 16u * (4 * qi + s));      // {byte offset of P[c0], cnt, weights address, row}
         const int maxc = s_qinfo[kWarps + 1 + qi];
         const int cnt = __float_as_int(rf.y);
-        const unsigned pa = pbase + __float_as_uint(rf.x) + 4u * j;
+        unsigned pe = pbase + __float_as_uint(rf.x);
         unsigned wa = __float_as_uint(rf.z);
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        unsigned pe = pa;
 #pragma unroll 1
         for (int e = 0; e < maxc; ++e, wa += 4, pe += kFT * 4) {
             const float w = lds_f32(wa);
-            const float x0 = lds_f32(pe + 32u * ((s + 0) & 3)), x1 = lds_f32(pe + 32u * ((s + 1) & 3));
-            const float x2 = lds_f32(pe + 32u * ((s + 2) & 3)), x3 = lds_f32(pe + 32u * ((s + 3) & 3));
+            const float4 x = lds_v4(pe);
             if (e < cnt) {
-                a0 = __fadd_rn(a0, __fmul_rn(w, x0));
-                a1 = __fadd_rn(a1, __fmul_rn(w, x1));
-                a2 = __fadd_rn(a2, __fmul_rn(w, x2));
-                a3 = __fadd_rn(a3, __fmul_rn(w, x3));
+                a0 = __fadd_rn(a0, __fmul_rn(w, x.x));
+                a1 = __fadd_rn(a1, __fmul_rn(w, x.y));
+                a2 = __fadd_rn(a2, __fmul_rn(w, x.z));
+                a3 = __fadd_rn(a3, __fmul_rn(w, x.w));
             }
         }
         const int row = __float_as_int(rf.w);
@@ -141,10 +134,10 @@ __device__ __forceinline__ void sparse_quads_epilogue(const KParams &p, const fl
             char *orow = ob + static_cast<size_t>(static_cast<unsigned>(row)) * ors4;
             const float v0 = finish_value<AMP>(a0, eps), v1 = finish_value<AMP>(a1, eps);
             const float v2 = finish_value<AMP>(a2, eps), v3 = finish_value<AMP>(a3, eps);
-            if (fr[0] < nf) *reinterpret_cast<float *>(orow + 4 * fr[0]) = v0;
-            if (fr[1] < nf) *reinterpret_cast<float *>(orow + 4 * fr[1]) = v1;
-            if (fr[2] < nf) *reinterpret_cast<float *>(orow + 4 * fr[2]) = v2;
-            if (fr[3] < nf) *reinterpret_cast<float *>(orow + 4 * fr[3]) = v3;
+            if (j < nf) *reinterpret_cast<float *>(orow) = v0;
+            if (j + 8 < nf) *reinterpret_cast<float *>(orow + 32) = v1;
+            if (j + 16 < nf) *reinterpret_cast<float *>(orow + 64) = v2;
+            if (j + 24 < nf) *reinterpret_cast<float *>(orow + 96) = v3;
         }
     }
 }
@@ -194,7 +187,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_r2c_fused_n400(const __grid_con
     int buf = 0;
     if (clip < p.n_clips)
         load_tile(sig0, xbase + static_cast<long long>(clip) * p.clip_stride,
-                  (p.frame_begin + static_cast<long long>(tile) * kFT) * kHop - p.pad, p.n_samples, vec_ok, tid);
+                  (p.frame_begin + static_cast<long long>(tile) * kFT) * kHop - p.pad, p.n_samples, vec_ok, tid, kThreads);
     for (; clip < p.n_clips; buf ^= 1) {
         const long long f0 = p.frame_begin + static_cast<long long>(tile) * kFT;
         const long long rem = p.frame_begin + p.frames_todo - f0;
@@ -208,11 +201,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_r2c_fused_n400(const __grid_con
         clip += step_clip;                     // next tile of this CTA
         tile += step_tile;
         if (tile >= tpc) { tile -= tpc; ++clip; }
-        if (clip < p.n_clips)                  // prefetch it into the other buffer
+        // warp 10 has no pass-1 role: it prefetches the next tile into the other buffer while warps 0..9 run pass 1
+        if (warp < 10) {
+            pass1_task(sig, ybuf, P.c, lane, warp);
+        } else if (clip < p.n_clips) {
             load_tile(buf ? sig0 : sig1, xbase + static_cast<long long>(clip) * p.clip_stride,
-                      (p.frame_begin + static_cast<long long>(tile) * kFT) * kHop - p.pad, p.n_samples, vec_ok, tid);
-
-        if (warp < 10) pass1_task(sig, ybuf, P.c, lane, warp);
+                      (p.frame_begin + static_cast<long long>(tile) * kFT) * kHop - p.pad, p.n_samples, vec_ok, lane, 32);
+        }
         __syncthreads();
 
         float2 v[20];
@@ -227,7 +222,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_r2c_fused_n400(const __grid_con
             else if (p.amp == SGX_AMP_MAGNITUDE) sparse_quads_epilogue<1>(p, ptile, s_quads, s_qinfo, ocf, nf, warp, lane);
             else sparse_quads_epilogue<0>(p, ptile, s_quads, s_qinfo, ocf, nf, warp, lane);
         } else {
-            epilogue_lane_frames<float>(p, ptile, scratch, cur_clip, f0, nf);
+            epilogue_lane_frames<float>(p, ptile, scratch, cur_clip, f0, nf, frame_col(lane));
         }
     }
 }

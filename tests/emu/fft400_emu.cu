@@ -29,6 +29,7 @@ extern "C" int emu_fft400_tile(const float *samples, long long n_samples, long l
         for (int f = 0; f < kFT; ++f) pass1_task(sig.data(), ybuf.data(), c, f, t);
     for (int k1 = 0; k1 <= 10; ++k1)
         for (int f = 0; f < kFT; ++f) pass2_task(ybuf.data(), p.data(), c, f, k1);
-    std::memcpy(power_out, p.data(), sizeof(float) * kPWords);
+    for (int b = 0; b < kBins; ++b)
+        for (int f = 0; f < kFT; ++f) power_out[b * kFT + f] = p[b * kFT + frame_col(f)];
     return 0;
 }
