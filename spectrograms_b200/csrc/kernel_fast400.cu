@@ -100,9 +100,11 @@ __device__ __forceinline__ float finish_value(float acc, float eps) {
     return acc;
 }
 
-template <int AMP>
+// TO_SMEM: instead of storing to global memory, leave the scaled rows in a shared tile mtile[row][32] (same permuted
+// frame order as the power tile) for the fused DCT.
+template <int AMP, bool TO_SMEM>
 __device__ __forceinline__ void sparse_quads_epilogue(const KParams &p, const float *ptile, const int4 *s_quads, const int *s_qinfo,
-                                                      float *out_clip_frame, int nf, int warp, int lane) {
+                                                      float *out_clip_frame, float *mtile, int nf, int warp, int lane) {
     const float eps = static_cast<float>(p.eps);
     const int s = lane >> 3, j = lane & 7;
     const unsigned pbase = smem_u32(ptile) + 16u * j;             // columns 4j..4j+3 = frames j, j+8, j+16, j+24
@@ -131,13 +133,64 @@ __device__ __forceinline__ void sparse_quads_epilogue(const KParams &p, const fl
         }
         const int row = __float_as_int(rf.w);
         if (row >= 0) {
-            char *orow = ob + static_cast<size_t>(static_cast<unsigned>(row)) * ors4;
             const float v0 = finish_value<AMP>(a0, eps), v1 = finish_value<AMP>(a1, eps);
             const float v2 = finish_value<AMP>(a2, eps), v3 = finish_value<AMP>(a3, eps);
+            if (TO_SMEM) {
+                *reinterpret_cast<float4 *>(mtile + row * kFT + 4 * j) = make_float4(v0, v1, v2, v3);
+                continue;
+            }
+            char *orow = ob + static_cast<size_t>(static_cast<unsigned>(row)) * ors4;
             if (j < nf) *reinterpret_cast<float *>(orow) = v0;
             if (j + 8 < nf) *reinterpret_cast<float *>(orow + 32) = v1;
             if (j + 16 < nf) *reinterpret_cast<float *>(orow + 64) = v2;
             if (j + 24 < nf) *reinterpret_cast<float *>(orow + 96) = v3;
+        }
+    }
+}
+
+// Fused DCT-II + lifter on the log-mel tile mtile[n][32] (mfcc_from_log_mel, src/mfcc.rs:224-273) using the basis
+// symmetry B[c][n-1-i] = (-1)^c B[c][i]: fold the tile in place into E[i] = m[i] + m[n-1-i] (kept in row i) and
+// O[i] = m[i] - m[n-1-i] (kept in row n-1-i), then every coefficient needs n/2 instead of n multiply-adds. One warp
+// task = 4 coefficients of one parity x 32 frames (lane = frame); the half basis streams through the read-only path
+// as one warp-uniform 16-byte load per step. Requires n even (host falls back to the general epilogue otherwise).
+__device__ __forceinline__ void folded_dct_epilogue(const KParams &p, float *mtile, float *out_clip_frame, int nf, int warp, int lane,
+                                                    int tid) {
+    const int n = p.n_bins, half = n >> 1;
+    for (int idx = tid; idx < half * kFT; idx += kThreads) {
+        const int i = idx >> 5, c = idx & 31;
+        const float a = mtile[i * kFT + c], b = mtile[(n - 1 - i) * kFT + c];
+        mtile[i * kFT + c] = a + b;
+        mtile[(n - 1 - i) * kFT + c] = a - b;
+    }
+    __syncthreads();
+    const float4 *basis = static_cast<const float4 *>(p.dct_folded);
+    const float *lift = static_cast<const float *>(p.lifter);
+    const int col = frame_col(lane);
+    const bool live = lane < nf;
+    const int groups_even = ((p.n_mfcc + 1) / 2 + 3) / 4;        // tasks [0, groups_even) are even coefficients
+#pragma unroll 1
+    for (int task = warp; task < p.dct_tasks; task += kWarps) {
+        const bool odd = task >= groups_even;
+        const int g = odd ? task - groups_even : task;
+        const float *m = mtile + col + (odd ? (n - 1) * kFT : 0);
+        const int mstep = odd ? -kFT : kFT;
+        const float4 *b = basis + static_cast<long long>(task) * half;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 8
+        for (int i = 0; i < half; ++i) {
+            const float4 w = __ldg(b + i);
+            const float x = m[i * mstep];
+            a0 = fmaf(x, w.x, a0);
+            a1 = fmaf(x, w.y, a1);
+            a2 = fmaf(x, w.z, a2);
+            a3 = fmaf(x, w.w, a3);
+        }
+        const float acc[4] = {a0, a1, a2, a3};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = (odd ? 1 : 0) + 2 * (4 * g + k);
+            if (c < p.n_mfcc && c >= p.mfcc_row0 && live)
+                out_clip_frame[static_cast<long long>(c - p.mfcc_row0) * p.out_row_stride + lane] = acc[k] * __ldg(lift + c);
         }
     }
 }
@@ -216,11 +269,17 @@ __global__ void __launch_bounds__(kThreads, 2) k_r2c_fused_n400(const __grid_con
         pass2_finish(v, ptile, lane, warp);
         __syncthreads();
 
+        float *ocf = static_cast<float *>(p.out) + static_cast<long long>(cur_clip) * p.out_clip_stride + (f0 - p.out_frame_origin);
         if (SPARSE && p.output != SGX_OUT_MFCC) {
-            float *ocf = static_cast<float *>(p.out) + static_cast<long long>(cur_clip) * p.out_clip_stride + (f0 - p.out_frame_origin);
-            if (p.apply_db) sparse_quads_epilogue<2>(p, ptile, s_quads, s_qinfo, ocf, nf, warp, lane);
-            else if (p.amp == SGX_AMP_MAGNITUDE) sparse_quads_epilogue<1>(p, ptile, s_quads, s_qinfo, ocf, nf, warp, lane);
-            else sparse_quads_epilogue<0>(p, ptile, s_quads, s_qinfo, ocf, nf, warp, lane);
+            if (p.apply_db) sparse_quads_epilogue<2, false>(p, ptile, s_quads, s_qinfo, ocf, nullptr, nf, warp, lane);
+            else if (p.amp == SGX_AMP_MAGNITUDE) sparse_quads_epilogue<1, false>(p, ptile, s_quads, s_qinfo, ocf, nullptr, nf, warp, lane);
+            else sparse_quads_epilogue<0, false>(p, ptile, s_quads, s_qinfo, ocf, nullptr, nf, warp, lane);
+        } else if (SPARSE && p.dct_folded != nullptr) {
+            // fused mfcc(): mel -> dB (always has a floor here, src/mfcc.rs:371) -> folded DCT-II -> lifter
+            if (p.apply_db) sparse_quads_epilogue<2, true>(p, ptile, s_quads, s_qinfo, ocf, scratch, nf, warp, lane);
+            else sparse_quads_epilogue<0, true>(p, ptile, s_quads, s_qinfo, ocf, scratch, nf, warp, lane);
+            __syncthreads();
+            folded_dct_epilogue(p, scratch, ocf, nf, warp, lane, tid);
         } else {
             epilogue_lane_frames<float>(p, ptile, scratch, cur_clip, f0, nf, frame_col(lane));
         }

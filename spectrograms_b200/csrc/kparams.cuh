@@ -52,6 +52,8 @@ struct KParams {
     int mfcc_row0;        // 1 when c0 is dropped (!include_c0 && n_mfcc > 1), else 0
     const void *dct;      // T[n_mfcc][n_bins]
     const void *lifter;   // T[n_mfcc]
+    const void *dct_folded;   // T[tasks][n_bins/2][4]: even/odd-symmetric half basis, 4 coefficients per task (n_bins even), or null
+    int dct_tasks;            // number of (parity, 4-coefficient group) tasks
     // ---- shared-memory geometry chosen by the host
     int buf_elems;        // complex elements per ping-pong buffer
     int frame_stride;     // complex elements between frames in a buffer (>= L+1)

@@ -124,7 +124,9 @@ struct sgx_plan {
     std::vector<int> radix;
     // device tables
     void *d_window = nullptr, *d_tw = nullptr, *d_post = nullptr, *d_val = nullptr, *d_dense = nullptr;
-    void *d_dct = nullptr, *d_lifter = nullptr;
+    void *d_dct = nullptr, *d_lifter = nullptr, *d_dct_folded = nullptr;
+    std::vector<double> dct_folded;  // [tasks][n_mels/2][4]
+    int dct_tasks = 0;
     int *d_row_ptr = nullptr, *d_col = nullptr, *d_wofs = nullptr;
     std::vector<int> wofs;           // padded weight offset per row (fast sparse table)
     // generic-family geometry
@@ -146,7 +148,7 @@ struct sgx_plan {
         if (!on_device) return;
         int prev = -1;
         if (cudaGetDevice(&prev) == cudaSuccess && prev != device) cudaSetDevice(device); else prev = -1;
-        for (void *p : {d_window, d_tw, d_post, d_val, d_dense, d_dct, d_lifter}) if (p) cudaFree(p);
+        for (void *p : {d_window, d_tw, d_post, d_val, d_dense, d_dct, d_lifter, d_dct_folded}) if (p) cudaFree(p);
         if (d_row_ptr) cudaFree(d_row_ptr);
         if (d_col) cudaFree(d_col);
         if (d_wofs) cudaFree(d_wofs);
@@ -248,6 +250,25 @@ void select_family(sgx_plan &pl) {
     pl.fast400_sparse = pl.fast400 && csr && contiguous && static_cast<int>(pl.tab.n_bins) <= fast400_max_sparse_rows() &&
                         padded <= fast400_max_sparse_nnz();
     pl.kernel_name = pl.fast400 ? "r2c_fused_n400" : "r2c_fused_generic";
+    // folded DCT basis for the fused MFCC epilogue: B[c][n-1-i] = (-1)^c B[c][i] -> half basis, tasks of 4 coefficients of
+    // one parity: [task][i < n/2][4], even-coefficient tasks first
+    pl.dct_folded.clear();
+    pl.dct_tasks = 0;
+    if (pl.fast400_sparse && d.output == SGX_OUT_MFCC && pl.tab.n_bins % 2 == 0) {
+        const size_t n = pl.tab.n_bins, half = n / 2, nm = d.n_mfcc;
+        const size_t ge = ((nm + 1) / 2 + 3) / 4, go = (nm / 2 + 3) / 4;
+        pl.dct_tasks = static_cast<int>(ge + go);
+        pl.dct_folded.assign((ge + go) * half * 4, 0.0);
+        for (size_t task = 0; task < ge + go; ++task) {
+            const bool odd = task >= ge;
+            const size_t g = odd ? task - ge : task;
+            for (size_t k = 0; k < 4; ++k) {
+                const size_t c = (odd ? 1 : 0) + 2 * (4 * g + k);
+                if (c >= nm) continue;
+                for (size_t i = 0; i < half; ++i) pl.dct_folded[(task * half + i) * 4 + k] = pl.tab.dct[c * n + i];
+            }
+        }
+    }
 }
 
 void choose_generic_geometry(sgx_plan &pl) {
@@ -295,6 +316,7 @@ void ensure_device(sgx_plan &pl) {
     pl.d_dense = upload(pl.tab.dense, pl.f64);
     pl.d_dct = upload(pl.tab.dct, pl.f64);
     pl.d_lifter = upload(pl.tab.lifter, pl.f64);
+    pl.d_dct_folded = upload(pl.dct_folded, pl.f64);
     cudaDeviceProp prop;
     ck(cudaGetDeviceProperties(&prop, dev), "cudaGetDeviceProperties");
     pl.sm_count = prop.multiProcessorCount;
@@ -323,6 +345,7 @@ void fill_params(const sgx_plan &pl, KParams &p) {
     p.n_mfcc = static_cast<int>(d.n_mfcc);
     p.mfcc_row0 = (d.output == SGX_OUT_MFCC && !d.include_c0 && d.n_mfcc > 1) ? 1 : 0;
     p.dct = pl.d_dct; p.lifter = pl.d_lifter;
+    p.dct_folded = pl.d_dct_folded; p.dct_tasks = pl.dct_tasks;
     p.FT = pl.FT; p.buf_elems = pl.buf_elems; p.frame_stride = pl.frame_stride; p.tile_stride = pl.tile_stride;
 }
 
