@@ -11,8 +11,8 @@
 //                                   outputs k2 >= 10 are the conjugates of bins 400 - k: every output is a wanted bin,
 //                                   so bins 0..200 come out of 11 butterflies with nothing left to untangle.
 //
-// The 20-point DFT is a Good-Thomas 4 x 5 prime-factor butterfly: no internal twiddles, 224 flops-ish instructions,
-// pure register renaming. Everything here is __host__ __device__ so tests/test_fft400_core.py can run the exact task
+// The 20-point DFT is a Good-Thomas 4 x 5 prime-factor butterfly: no internal twiddles, pure register renaming, and --
+// written with Blackwell's packed FP32x2 instructions -- about 112 issue slots instead of 224. Everything here is __host__ __device__ so tests/test_fft400_core.py can run the exact task
 // functions on the CPU (the build container has no GPU) against the oracle before a kernel ever launches.
 #pragma once
 
@@ -55,16 +55,33 @@ struct Consts {
 SGX_HD int sig_word(int u) { return u + 2 * (u / kHop); }
 SGX_HD int frame_col(int f) { return ((f & 7) << 2) | (f >> 3); }
 
+// Packed FP32x2 arithmetic (Blackwell FADD2 / FMUL2 / FFMA2): one instruction works on a (re, im) register pair, and
+// the operand swizzle / per-half negate of the packed forms absorbs the +-i rotations of the butterflies, so a complex
+// add, a complex-by-real scale and a "t1 + (-i) t3" each cost ONE issue slot. Host builds (the CPU emulation test) get
+// the plain scalar definitions; both round every operation to nearest exactly once, so the results are identical.
+#ifdef __CUDA_ARCH__
+SGX_HD unsigned long long pk2(float2 v) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(v.x), "f"(v.y)); return r; }
+SGX_HD float2 upk2(unsigned long long v) { float2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
+SGX_HD float2 cadd(float2 a, float2 b) { unsigned long long r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a)), "l"(pk2(b))); return upk2(r); }
+SGX_HD float2 csub(float2 a, float2 b) { unsigned long long r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a)), "l"(pk2(b))); return upk2(r); }
+SGX_HD float2 cmul2(float2 a, float2 b) { unsigned long long r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a)), "l"(pk2(b))); return upk2(r); }
+SGX_HD float2 cfma2(float2 a, float2 b, float2 c) { unsigned long long r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pk2(a)), "l"(pk2(b)), "l"(pk2(c))); return upk2(r); }
+#else
 SGX_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 SGX_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+SGX_HD float2 cmul2(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+SGX_HD float2 cfma2(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+#endif
+SGX_HD float2 bc2(float s) { return make_float2(s, s); }
+SGX_HD float2 rot_mi(float2 v) { return make_float2(v.y, -v.x); }   // multiply by -i
 
 // in-place 4-point DFT (forward): (a,b,c,d) <- (X0,X1,X2,X3)
 SGX_HD void dft4(float2 &a, float2 &b, float2 &c, float2 &d) {
-    const float2 t0 = cadd(a, c), t1 = csub(a, c), t2 = cadd(b, d), t3 = csub(b, d);
+    const float2 t0 = cadd(a, c), t1 = csub(a, c), t2 = cadd(b, d), t3 = rot_mi(csub(b, d));
     a = cadd(t0, t2);
     c = csub(t0, t2);
-    b = make_float2(t1.x + t3.y, t1.y - t3.x);
-    d = make_float2(t1.x - t3.y, t1.y + t3.x);
+    b = cadd(t1, t3);
+    d = csub(t1, t3);
 }
 
 // in-place 5-point DFT (forward): (a0..a4) <- (X0..X4)
@@ -72,15 +89,15 @@ SGX_HD void dft5(float2 &a0, float2 &a1, float2 &a2, float2 &a3, float2 &a4) {
     constexpr float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;
     constexpr float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;
     const float2 p1 = cadd(a1, a4), m1 = csub(a1, a4), p2 = cadd(a2, a3), m2 = csub(a2, a3);
-    const float2 e1 = make_float2(a0.x + c1 * p1.x + c2 * p2.x, a0.y + c1 * p1.y + c2 * p2.y);
-    const float2 e2 = make_float2(a0.x + c2 * p1.x + c1 * p2.x, a0.y + c2 * p1.y + c1 * p2.y);
-    const float2 u1 = make_float2(s1 * m1.x + s2 * m2.x, s1 * m1.y + s2 * m2.y);
-    const float2 u2 = make_float2(s2 * m1.x - s1 * m2.x, s2 * m1.y - s1 * m2.y);
-    a0 = make_float2(a0.x + p1.x + p2.x, a0.y + p1.y + p2.y);
-    a1 = make_float2(e1.x + u1.y, e1.y - u1.x);   // e1 - i u1
-    a4 = make_float2(e1.x - u1.y, e1.y + u1.x);   // e1 + i u1
-    a2 = make_float2(e2.x + u2.y, e2.y - u2.x);   // e2 - i u2
-    a3 = make_float2(e2.x - u2.y, e2.y + u2.x);   // e2 + i u2
+    const float2 e1 = cfma2(bc2(c2), p2, cfma2(bc2(c1), p1, a0));
+    const float2 e2 = cfma2(bc2(c1), p2, cfma2(bc2(c2), p1, a0));
+    const float2 u1 = rot_mi(cfma2(bc2(s2), m2, cmul2(bc2(s1), m1)));    // -i (s1 m1 + s2 m2)
+    const float2 u2 = rot_mi(cfma2(bc2(-s1), m2, cmul2(bc2(s2), m1)));   // -i (s2 m1 - s1 m2)
+    a0 = cadd(cadd(a0, p1), p2);
+    a1 = cadd(e1, u1);
+    a4 = csub(e1, u1);
+    a2 = cadd(e2, u2);
+    a3 = csub(e2, u2);
 }
 
 // Good-Thomas 20 = 4 x 5: input sample n sits in v[n]; afterwards output bin k sits in v[reg_of_bin(k)].
@@ -102,8 +119,8 @@ SGX_HD void pass1_task(const float *__restrict__ sig, float *__restrict__ ybuf, 
 #pragma unroll
     for (int n1 = 0; n1 < 20; ++n1) {
         const float2 x = *reinterpret_cast<const float2 *>(s + 20 * n1 + 2 * (n1 / 8));
-        const float wa = c.win[20 * n1 + 2 * t], wb = c.win[20 * n1 + 2 * t + 1];
-        v[n1] = make_float2(x.x * wa, x.y * wb);      // sample * window[i] (src/spectrogram.rs:1319)
+        const float2 w = *reinterpret_cast<const float2 *>(&c.win[20 * n1 + 2 * t]);
+        v[n1] = cmul2(x, w);                          // sample * window[i] (src/spectrogram.rs:1319)
     }
     dft20(v);
     float *y = ybuf + kYFrameStride * f + 4 * t;      // complex index 2t -> word 4t
@@ -117,7 +134,9 @@ SGX_HD void pass1_task(const float *__restrict__ sig, float *__restrict__ ybuf, 
     for (int k1 = 1; k1 < 10; ++k1) {
         const float2 A = v[reg_of_bin(k1)], B = v[reg_of_bin(20 - k1)];
         // 2*Ya = A + conj(B) ; 2*Yb = (A - conj(B)) / i   (the 1/2 lives in tw2)
-        *reinterpret_cast<float4 *>(y + 40 * k1) = make_float4(A.x + B.x, A.y - B.y, A.y + B.y, B.x - A.x);
+        const float2 sa = cadd(A, make_float2(B.x, -B.y));                      // A + conj(B)
+        const float2 sb = cadd(make_float2(A.y, -A.x), make_float2(B.y, B.x));  // (A - conj(B)) / i
+        *reinterpret_cast<float4 *>(y + 40 * k1) = make_float4(sa.x, sa.y, sb.x, sb.y);
     }
 }
 
@@ -129,8 +148,9 @@ SGX_HD void pass2_load(const float *__restrict__ ybuf, const Consts &c, int f, i
     for (int j = 0; j < 10; ++j) {
         const float4 q = *reinterpret_cast<const float4 *>(y + 4 * j);
         const float2 w0 = c.tw2[k1][2 * j], w1 = c.tw2[k1][2 * j + 1];
-        v[2 * j] = make_float2(q.x * w0.x - q.y * w0.y, q.x * w0.y + q.y * w0.x);
-        v[2 * j + 1] = make_float2(q.z * w1.x - q.w * w1.y, q.z * w1.y + q.w * w1.x);
+        // q * w = q.x * (w.x, w.y) + q.y * (-w.y, w.x)
+        v[2 * j] = cfma2(bc2(q.y), make_float2(-w0.y, w0.x), cmul2(bc2(q.x), w0));
+        v[2 * j + 1] = cfma2(bc2(q.w), make_float2(-w1.y, w1.x), cmul2(bc2(q.z), w1));
     }
 }
 
@@ -141,7 +161,8 @@ SGX_HD void pass2_finish(float2 (&v)[20], float *__restrict__ ptile, int f, int 
 #pragma unroll
     for (int k2 = 0; k2 < 20; ++k2) {
         const float2 X = v[reg_of_bin(k2)];
-        const float pw = X.x * X.x + X.y * X.y;       // norm_sqr (src/spectrogram.rs:1332-1334)
+        const float2 sq = cmul2(X, X);
+        const float pw = sq.x + sq.y;                 // norm_sqr = re*re + im*im (src/spectrogram.rs:1332-1334)
         if (k2 < 10) {
             p[kFT * (k1 + 20 * k2)] = pw;             // bin k1 + 20 k2
         } else if (k2 == 10) {

@@ -6,8 +6,8 @@
 //             (src/spectrogram.rs:1309-1320) with no per-tap branch
 //   pass 1    warps 0..9 : window multiply + 20-point real-pair DFT in registers        (fft400_core.cuh)
 //   ----      one shared-memory exchange (Y[k1][n2], 11 x 20 complex per frame)
-//   pass 2    warps 0..10: twiddle + 20-point DFT in registers -> |X|^2 into the power tile P[bin][frame]
-//             (P aliases the Y buffer: a barrier separates the last Y read from the first P write)
+//   pass 2    warps 0..10: twiddle + 20-point DFT in registers -> |X|^2 into the power tile P[bin][frame], which reuses
+//             the tile's own signal buffer (its samples are dead after pass 1; the prefetch targets the other buffer)
 //   epilogue  sparse filterbank rows from a shared-memory table -> sqrt / dB -> 128-byte row stores; other mappings and
 //             the fused DCT-II take the general lane = frame epilogue (epilogue.cuh)
 //
@@ -28,9 +28,12 @@ namespace {
 
 using namespace f400;
 
-constexpr int kMaxNnz = 1536;      // sparse-table capacity in shared memory (padded weights)
-constexpr int kMaxRows = 256;      // rows incl. padding to whole quads
-constexpr int kQInfoInts = (kWarps + 1 + kMaxRows / 4 + 3) & ~3;
+// shared memory: two signal buffers, each big enough to be reused as the power tile of its tile once pass 1 has
+// consumed the samples (kPWords >= kSigWords), the Y exchange buffer, then the plan's sparse schedule (sized per plan).
+constexpr int kBufWords = kPWords > kSigWords ? kPWords : kSigWords;
+constexpr size_t kFixedSmemBytes = sizeof(float) * (2 * kBufWords + kYWords);
+constexpr int kPrefetchSplit = 40 * 32;       // float2 units of a tile (2680) prefetched by warp 10
+constexpr size_t kSmemBudget = (233472 - 2 * 1024) / 2;      // two CTAs per SM: 228 KB per SM, 1 KB reserved per CTA
 
 __device__ __forceinline__ void cp_async8(float *dst_smem, const float *src, int src_bytes) {
     const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(dst_smem));
@@ -41,22 +44,23 @@ __device__ __forceinline__ void cp_async_commit_wait_all() {
 }
 
 // stage one tile's samples [s0, s0 + 5360) of a clip into a padded signal buffer
-// (tid, nthr): the threads taking part -- the whole CTA for the first tile, one warp for the prefetches
-__device__ __forceinline__ void load_tile(float *sig, const float *x, long long s0, long long n, bool vec_ok, int tid, int nthr) {
+// float2 units j = first, first + step, ... < last of the tile are handled by the calling thread
+__device__ __forceinline__ void load_tile(float *sig, const float *x, long long s0, long long n, bool vec_ok, int first, int step,
+                                          int last) {
     if (vec_ok && s0 >= 0 && s0 + kTileSamples <= n) {
         // interior tile (all but the first / last tile of a clip): no bounds logic at all
         const float *src = x + s0;
 #pragma unroll 4
-        for (int j = tid; j < kTileSamples / 2; j += nthr) cp_async8(sig + 2 * j + 2 * (j / (kHop / 2)), src + 2 * j, 8);
+        for (int j = first; j < last; j += step) cp_async8(sig + 2 * j + 2 * (j / (kHop / 2)), src + 2 * j, 8);
     } else if (vec_ok) {
-        for (int j = tid; j < kTileSamples / 2; j += nthr) {
+        for (int j = first; j < last; j += step) {
             const long long s = s0 + 2 * j;
             const long long avail = n - s;                // samples available from s on
             const int bytes = (s < 0 || avail <= 0) ? 0 : (avail >= 2 ? 8 : 4);
             cp_async8(sig + 2 * j + 2 * (j / (kHop / 2)), bytes ? x + s : x, bytes);
         }
     } else {
-        for (int j = tid; j < kTileSamples / 2; j += nthr) {
+        for (int j = first; j < last; j += step) {
             const long long s = s0 + 2 * j;
             float2 v;
             v.x = (s >= 0 && s < n) ? __ldg(x + s) : 0.f;
@@ -200,13 +204,13 @@ template <bool SPARSE>
 __global__ void __launch_bounds__(kThreads, 2) k_r2c_fused_n400(const __grid_constant__ F400Params P) {
     extern __shared__ __align__(16) float smem[];
     float *sig0 = smem;
-    float *sig1 = sig0 + kSigWords;
-    float *ybuf = sig1 + kSigWords;
-    float *ptile = ybuf;                       // aliases the Y exchange buffer
-    float *scratch = ybuf + kPWords;           // log-mel tile of the MFCC path (rows * 32 <= kYWords - kPWords)
+    float *sig1 = sig0 + kBufWords;
+    float *ybuf = sig1 + kBufWords;
+    float *scratch = ybuf;                     // log-mel tile of the MFCC path: Y is dead once pass 2 is done
+    const int nq_smem = SPARSE ? __ldg(reinterpret_cast<const int *>(P.k.dense)) : 0;
     int4 *s_quads = reinterpret_cast<int4 *>(ybuf + kYWords);        // [4 * n_quads] {byte offset of P[c0], cnt, weights address, row}
-    int *s_qinfo = reinterpret_cast<int *>(s_quads + kMaxRows);      // [kWarps + 1] quad ranges per warp, then [n_quads] max cnt
-    float *s_w = reinterpret_cast<float *>(s_qinfo + kQInfoInts);    // weights, rows padded to multiples of 4
+    int *s_qinfo = reinterpret_cast<int *>(s_quads + 4 * nq_smem);   // [kWarps + 1] quad ranges per warp, then [n_quads] max cnt
+    float *s_w = reinterpret_cast<float *>(s_qinfo + ((kWarps + 1 + nq_smem + 3) & ~3));   // weights, rows padded to multiples of 4
     const KParams &p = P.k;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -240,12 +244,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_r2c_fused_n400(const __grid_con
     int buf = 0;
     if (clip < p.n_clips)
         load_tile(sig0, xbase + static_cast<long long>(clip) * p.clip_stride,
-                  (p.frame_begin + static_cast<long long>(tile) * kFT) * kHop - p.pad, p.n_samples, vec_ok, tid, kThreads);
+                  (p.frame_begin + static_cast<long long>(tile) * kFT) * kHop - p.pad, p.n_samples, vec_ok, tid, kThreads, kTileSamples / 2);
     for (; clip < p.n_clips; buf ^= 1) {
         const long long f0 = p.frame_begin + static_cast<long long>(tile) * kFT;
         const long long rem = p.frame_begin + p.frames_todo - f0;
         const int nf = rem < kFT ? static_cast<int>(rem) : kFT;
         float *sig = buf ? sig1 : sig0;
+        float *ptile = sig;                    // the signal buffer becomes this tile's power tile after pass 1
         const int cur_clip = clip;
 
         cp_async_commit_wait_all();
@@ -254,19 +259,21 @@ __global__ void __launch_bounds__(kThreads, 2) k_r2c_fused_n400(const __grid_con
         clip += step_clip;                     // next tile of this CTA
         tile += step_tile;
         if (tile >= tpc) { tile -= tpc; ++clip; }
-        // warp 10 has no pass-1 role: it prefetches the next tile into the other buffer while warps 0..9 run pass 1
+        // Prefetch of the next tile into the other buffer, overlapped with pass 1. Warp 10 has no pass-1 role and takes
+        // the first kPrefetchSplit float2 units; warps 0..9 share the rest, sized so that both kinds of warp issue about
+        // the same number of instructions in this phase.
+        const bool more = clip < p.n_clips;
+        const float *xn = xbase + static_cast<long long>(more ? clip : 0) * p.clip_stride;
+        const long long sn = (p.frame_begin + static_cast<long long>(tile) * kFT) * kHop - p.pad;
         if (warp < 10) {
             pass1_task(sig, ybuf, P.c, lane, warp);
-        } else if (clip < p.n_clips) {
-            load_tile(buf ? sig0 : sig1, xbase + static_cast<long long>(clip) * p.clip_stride,
-                      (p.frame_begin + static_cast<long long>(tile) * kFT) * kHop - p.pad, p.n_samples, vec_ok, lane, 32);
+            if (more) load_tile(buf ? sig0 : sig1, xn, sn, p.n_samples, vec_ok, kPrefetchSplit + tid, 320, kTileSamples / 2);
+        } else if (more) {
+            load_tile(buf ? sig0 : sig1, xn, sn, p.n_samples, vec_ok, lane, 32, kPrefetchSplit);
         }
         __syncthreads();
 
-        float2 v[20];
-        pass2_load(ybuf, P.c, lane, warp, v);
-        __syncthreads();                       // every Y value is in registers: P may overwrite the buffer
-        pass2_finish(v, ptile, lane, warp);
+        pass2_task(ybuf, ptile, P.c, lane, warp);     // samples are consumed: P overwrites the signal buffer
         __syncthreads();
 
         float *ocf = static_cast<float *>(p.out) + static_cast<long long>(cur_clip) * p.out_clip_stride + (f0 - p.out_frame_origin);
@@ -288,17 +295,20 @@ __global__ void __launch_bounds__(kThreads, 2) k_r2c_fused_n400(const __grid_con
 
 }  // namespace
 
-size_t fast400_smem_bytes() {
-    return sizeof(float) * (2 * f400::kSigWords + f400::kYWords) + sizeof(int4) * kMaxRows + sizeof(int) * kQInfoInts +
-           sizeof(float) * (kMaxNnz + 64);
+// dynamic shared memory of a launch whose sparse schedule has n_quads quads and padded_weights weights (0, 0: none)
+size_t fast400_smem_bytes(int n_quads, int padded_weights) {
+    if (n_quads == 0) return kFixedSmemBytes;
+    return kFixedSmemBytes + sizeof(int4) * 4 * n_quads + sizeof(int) * ((f400::kWarps + 1 + n_quads + 3) & ~3) +
+           sizeof(float) * (padded_weights + 64);
 }
-int fast400_max_scratch_rows() { return (f400::kYWords - f400::kPWords) / 32; }
-int fast400_max_sparse_rows() { return kMaxRows; }
-int fast400_max_sparse_nnz() { return kMaxNnz; }
+// the sparse schedule is used only while two CTAs still fit on an SM
+bool fast400_sparse_fits(int n_quads, int padded_weights) { return fast400_smem_bytes(n_quads, padded_weights) <= kSmemBudget; }
+int fast400_max_scratch_rows() { return f400::kYWords / 32; }
 int fast400_warps() { return f400::kWarps; }
 
 
-cudaError_t launch_fast400(const KParams &p, const float *window_f32, bool sparse_table, int sm_count, cudaStream_t stream) {
+cudaError_t launch_fast400(const KParams &p, const float *window_f32, bool sparse_table, int n_quads, int padded_weights,
+                           int sm_count, cudaStream_t stream) {
     static_assert(sizeof(F400Params) <= 4096, "kernel parameter block must fit the classic 4 KiB limit");
     F400Params P;
     P.k = p;
@@ -316,7 +326,7 @@ cudaError_t launch_fast400(const KParams &p, const float *window_f32, bool spars
     const long long total = static_cast<long long>(p.n_clips) * P.k.tiles_per_clip;
     if (total <= 0) return cudaSuccess;
     const long long grid = std::min<long long>(total, 2LL * sm_count);     // persistent: 2 CTAs per SM
-    const size_t smem = fast400_smem_bytes();
+    const size_t smem = sparse_table ? fast400_smem_bytes(n_quads, padded_weights) : fast400_smem_bytes(0, 0);
     cudaError_t e;
     if (sparse_table) {
         e = cudaFuncSetAttribute(k_r2c_fused_n400<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));

@@ -17,11 +17,11 @@ cudaError_t launch_generic(const KParams &p, bool f64, size_t smem_bytes, cudaSt
 // p.buf_elems is reused as the "8-byte aligned input" flag; window_f32 is the host copy of the plan window.
 // sparse_table: serve mel / loghz rows from a shared-memory copy of the CSR table (needs rows <= max_sparse_rows and
 // nnz <= max_sparse_nnz); sm_count sizes the persistent grid (2 CTAs per SM).
-cudaError_t launch_fast400(const KParams &p, const float *window_f32, bool sparse_table, int sm_count, cudaStream_t stream);
-size_t fast400_smem_bytes();
+cudaError_t launch_fast400(const KParams &p, const float *window_f32, bool sparse_table, int n_quads, int padded_weights,
+                           int sm_count, cudaStream_t stream);
+size_t fast400_smem_bytes(int n_quads, int padded_weights);
+bool fast400_sparse_fits(int n_quads, int padded_weights);
 int fast400_max_scratch_rows();
-int fast400_max_sparse_rows();
-int fast400_max_sparse_nnz();
 int fast400_warps();
 
 // standalone mfcc_from_log_mel (kernel_mfcc.cu): log_mel [n_clips][n_mels][n_frames] -> out [n_clips][rows][n_frames]

@@ -139,6 +139,7 @@ struct sgx_plan {
     std::string kernel_name = "r2c_fused_generic";
     bool fast400 = false;            // eligible for r2c_fused_n400
     bool fast400_sparse = false;     // ... with the shared-memory sparse table
+    int sparse_quads = 0, sparse_weights = 0;
     int sm_count = 148;
     std::vector<float> window_f32;
     // staging for host-pointer calls
@@ -245,10 +246,10 @@ void select_family(sgx_plan &pl) {
         blob[1 + W] = idx;
         pl.wofs = blob;
         padded = std::max(padded, 4);
-        if (static_cast<int>(order.size()) > fast400_max_sparse_rows()) contiguous = false;
+        pl.sparse_quads = nq;
+        pl.sparse_weights = padded;
     }
-    pl.fast400_sparse = pl.fast400 && csr && contiguous && static_cast<int>(pl.tab.n_bins) <= fast400_max_sparse_rows() &&
-                        padded <= fast400_max_sparse_nnz();
+    pl.fast400_sparse = pl.fast400 && csr && contiguous && fast400_sparse_fits(pl.sparse_quads, pl.sparse_weights);
     pl.kernel_name = pl.fast400 ? "r2c_fused_n400" : "r2c_fused_generic";
     // folded DCT basis for the fused MFCC epilogue: B[c][n-1-i] = (-1)^c B[c][i] -> half basis, tasks of 4 coefficients of
     // one parity: [task][i < n/2][4], even-coefficient tasks first
@@ -380,7 +381,7 @@ void run_device(sgx_plan &pl, const void *d_samples, size_t n_clips, size_t n_sa
             // 8-byte vector loads need an 8-byte aligned base and an even clip stride
             q.buf_elems = (reinterpret_cast<uintptr_t>(q.samples) % 8 == 0 && clip_stride % 2 == 0) ? 1 : 0;
             if (pl.fast400_sparse) q.dense = pl.d_wofs;      // sparse mappings do not use `dense`: carries the weight offsets
-            ck(launch_fast400(q, pl.window_f32.data(), pl.fast400_sparse, pl.sm_count, stream), "kernel launch (r2c_fused_n400)");
+            ck(launch_fast400(q, pl.window_f32.data(), pl.fast400_sparse, pl.sparse_quads, pl.sparse_weights, pl.sm_count, stream), "kernel launch (r2c_fused_n400)");
         } else {
             ck(launch_generic(q, pl.f64, pl.smem_bytes, stream), "kernel launch (r2c_fused_generic)");
         }
