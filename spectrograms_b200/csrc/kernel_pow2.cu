@@ -1,0 +1,318 @@
+// kernel_pow2.cu -- "r2c_fused_pow2": power-of-two n_fft (256 .. 8192), f32 and f64 (BASELINE configs 0, 2 and 4).
+//
+// One CTA = FT consecutive frames of one clip; a frame's packed M = n_fft/2 complex FFT is shared by TPF = M/16
+// threads, each holding 16 complex values in registers:
+//
+//   load      samples straight from global memory (coalesced 8/16-byte pairs, zero outside the clip = centre padding,
+//             src/spectrogram.rs:1309-1320) times the window, packed as z[n] = x[2n] + i x[2n+1]
+//   passes    Stockham autosort with register radix-16 butterflies (one per thread and pass) and a last pass of radix
+//             M / 16^p in {1, 2, 4, 8} (16/r butterflies per thread). The exchange between passes goes through ONE
+//             shared buffer per frame (read everything - barrier - write everything), padded by one element per 16 so
+//             that both the strided writes of the early passes and the contiguous reads are conflict free.
+//   post      split of the packed spectrum (realfft-style): one twiddle multiply serves bins k and M-k
+//   epilogue  |X|^2 (or X) tile -> mapping -> scaling -> (DCT) -> store            (epilogue.cuh)
+//
+// Compared with the generic family this cuts the shared-memory round trips from log4(M) to 2-3 and removes every
+// runtime division from the index math (all radices, strides and shifts are template constants).
+#include "epilogue.cuh"
+#include "launch.hpp"
+
+namespace sgx {
+namespace {
+
+template <typename T> struct Cx { T x, y; };
+template <typename T> __device__ __forceinline__ Cx<T> operator+(Cx<T> a, Cx<T> b) { return {a.x + b.x, a.y + b.y}; }
+template <typename T> __device__ __forceinline__ Cx<T> operator-(Cx<T> a, Cx<T> b) { return {a.x - b.x, a.y - b.y}; }
+template <typename T> __device__ __forceinline__ Cx<T> operator*(Cx<T> a, Cx<T> b) { return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+template <typename T> __device__ __forceinline__ Cx<T> mul_mi(Cx<T> a) { return {a.y, -a.x}; }   // * (-i)
+
+template <typename T> __device__ __forceinline__ void dft2(Cx<T> &a, Cx<T> &b) { const Cx<T> t = a - b; a = a + b; b = t; }
+template <typename T> __device__ __forceinline__ void dft4(Cx<T> &a, Cx<T> &b, Cx<T> &c, Cx<T> &d) {
+    const Cx<T> t0 = a + c, t1 = a - c, t2 = b + d, t3 = mul_mi(b - d);
+    a = t0 + t2; c = t0 - t2; b = t1 + t3; d = t1 - t3;
+}
+
+// forward DFT of v[0..R-1] in natural order, in place
+template <typename T, int R> struct Dft;
+template <typename T> struct Dft<T, 1> { static __device__ __forceinline__ void run(Cx<T> *) {} };
+template <typename T> struct Dft<T, 2> { static __device__ __forceinline__ void run(Cx<T> *v) { dft2(v[0], v[1]); } };
+template <typename T> struct Dft<T, 4> { static __device__ __forceinline__ void run(Cx<T> *v) { dft4(v[0], v[1], v[2], v[3]); } };
+template <typename T> struct Dft<T, 8> {
+    static __device__ __forceinline__ void run(Cx<T> *v) {
+        // n = j + 2 n1: A_j = DFT4 over n1; X[k1] = A0[k1] + W8^k1 A1[k1], X[k1+4] = A0[k1] - W8^k1 A1[k1]
+        Cx<T> a0 = v[0], a1 = v[2], a2 = v[4], a3 = v[6], b0 = v[1], b1 = v[3], b2 = v[5], b3 = v[7];
+        dft4(a0, a1, a2, a3);
+        dft4(b0, b1, b2, b3);
+        const T h = T(0.70710678118654752440084436210485);
+        b1 = {h * (b1.x + b1.y), h * (b1.y - b1.x)};     // * W8^1
+        b2 = mul_mi(b2);                                  // * W8^2
+        b3 = {h * (b3.y - b3.x), -h * (b3.x + b3.y)};    // * W8^3
+        v[0] = a0 + b0; v[4] = a0 - b0; v[1] = a1 + b1; v[5] = a1 - b1;
+        v[2] = a2 + b2; v[6] = a2 - b2; v[3] = a3 + b3; v[7] = a3 - b3;
+    }
+};
+template <typename T> struct Dft<T, 16> {
+    static __device__ __forceinline__ void run(Cx<T> *v) {
+        // n = j + 4 n1: A_j[k1] = DFT4 over n1 of v[j + 4 n1]; X[k1 + 4 k2] = DFT4 over j of W16^(j k1) A_j[k1]
+        const T c = T(0.92387953251128675612818318939679), s = T(0.38268343236508977172845998403040);
+        const T h = T(0.70710678118654752440084436210485);
+        Cx<T> a[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            a[j][0] = v[j]; a[j][1] = v[j + 4]; a[j][2] = v[j + 8]; a[j][3] = v[j + 12];
+            dft4(a[j][0], a[j][1], a[j][2], a[j][3]);
+        }
+        const Cx<T> w1 = {c, -s}, w2 = {h, -h}, w3 = {s, -c}, w6 = {-h, -h}, w9 = {-c, s};
+        a[1][1] = a[1][1] * w1; a[1][2] = a[1][2] * w2; a[1][3] = a[1][3] * w3;
+        a[2][1] = a[2][1] * w2; a[2][2] = mul_mi(a[2][2]); a[2][3] = a[2][3] * w6;
+        a[3][1] = a[3][1] * w3; a[3][2] = a[3][2] * w6; a[3][3] = a[3][3] * w9;
+#pragma unroll
+        for (int k1 = 0; k1 < 4; ++k1) {
+            dft4(a[0][k1], a[1][k1], a[2][k1], a[3][k1]);
+            v[k1] = a[0][k1]; v[k1 + 4] = a[1][k1]; v[k1 + 8] = a[2][k1]; v[k1 + 12] = a[3][k1];
+        }
+    }
+};
+
+__host__ __device__ constexpr int pad16(int i) { return i + (i >> 4); }
+
+// One Stockham pass of radix R with accumulated length CUR on a frame's M-point buffer; the thread owns butterflies
+// b = t + TPF*u (u < 16/R). v[16] is the thread's register file for the whole pass: load - (CTA barrier) - store.
+template <typename T, int M, int R, int CUR>
+__device__ __forceinline__ void pass_load(const Cx<T> *z, const Cx<T> *__restrict__ tw, int t, Cx<T> *v) {
+    constexpr int TPF = M / 16, B = M / R, MM = M / (CUR * R);
+#pragma unroll
+    for (int u = 0; u < 16 / R; ++u) {
+        const int b = t + TPF * u;
+        const int q = b & (CUR - 1);
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            Cx<T> x = z[pad16(j * B + b)];
+            if (CUR > 1 && j > 0) x = x * tw[j * q * MM];      // W_{CUR*R}^{j q} = W_M^{j q MM}
+            v[u * R + j] = x;
+        }
+    }
+}
+template <typename T, int M, int R, int CUR>
+__device__ __forceinline__ void pass_store(Cx<T> *z, int t, Cx<T> *v) {
+    constexpr int TPF = M / 16;
+#pragma unroll
+    for (int u = 0; u < 16 / R; ++u) {
+        const int b = t + TPF * u;
+        const int q = b & (CUR - 1), i = b / CUR;
+        Dft<T, R>::run(v + u * R);
+#pragma unroll
+        for (int k = 0; k < R; ++k) z[pad16((i * R + k) * CUR + q)] = v[u * R + k];
+    }
+}
+
+template <int M> struct Radices {          // M = 16^P16 * LAST, LAST in {1, 2, 4, 8}
+    static constexpr int P16 = M >= 4096 ? 3 : (M >= 256 ? 2 : 1);
+    static constexpr int LAST = M / (P16 == 3 ? 4096 : (P16 == 2 ? 256 : 16));
+};
+
+template <typename T> __device__ __forceinline__ Cx<T> ldg_cx(const Cx<T> *p);
+template <> __device__ __forceinline__ Cx<float> ldg_cx<float>(const Cx<float> *p) {
+    const float2 v = __ldg(reinterpret_cast<const float2 *>(p));
+    return {v.x, v.y};
+}
+template <> __device__ __forceinline__ Cx<double> ldg_cx<double>(const Cx<double> *p) {
+    const double2 v = __ldg(reinterpret_cast<const double2 *>(p));
+    return {v.x, v.y};
+}
+
+template <typename T, int M, int FT>
+__global__ void __launch_bounds__(FT *(M / 16), sizeof(T) == 4 ? 4 : 2) k_r2c_fused_pow2(const __grid_constant__ KParams p) {
+    constexpr int TPF = M / 16, N = 2 * M;
+    constexpr int ZS = pad16(M) + 2;                 // complex elements per frame buffer (M+1 spectrum bins fit too)
+    using C = Cx<T>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C *zbuf = reinterpret_cast<C *>(smem_raw);
+
+    const int tid = threadIdx.x;
+    const int fl = tid / TPF, t = tid - fl * TPF;    // frame within the tile, thread within the frame
+    const int clip = blockIdx.x / p.tiles_per_clip;
+    const int tile = blockIdx.x - clip * p.tiles_per_clip;
+    const long long f0 = p.frame_begin + static_cast<long long>(tile) * FT;
+    const long long rem = p.frame_begin + p.frames_todo - f0;
+    const int nf = rem < FT ? static_cast<int>(rem) : FT;
+    C *z = zbuf + fl * ZS;
+
+    const T *x = static_cast<const T *>(p.samples) + static_cast<long long>(clip) * p.clip_stride;
+    const T *win = static_cast<const T *>(p.window);
+    const C *tw = static_cast<const C *>(p.tw);
+    C v[16];
+
+    // ---- load + window + first pass (CUR = 1: no twiddles). Element n of the packed frame = samples 2n, 2n+1.
+    {
+        constexpr int R = 16, B = M / R;
+        const long long base = (f0 + fl) * p.hop - p.pad;
+        const bool vec_ok = p.buf_elems != 0;
+        if (vec_ok && base >= 0 && base + N <= p.n_samples) {
+            // interior frame (all but the first / last few of a clip): no bounds logic
+            const C *xf = reinterpret_cast<const C *>(x + base) + t;
+            const C *wf = reinterpret_cast<const C *>(win) + t;
+#pragma unroll
+            for (int j = 0; j < R; ++j) v[j] = ldg_cx<T>(xf + j * B);
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                const C w = ldg_cx<T>(wf + j * B);
+                v[j] = {v[j].x * w.x, v[j].y * w.y};
+            }
+        } else {
+#pragma unroll 1
+            for (int j = 0; j < R; ++j) {
+                const int n = j * B + t;
+                const long long s0 = base + 2 * n;
+                const T a = (s0 >= 0 && s0 < p.n_samples) ? __ldg(x + s0) : T(0);
+                const T b = (s0 + 1 >= 0 && s0 + 1 < p.n_samples) ? __ldg(x + s0 + 1) : T(0);
+                v[j] = {a * __ldg(win + 2 * n), b * __ldg(win + 2 * n + 1)};
+            }
+        }
+        pass_store<T, M, 16, 1>(z, t, v);
+    }
+    __syncthreads();
+    if constexpr (Radices<M>::P16 >= 2) {
+        pass_load<T, M, 16, 16>(z, tw, t, v);
+        __syncthreads();
+        pass_store<T, M, 16, 16>(z, t, v);
+        __syncthreads();
+    }
+    if constexpr (Radices<M>::P16 >= 3) {
+        pass_load<T, M, 16, 256>(z, tw, t, v);
+        __syncthreads();
+        pass_store<T, M, 16, 256>(z, t, v);
+        __syncthreads();
+    }
+    if constexpr (Radices<M>::LAST > 1) {
+        constexpr int CUR = M / Radices<M>::LAST;
+        pass_load<T, M, Radices<M>::LAST, CUR>(z, tw, t, v);
+        __syncthreads();
+        pass_store<T, M, Radices<M>::LAST, CUR>(z, t, v);
+        __syncthreads();
+    }
+
+    // ---- post pass: X[k] = E + W_N^k O, X[M-k] = conj(E - W_N^k O); thread owns k = t + TPF*u (u < 8), plus k = M/2
+    //      and k = 0 / M on thread 0. Values are held in registers across the barrier because the tile may alias z.
+    const C *post = static_cast<const C *>(p.post);
+    C xa[8], xb[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int k = t + TPF * u;                 // 0 .. M/2 - 1
+        if (k == 0) {
+            const C z0 = z[0];
+            xa[u] = {z0.x + z0.y, T(0)};           // bin 0
+            xb[u] = {z0.x - z0.y, T(0)};           // bin M
+        } else {
+            const C a = z[pad16(k)], b = z[pad16(M - k)];
+            const C ev = {T(0.5) * (a.x + b.x), T(0.5) * (a.y - b.y)};
+            const C od = {T(0.5) * (a.y + b.y), T(0.5) * (b.x - a.x)};
+            const C wo = od * ldg_cx<T>(post + k);
+            xa[u] = ev + wo;                       // bin k
+            const C d = ev - wo;
+            xb[u] = {d.x, -d.y};                   // bin M - k
+        }
+    }
+    C xm = {T(0), T(0)};
+    if (t == 0) {                                  // bin M/2: E and O are both Z[M/2]-derived, W_N^(M/2) = -i
+        const C a = z[pad16(M / 2)];
+        xm = {a.x, -a.y};
+    }
+    __syncthreads();
+
+    if (p.output == SGX_OUT_COMPLEX_STFT) {
+        typename Cplx<T>::type *S = reinterpret_cast<typename Cplx<T>::type *>(zbuf) + fl * p.frame_stride;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int k = t + TPF * u;
+            S[k] = mk<T>(xa[u].x, xa[u].y);
+            S[M - k] = mk<T>(xb[u].x, xb[u].y);
+        }
+        if (t == 0) S[M / 2] = mk<T>(xm.x, xm.y);
+        __syncthreads();
+        epilogue_complex<T>(p, reinterpret_cast<typename Cplx<T>::type *>(zbuf), clip, f0, nf);
+        return;
+    }
+    T *P = reinterpret_cast<T *>(zbuf);
+    T *pf = P + fl * p.tile_stride;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int k = t + TPF * u;
+        pf[k] = xa[u].x * xa[u].x + xa[u].y * xa[u].y;      // norm_sqr (src/spectrogram.rs:1332-1334)
+        pf[M - k] = xb[u].x * xb[u].x + xb[u].y * xb[u].y;
+    }
+    if (t == 0) pf[M / 2] = xm.x * xm.x + xm.y * xm.y;
+    __syncthreads();
+    if (FT <= 8 && p.output == SGX_OUT_SPECTROGRAM && (p.mapping == SGX_MAP_MEL || p.mapping == SGX_MAP_LOGHZ)) {
+        // small tiles: one thread per filterbank row, all FT frames of the tile in registers -- every weight / column
+        // index is loaded once per FT outputs. Same ascending-column, un-fused arithmetic as SparseMatrix::multiply_vec.
+        const T eps = static_cast<T>(p.eps);
+        const T *val = static_cast<const T *>(p.val);
+        T *out = static_cast<T *>(p.out) + static_cast<long long>(clip) * p.out_clip_stride + (f0 - p.out_frame_origin);
+        for (int row = tid; row < p.n_bins; row += FT * TPF) {
+            const int e0 = __ldg(p.row_ptr + row), e1 = __ldg(p.row_ptr + row + 1);
+            T acc[FT];
+#pragma unroll
+            for (int f = 0; f < FT; ++f) acc[f] = T(0);
+            for (int e = e0; e < e1; ++e) {
+                const T w = __ldg(val + e);
+                const T *pc = P + __ldg(p.col + e);
+#pragma unroll
+                for (int f = 0; f < FT; ++f) acc[f] = t_add_rn(acc[f], t_mul_rn(w, pc[f * p.tile_stride]));
+            }
+            T *orow = out + static_cast<long long>(row) * p.out_row_stride;
+#pragma unroll
+            for (int f = 0; f < FT; ++f)
+                if (f < nf) orow[f] = amp_scale<T>(acc[f], p.amp, p.apply_db, eps);
+        }
+        return;
+    }
+    // scratch for the fused-MFCC log-mel tile sits behind the power tile (host sizes the buffer for it)
+    epilogue_from_power<T>(p, P, P + FT * p.tile_stride, clip, f0, nf);
+    (void)N;
+}
+
+template <typename T, int M, int FT>
+cudaError_t launch_one(const KParams &p, size_t smem, cudaStream_t stream) {
+    const long long grid = static_cast<long long>(p.n_clips) * p.tiles_per_clip;
+    if (grid <= 0) return cudaSuccess;
+    if (grid > 2147483647LL) return cudaErrorInvalidConfiguration;
+    cudaError_t e = cudaFuncSetAttribute(k_r2c_fused_pow2<T, M, FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    k_r2c_fused_pow2<T, M, FT><<<static_cast<unsigned>(grid), FT *(M / 16), smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+// frames per tile: ~256 threads per CTA (f32) / 128-256 (f64)
+constexpr int ft_of(int M, bool f64) {
+    const int tpf = M / 16;
+    const int want = f64 ? 256 : 256;
+    const int ft = want / tpf;
+    return ft < 1 ? 1 : (ft > 32 ? 32 : ft);
+}
+
+}  // namespace
+
+bool pow2_supported(size_t n_fft) {
+    return n_fft >= 256 && n_fft <= 8192 && (n_fft & (n_fft - 1)) == 0;
+}
+int pow2_frames_per_tile(size_t n_fft, bool f64) { return ft_of(static_cast<int>(n_fft / 2), f64); }
+int pow2_frame_elems(size_t n_fft) { return pad16(static_cast<int>(n_fft / 2)) + 2; }
+
+cudaError_t launch_pow2(const KParams &p, bool f64, size_t smem, cudaStream_t stream) {
+#define SGX_POW2_CASE(MM)                                                                         \
+    case MM:                                                                                      \
+        return f64 ? launch_one<double, MM, ft_of(MM, true)>(p, smem, stream) : launch_one<float, MM, ft_of(MM, false)>(p, smem, stream);
+    switch (p.n_fft / 2) {
+        SGX_POW2_CASE(128)
+        SGX_POW2_CASE(256)
+        SGX_POW2_CASE(512)
+        SGX_POW2_CASE(1024)
+        SGX_POW2_CASE(2048)
+        SGX_POW2_CASE(4096)
+        default: return cudaErrorInvalidValue;
+    }
+#undef SGX_POW2_CASE
+}
+
+}  // namespace sgx

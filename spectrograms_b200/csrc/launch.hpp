@@ -24,6 +24,13 @@ bool fast400_sparse_fits(int n_quads, int padded_weights);
 int fast400_max_scratch_rows();
 int fast400_warps();
 
+// r2c_fused_pow2: n_fft = 256 .. 8192 (powers of two), f32 / f64 (kernel_pow2.cu). p.FT, p.frame_stride, p.tile_stride and
+// p.tiles_per_clip must be set from the helpers below; p.buf_elems is the "vector loads allowed" flag.
+bool pow2_supported(size_t n_fft);
+int pow2_frames_per_tile(size_t n_fft, bool f64);
+int pow2_frame_elems(size_t n_fft);
+cudaError_t launch_pow2(const KParams &p, bool f64, size_t smem_bytes, cudaStream_t stream);
+
 // standalone mfcc_from_log_mel (kernel_mfcc.cu): log_mel [n_clips][n_mels][n_frames] -> out [n_clips][rows][n_frames]
 cudaError_t launch_mfcc(bool f64, const void *log_mel, void *out, long long n_clips, int n_mels, long long n_frames,
                         int n_mfcc, int row0, const void *dct, const void *lifter, cudaStream_t stream);

@@ -138,6 +138,9 @@ struct sgx_plan {
     size_t last_launches = 0;
     std::string kernel_name = "r2c_fused_generic";
     bool fast400 = false;            // eligible for r2c_fused_n400
+    bool pow2 = false;               // eligible for r2c_fused_pow2
+    int pow2_ft = 1, pow2_frame_stride = 0, pow2_tile_stride = 0;
+    size_t pow2_smem = 0;
     bool fast400_sparse = false;     // ... with the shared-memory sparse table
     int sparse_quads = 0, sparse_weights = 0;
     int sm_count = 148;
@@ -187,6 +190,23 @@ void select_family(sgx_plan &pl) {
     if (pl.fast400) {
         pl.window_f32.resize(d.n_fft);
         for (size_t i = 0; i < d.n_fft; ++i) pl.window_f32[i] = static_cast<float>(pl.tab.window[i]);
+    }
+    // power-of-two family
+    pl.pow2 = false;
+    if (!pl.fast400 && pow2_supported(d.n_fft)) {
+        const size_t es = pl.esize;
+        const int ft = pow2_frames_per_tile(d.n_fft, pl.f64);
+        const size_t zs = static_cast<size_t>(pow2_frame_elems(d.n_fft));
+        size_t ts = std::max(pl.tab.out_len, pl.tab.n_bins);
+        if (ts % 2 == 0) ts += 1;
+        const size_t smem = std::max(ft * zs * 2 * es, 2 * ft * ts * es);
+        if (smem <= 200 * 1024) {
+            pl.pow2 = true;
+            pl.pow2_ft = ft;
+            pl.pow2_frame_stride = static_cast<int>(zs);
+            pl.pow2_tile_stride = static_cast<int>(ts);
+            pl.pow2_smem = smem;
+        }
     }
     const bool csr = d.mapping == SGX_MAP_MEL || d.mapping == SGX_MAP_LOGHZ;
     // The shared-memory sparse schedule needs rows with contiguous columns (mel triangles, loghz pairs). Rows are sorted
@@ -250,7 +270,7 @@ void select_family(sgx_plan &pl) {
         pl.sparse_weights = padded;
     }
     pl.fast400_sparse = pl.fast400 && csr && contiguous && fast400_sparse_fits(pl.sparse_quads, pl.sparse_weights);
-    pl.kernel_name = pl.fast400 ? "r2c_fused_n400" : "r2c_fused_generic";
+    pl.kernel_name = pl.fast400 ? "r2c_fused_n400" : pl.pow2 ? "r2c_fused_pow2" : "r2c_fused_generic";
     // folded DCT basis for the fused MFCC epilogue: B[c][n-1-i] = (-1)^c B[c][i] -> half basis, tasks of 4 coefficients of
     // one parity: [task][i < n/2][4], even-coefficient tasks first
     pl.dct_folded.clear();
@@ -366,7 +386,7 @@ void run_device(sgx_plan &pl, const void *d_samples, size_t n_clips, size_t n_sa
     p.out_row_stride = out_row_stride;
     p.out_clip_stride = out_clip_stride;
     p.out_frame_origin = frame_begin;
-    const int tile_frames = (pl.fast400 && !pl.force_generic) ? 32 : p.FT;
+    const int tile_frames = pl.force_generic ? p.FT : pl.fast400 ? 32 : pl.pow2 ? pl.pow2_ft : p.FT;
     p.tiles_per_clip = static_cast<int>((frames_todo + tile_frames - 1) / tile_frames);
     // the grid is limited to 2^31-1 CTAs: split very large batches
     const long long max_clips = std::max<long long>(1, 2000000000LL / std::max(1, p.tiles_per_clip));
@@ -382,6 +402,14 @@ void run_device(sgx_plan &pl, const void *d_samples, size_t n_clips, size_t n_sa
             q.buf_elems = (reinterpret_cast<uintptr_t>(q.samples) % 8 == 0 && clip_stride % 2 == 0) ? 1 : 0;
             if (pl.fast400_sparse) q.dense = pl.d_wofs;      // sparse mappings do not use `dense`: carries the weight offsets
             ck(launch_fast400(q, pl.window_f32.data(), pl.fast400_sparse, pl.sparse_quads, pl.sparse_weights, pl.sm_count, stream), "kernel launch (r2c_fused_n400)");
+        } else if (pl.pow2 && !pl.force_generic) {
+            q.FT = pl.pow2_ft;
+            q.frame_stride = pl.pow2_frame_stride;
+            q.tile_stride = pl.pow2_tile_stride;
+            // vector loads of (x[2n], x[2n+1]) pairs need pair-aligned addresses: aligned base, even stride, even hop and pad
+            q.buf_elems = (reinterpret_cast<uintptr_t>(q.samples) % (2 * pl.esize) == 0 && clip_stride % 2 == 0 &&
+                           pl.desc.hop_size % 2 == 0 && q.pad % 2 == 0) ? 1 : 0;
+            ck(launch_pow2(q, pl.f64, pl.pow2_smem, stream), "kernel launch (r2c_fused_pow2)");
         } else {
             ck(launch_generic(q, pl.f64, pl.smem_bytes, stream), "kernel launch (r2c_fused_generic)");
         }
@@ -499,7 +527,7 @@ sgx_status sgx_plan_filterbank(const sgx_plan *plan, double *dense_out, size_t *
 
 const char *sgx_plan_kernel_name(const sgx_plan *plan) {
     if (!plan) return "";
-    return (plan->force_generic || !plan->fast400) ? "r2c_fused_generic" : plan->kernel_name.c_str();
+    return plan->force_generic ? "r2c_fused_generic" : plan->kernel_name.c_str();
 }
 size_t sgx_plan_last_launch_count(const sgx_plan *plan) { return plan ? plan->last_launches : 0; }
 sgx_status sgx_plan_force_generic(sgx_plan *plan, int force) {
