@@ -21,9 +21,19 @@ namespace sgx {
 namespace {
 
 template <typename T> struct Cx { T x, y; };
-template <typename T> __device__ __forceinline__ Cx<T> operator+(Cx<T> a, Cx<T> b) { return {a.x + b.x, a.y + b.y}; }
-template <typename T> __device__ __forceinline__ Cx<T> operator-(Cx<T> a, Cx<T> b) { return {a.x - b.x, a.y - b.y}; }
-template <typename T> __device__ __forceinline__ Cx<T> operator*(Cx<T> a, Cx<T> b) { return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+// f32: Blackwell packed FP32x2 (FADD2 / FMUL2 / FFMA2) -- a complex add is one issue slot and the operand swizzle of the
+// packed forms absorbs the (y, -x) rotations; f64 stays scalar.
+__device__ __forceinline__ unsigned long long pk2(Cx<float> v) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(v.x), "f"(v.y)); return r; }
+__device__ __forceinline__ Cx<float> upk2(unsigned long long v) { Cx<float> r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
+__device__ __forceinline__ Cx<float> operator+(Cx<float> a, Cx<float> b) { unsigned long long r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a)), "l"(pk2(b))); return upk2(r); }
+__device__ __forceinline__ Cx<float> operator-(Cx<float> a, Cx<float> b) { unsigned long long r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a)), "l"(pk2(b))); return upk2(r); }
+__device__ __forceinline__ Cx<float> mul2(Cx<float> a, Cx<float> b) { unsigned long long r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a)), "l"(pk2(b))); return upk2(r); }
+__device__ __forceinline__ Cx<float> fma2(Cx<float> a, Cx<float> b, Cx<float> c) { unsigned long long r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pk2(a)), "l"(pk2(b)), "l"(pk2(c))); return upk2(r); }
+// a * b = a.x * (b.x, b.y) + a.y * (-b.y, b.x)
+__device__ __forceinline__ Cx<float> operator*(Cx<float> a, Cx<float> b) { return fma2(Cx<float>{a.y, a.y}, Cx<float>{-b.y, b.x}, mul2(Cx<float>{a.x, a.x}, b)); }
+__device__ __forceinline__ Cx<double> operator+(Cx<double> a, Cx<double> b) { return {a.x + b.x, a.y + b.y}; }
+__device__ __forceinline__ Cx<double> operator-(Cx<double> a, Cx<double> b) { return {a.x - b.x, a.y - b.y}; }
+__device__ __forceinline__ Cx<double> operator*(Cx<double> a, Cx<double> b) { return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
 template <typename T> __device__ __forceinline__ Cx<T> mul_mi(Cx<T> a) { return {a.y, -a.x}; }   // * (-i)
 
 template <typename T> __device__ __forceinline__ void dft2(Cx<T> &a, Cx<T> &b) { const Cx<T> t = a - b; a = a + b; b = t; }
@@ -74,6 +84,16 @@ template <typename T> struct Dft<T, 16> {
     }
 };
 
+template <typename T> __device__ __forceinline__ Cx<T> ldg_cx(const Cx<T> *p);
+template <> __device__ __forceinline__ Cx<float> ldg_cx<float>(const Cx<float> *p) {
+    const float2 v = __ldg(reinterpret_cast<const float2 *>(p));
+    return {v.x, v.y};
+}
+template <> __device__ __forceinline__ Cx<double> ldg_cx<double>(const Cx<double> *p) {
+    const double2 v = __ldg(reinterpret_cast<const double2 *>(p));
+    return {v.x, v.y};
+}
+
 __host__ __device__ constexpr int pad16(int i) { return i + (i >> 4); }
 
 // One Stockham pass of radix R with accumulated length CUR on a frame's M-point buffer; the thread owns butterflies
@@ -85,10 +105,24 @@ __device__ __forceinline__ void pass_load(const Cx<T> *z, const Cx<T> *__restric
     for (int u = 0; u < 16 / R; ++u) {
         const int b = t + TPF * u;
         const int q = b & (CUR - 1);
+        // twiddles W_{CUR*R}^{j q} = w^j with w = W_M^{q MM}: two table loads (w, w^4); the other powers are products of
+        // one of {w, w^2, w^3} and one of {w^4, w^8, w^12}, formed on the fly (at most three chained multiplications) --
+        // the memory-instruction queue, not the FP pipe, is what these passes run out of
+        Cx<T> wl[4], wh[4];
+        if (CUR > 1) {
+            wl[1] = ldg_cx<T>(tw + q * MM);
+            if (R > 2) { wl[2] = wl[1] * wl[1]; wl[3] = wl[2] * wl[1]; }
+            if (R > 4) wh[1] = ldg_cx<T>(tw + 4 * q * MM);
+            if (R > 8) { wh[2] = wh[1] * wh[1]; wh[3] = wh[2] * wh[1]; }
+        }
 #pragma unroll
         for (int j = 0; j < R; ++j) {
             Cx<T> x = z[pad16(j * B + b)];
-            if (CUR > 1 && j > 0) x = x * tw[j * q * MM];      // W_{CUR*R}^{j q} = W_M^{j q MM}
+            if (CUR > 1 && j > 0) {
+                const int hi = j >> 2, lo = j & 3;
+                const Cx<T> wj = hi == 0 ? wl[lo] : (lo == 0 ? wh[hi] : wh[hi] * wl[lo]);
+                x = x * wj;
+            }
             v[u * R + j] = x;
         }
     }
@@ -110,16 +144,6 @@ template <int M> struct Radices {          // M = 16^P16 * LAST, LAST in {1, 2, 
     static constexpr int P16 = M >= 4096 ? 3 : (M >= 256 ? 2 : 1);
     static constexpr int LAST = M / (P16 == 3 ? 4096 : (P16 == 2 ? 256 : 16));
 };
-
-template <typename T> __device__ __forceinline__ Cx<T> ldg_cx(const Cx<T> *p);
-template <> __device__ __forceinline__ Cx<float> ldg_cx<float>(const Cx<float> *p) {
-    const float2 v = __ldg(reinterpret_cast<const float2 *>(p));
-    return {v.x, v.y};
-}
-template <> __device__ __forceinline__ Cx<double> ldg_cx<double>(const Cx<double> *p) {
-    const double2 v = __ldg(reinterpret_cast<const double2 *>(p));
-    return {v.x, v.y};
-}
 
 template <typename T, int M, int FT>
 __global__ void __launch_bounds__(FT *(M / 16), sizeof(T) == 4 ? 4 : 2) k_r2c_fused_pow2(const __grid_constant__ KParams p) {
@@ -234,18 +258,19 @@ __global__ void __launch_bounds__(FT *(M / 16), sizeof(T) == 4 ? 4 : 2) k_r2c_fu
         return;
     }
     T *P = reinterpret_cast<T *>(zbuf);
-    T *pf = P + fl * p.tile_stride;
+    const bool rows_per_thread = FT <= 8 && p.output == SGX_OUT_SPECTROGRAM && (p.mapping == SGX_MAP_MEL || p.mapping == SGX_MAP_LOGHZ);
+    if (rows_per_thread) {
+        // Small tiles, sparse mapping: power tile transposed to P[bin][FT] so that one filterbank row = one thread reads all
+        // FT frames of a column with a single vector load, and every weight / column index is loaded once per FT outputs.
+        // Same ascending-column, un-fused arithmetic as SparseMatrix::multiply_vec (src/spectrogram.rs:102-117).
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-        const int k = t + TPF * u;
-        pf[k] = xa[u].x * xa[u].x + xa[u].y * xa[u].y;      // norm_sqr (src/spectrogram.rs:1332-1334)
-        pf[M - k] = xb[u].x * xb[u].x + xb[u].y * xb[u].y;
-    }
-    if (t == 0) pf[M / 2] = xm.x * xm.x + xm.y * xm.y;
-    __syncthreads();
-    if (FT <= 8 && p.output == SGX_OUT_SPECTROGRAM && (p.mapping == SGX_MAP_MEL || p.mapping == SGX_MAP_LOGHZ)) {
-        // small tiles: one thread per filterbank row, all FT frames of the tile in registers -- every weight / column
-        // index is loaded once per FT outputs. Same ascending-column, un-fused arithmetic as SparseMatrix::multiply_vec.
+        for (int u = 0; u < 8; ++u) {
+            const int k = t + TPF * u;
+            P[k * FT + fl] = xa[u].x * xa[u].x + xa[u].y * xa[u].y;
+            P[(M - k) * FT + fl] = xb[u].x * xb[u].x + xb[u].y * xb[u].y;
+        }
+        if (t == 0) P[(M / 2) * FT + fl] = xm.x * xm.x + xm.y * xm.y;
+        __syncthreads();
         const T eps = static_cast<T>(p.eps);
         const T *val = static_cast<const T *>(p.val);
         T *out = static_cast<T *>(p.out) + static_cast<long long>(clip) * p.out_clip_stride + (f0 - p.out_frame_origin);
@@ -256,9 +281,12 @@ __global__ void __launch_bounds__(FT *(M / 16), sizeof(T) == 4 ? 4 : 2) k_r2c_fu
             for (int f = 0; f < FT; ++f) acc[f] = T(0);
             for (int e = e0; e < e1; ++e) {
                 const T w = __ldg(val + e);
-                const T *pc = P + __ldg(p.col + e);
+                const T *pc = P + __ldg(p.col + e) * FT;
+                T x[FT];
 #pragma unroll
-                for (int f = 0; f < FT; ++f) acc[f] = t_add_rn(acc[f], t_mul_rn(w, pc[f * p.tile_stride]));
+                for (int f = 0; f < FT; ++f) x[f] = pc[f];
+#pragma unroll
+                for (int f = 0; f < FT; ++f) acc[f] = t_add_rn(acc[f], t_mul_rn(w, x[f]));
             }
             T *orow = out + static_cast<long long>(row) * p.out_row_stride;
 #pragma unroll
@@ -267,6 +295,15 @@ __global__ void __launch_bounds__(FT *(M / 16), sizeof(T) == 4 ? 4 : 2) k_r2c_fu
         }
         return;
     }
+    T *pf = P + fl * p.tile_stride;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int k = t + TPF * u;
+        pf[k] = xa[u].x * xa[u].x + xa[u].y * xa[u].y;      // norm_sqr (src/spectrogram.rs:1332-1334)
+        pf[M - k] = xb[u].x * xb[u].x + xb[u].y * xb[u].y;
+    }
+    if (t == 0) pf[M / 2] = xm.x * xm.x + xm.y * xm.y;
+    __syncthreads();
     // scratch for the fused-MFCC log-mel tile sits behind the power tile (host sizes the buffer for it)
     epilogue_from_power<T>(p, P, P + FT * p.tile_stride, clip, f0, nf);
     (void)N;
