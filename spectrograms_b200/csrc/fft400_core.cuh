@@ -33,7 +33,8 @@ constexpr int kThreads = kWarps * 32;
 // shared-memory layouts (in 4-byte words)
 //   signal tile : sample u of the tile (u = 0 <-> sample f0*160 - pad) lives at u + 2*(u/160). The 2-word pad per hop
 //                 makes the frame stride 162 == 2 (mod 32): lanes = frames read 8-byte pairs from 16 distinct bank pairs.
-//   Y exchange  : Y[f][k1][n2] complex at 444 f + 40 k1 + 2 n2 ; 444/4 odd -> 16-byte accesses with lanes = frames are
+//   Y exchange  : Y[f][row][n2] complex at 404 f + 40 row + 2 n2, row = k1 for k1 = 1..9; rows k1 = 0 and k1 = 10 are purely
+//                 real and share row 0 as (Y[0][n2], Y[10][n2]). 404/4 odd -> 16-byte accesses with lanes = frames are
 //                 conflict free both when pass 1 writes and when pass 2 reads.
 //   power tile  : P[bin][frame_col(f)] at 32 bin + frame_col(f): frames fastest (conflict free for lanes = frames, and
 //                 already the (rows, frames) orientation of the output), with the frame order permuted inside a row so
@@ -42,8 +43,8 @@ constexpr int kSigBlocks = 34;                         // ceil((31*160 + 400) / 
 constexpr int kSigBlockStride = 162;
 constexpr int kSigWords = kSigBlocks * kSigBlockStride;   // 5508
 constexpr int kTileSamples = (kFT - 1) * kHop + kN;       // 5360
-constexpr int kYFrameStride = 444;
-constexpr int kYWords = kFT * kYFrameStride;              // 14208
+constexpr int kYFrameStride = 404;
+constexpr int kYWords = kFT * kYFrameStride;              // 12928
 constexpr int kPWords = kBins * kFT;                      // 6432
 
 // per-plan constants, passed by value as a kernel parameter (constant bank; indices are warp-uniform)
@@ -113,22 +114,21 @@ SGX_HD void dft20(float2 (&v)[20]) {
 }
 
 // ---- pass 1, one task = (frame f of the tile, column pair t): columns n2 = 2t and 2t+1
-SGX_HD void pass1_task(const float *__restrict__ sig, float *__restrict__ ybuf, const Consts &c, int f, int t) {
+SGX_HD void pass1_task(const float *__restrict__ sig, float *__restrict__ ybuf, const float *__restrict__ win, int f, int t) {
     float2 v[20];
     const float *s = sig + kSigBlockStride * f + 2 * t;
 #pragma unroll
     for (int n1 = 0; n1 < 20; ++n1) {
         const float2 x = *reinterpret_cast<const float2 *>(s + 20 * n1 + 2 * (n1 / 8));
-        const float2 w = *reinterpret_cast<const float2 *>(&c.win[20 * n1 + 2 * t]);
+        const float2 w = *reinterpret_cast<const float2 *>(win + 20 * n1 + 2 * t);
         v[n1] = cmul2(x, w);                          // sample * window[i] (src/spectrogram.rs:1319)
     }
     dft20(v);
     float *y = ybuf + kYFrameStride * f + 4 * t;      // complex index 2t -> word 4t
-    // k1 = 0 and k1 = 10: both column spectra are real there
+    // k1 = 0 and k1 = 10: both column spectra are real there; they share row 0 as (Y[0], Y[10]) pairs
     {
         const float2 z0 = v[reg_of_bin(0)], z10 = v[reg_of_bin(10)];
-        *reinterpret_cast<float4 *>(y) = make_float4(z0.x, 0.f, z0.y, 0.f);
-        *reinterpret_cast<float4 *>(y + 40 * 10) = make_float4(z10.x, 0.f, z10.y, 0.f);
+        *reinterpret_cast<float4 *>(y) = make_float4(z0.x, z10.x, z0.y, z10.y);
     }
 #pragma unroll
     for (int k1 = 1; k1 < 10; ++k1) {
@@ -142,12 +142,16 @@ SGX_HD void pass1_task(const float *__restrict__ sig, float *__restrict__ ybuf, 
 
 // ---- pass 2, one task = (frame f, k1), in two halves so that a barrier can sit between "every Y value has been
 // read" and "the power tile (which may alias the Y buffer) is written".
-SGX_HD void pass2_load(const float *__restrict__ ybuf, const Consts &c, int f, int k1, float2 (&v)[20]) {
-    const float *y = ybuf + kYFrameStride * f + 40 * k1;
+// tw2: this k1's 20 twiddles (constant bank or shared memory)
+SGX_HD void pass2_load(const float *__restrict__ ybuf, const float2 *__restrict__ tw2, int f, int k1, float2 (&v)[20]) {
+    const bool lo = k1 == 0, hi = k1 == 10;                   // the two real rows packed into row 0
+    const float *y = ybuf + kYFrameStride * f + 40 * (hi ? 0 : k1);
 #pragma unroll
     for (int j = 0; j < 10; ++j) {
-        const float4 q = *reinterpret_cast<const float4 *>(y + 4 * j);
-        const float2 w0 = c.tw2[k1][2 * j], w1 = c.tw2[k1][2 * j + 1];
+        float4 q = *reinterpret_cast<const float4 *>(y + 4 * j);
+        if (lo) q = make_float4(q.x, 0.f, q.z, 0.f);
+        if (hi) q = make_float4(q.y, 0.f, q.w, 0.f);
+        const float2 w0 = tw2[2 * j], w1 = tw2[2 * j + 1];
         // q * w = q.x * (w.x, w.y) + q.y * (-w.y, w.x)
         v[2 * j] = cfma2(bc2(q.y), make_float2(-w0.y, w0.x), cmul2(bc2(q.x), w0));
         v[2 * j + 1] = cfma2(bc2(q.w), make_float2(-w1.y, w1.x), cmul2(bc2(q.z), w1));
@@ -175,7 +179,7 @@ SGX_HD void pass2_finish(float2 (&v)[20], float *__restrict__ ptile, int f, int 
 
 SGX_HD void pass2_task(const float *__restrict__ ybuf, float *__restrict__ ptile, const Consts &c, int f, int k1) {
     float2 v[20];
-    pass2_load(ybuf, c, f, k1, v);
+    pass2_load(ybuf, c.tw2[k1], f, k1, v);
     pass2_finish(v, ptile, f, k1);
 }
 

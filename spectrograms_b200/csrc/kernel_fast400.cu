@@ -5,14 +5,15 @@
 //             by warp 10 (which has no pass-1 role) -- overlaps everything below; out-of-clip bytes are zero filled, which is the reference's centre padding
 //             (src/spectrogram.rs:1309-1320) with no per-tap branch
 //   pass 1    warps 0..9 : window multiply + 20-point real-pair DFT in registers        (fft400_core.cuh)
-//   ----      one shared-memory exchange (Y[k1][n2], 11 x 20 complex per frame)
+//   ----      one shared-memory exchange (Y[k1][n2], 10 rows x 20 complex per frame: the two real rows share one)
 //   pass 2    warps 0..10: twiddle + 20-point DFT in registers -> |X|^2 into the power tile P[bin][frame], which reuses
 //             the tile's own signal buffer (its samples are dead after pass 1; the prefetch targets the other buffer)
 //   epilogue  sparse filterbank rows from a shared-memory table -> sqrt / dB -> 128-byte row stores; other mappings and
 //             the fused DCT-II take the general lane = frame epilogue (epilogue.cuh)
 //
 // Every shared-memory access of the two passes is conflict free by construction of the layouts (fft400_core.cuh);
-// window and twiddles come from the constant bank (kernel parameter) with warp-uniform indices.
+// the window is copied once per CTA into shared memory (warp-uniform broadcast reads); the pass-2 twiddles are read from
+// the constant bank (kernel parameter) with warp-uniform indices.
 #include "epilogue.cuh"
 #include "fft400_core.cuh"
 #include "launch.hpp"
@@ -210,12 +211,16 @@ __global__ void __launch_bounds__(kThreads, 2) k_r2c_fused_n400(const __grid_con
     const int nq_smem = SPARSE ? __ldg(reinterpret_cast<const int *>(P.k.dense)) : 0;
     int4 *s_quads = reinterpret_cast<int4 *>(ybuf + kYWords);        // [4 * n_quads] {byte offset of P[c0], cnt, weights address, row}
     int *s_qinfo = reinterpret_cast<int *>(s_quads + 4 * nq_smem);   // [kWarps + 1] quad ranges per warp, then [n_quads] max cnt
-    float *s_w = reinterpret_cast<float *>(s_qinfo + ((kWarps + 1 + nq_smem + 3) & ~3));   // weights, rows padded to multiples of 4
+    // the window is read with warp-uniform addresses in pass 1: a shared-memory broadcast measurably beats the indexed
+    // constant-bank load there (-3.6 %); the pass-2 twiddles stay in the constant bank (shared memory was slower for them)
+    float *s_win = reinterpret_cast<float *>(s_qinfo + ((kWarps + 1 + nq_smem + 3) & ~3));
+    float *s_w = s_win + kN;                                         // weights, rows padded to multiples of 4
     const KParams &p = P.k;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool vec_ok = p.buf_elems != 0;
 
+    for (int i = tid; i < kN; i += kThreads) s_win[i] = P.c.win[i];
     if (SPARSE) {
         // p.dense carries the host-built schedule blob: int n_quads; int qrange[kWarps + 1]; int maxcnt[n_quads];
         // (16-byte aligned) int4 {c0, cnt, padded weight offset, row or -1}[4 * n_quads]
@@ -266,14 +271,18 @@ __global__ void __launch_bounds__(kThreads, 2) k_r2c_fused_n400(const __grid_con
         const float *xn = xbase + static_cast<long long>(more ? clip : 0) * p.clip_stride;
         const long long sn = (p.frame_begin + static_cast<long long>(tile) * kFT) * kHop - p.pad;
         if (warp < 10) {
-            pass1_task(sig, ybuf, P.c, lane, warp);
+            pass1_task(sig, ybuf, s_win, lane, warp);
             if (more) load_tile(buf ? sig0 : sig1, xn, sn, p.n_samples, vec_ok, kPrefetchSplit + tid, 320, kTileSamples / 2);
         } else if (more) {
             load_tile(buf ? sig0 : sig1, xn, sn, p.n_samples, vec_ok, lane, 32, kPrefetchSplit);
         }
         __syncthreads();
 
-        pass2_task(ybuf, ptile, P.c, lane, warp);     // samples are consumed: P overwrites the signal buffer
+        {
+            float2 v[20];
+            pass2_load(ybuf, P.c.tw2[warp], lane, warp, v);
+            pass2_finish(v, ptile, lane, warp);       // samples are consumed: P overwrites the signal buffer
+        }
         __syncthreads();
 
         float *ocf = static_cast<float *>(p.out) + static_cast<long long>(cur_clip) * p.out_clip_stride + (f0 - p.out_frame_origin);
@@ -297,9 +306,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_r2c_fused_n400(const __grid_con
 
 // dynamic shared memory of a launch whose sparse schedule has n_quads quads and padded_weights weights (0, 0: none)
 size_t fast400_smem_bytes(int n_quads, int padded_weights) {
-    if (n_quads == 0) return kFixedSmemBytes;
+    if (n_quads == 0) return kFixedSmemBytes + sizeof(float) * (f400::kN + 16);
     return kFixedSmemBytes + sizeof(int4) * 4 * n_quads + sizeof(int) * ((f400::kWarps + 1 + n_quads + 3) & ~3) +
-           sizeof(float) * (padded_weights + 64);
+           sizeof(float) * (padded_weights + 8 + f400::kN);
 }
 // the sparse schedule is used only while two CTAs still fit on an SM
 bool fast400_sparse_fits(int n_quads, int padded_weights) { return fast400_smem_bytes(n_quads, padded_weights) <= kSmemBudget; }

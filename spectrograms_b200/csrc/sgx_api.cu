@@ -401,8 +401,7 @@ void run_device(sgx_plan &pl, const void *d_samples, size_t n_clips, size_t n_sa
         if (pl.fast400 && !pl.force_generic) {
             // 8-byte vector loads need an 8-byte aligned base and an even clip stride
             q.buf_elems = (reinterpret_cast<uintptr_t>(q.samples) % 8 == 0 && clip_stride % 2 == 0) ? 1 : 0;
-            if (pl.fast400_sparse) q.dense = pl.d_wofs;
-            q.n_stages = getenv("SGX_DEBUG_SKIP") ? atoi(getenv("SGX_DEBUG_SKIP")) : 0;   // profiling aid: 1 = no epilogue, 2 = no FFT      // sparse mappings do not use `dense`: carries the weight offsets
+            if (pl.fast400_sparse) q.dense = pl.d_wofs;      // sparse mappings do not use `dense`: it carries the quad schedule
             ck(launch_fast400(q, pl.window_f32.data(), pl.fast400_sparse, pl.sparse_quads, pl.sparse_weights, pl.sm_count, stream), "kernel launch (r2c_fused_n400)");
         } else if (pl.pow2 && !pl.force_generic) {
             q.FT = pl.pow2_ft;

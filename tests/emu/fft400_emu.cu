@@ -26,7 +26,7 @@ extern "C" int emu_fft400_tile(const float *samples, long long n_samples, long l
         sig[sig_word(u)] = (s >= 0 && s < n_samples) ? samples[s] : 0.f;
     }
     for (int t = 0; t < 10; ++t)
-        for (int f = 0; f < kFT; ++f) pass1_task(sig.data(), ybuf.data(), c, f, t);
+        for (int f = 0; f < kFT; ++f) pass1_task(sig.data(), ybuf.data(), c.win, f, t);
     for (int k1 = 0; k1 <= 10; ++k1)
         for (int f = 0; f < kFT; ++f) pass2_task(ybuf.data(), p.data(), c, f, k1);
     for (int b = 0; b < kBins; ++b)
