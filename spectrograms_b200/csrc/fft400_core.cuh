@@ -142,19 +142,35 @@ SGX_HD void pass1_task(const float *__restrict__ sig, float *__restrict__ ybuf, 
 
 // ---- pass 2, one task = (frame f, k1), in two halves so that a barrier can sit between "every Y value has been
 // read" and "the power tile (which may alias the Y buffer) is written".
-// tw2: this k1's 20 twiddles (constant bank or shared memory)
+// tw2: this k1's 20 twiddles (constant bank or shared memory). k1 is warp-uniform in the kernel, so the three cases
+// below are branches, not selects.
 SGX_HD void pass2_load(const float *__restrict__ ybuf, const float2 *__restrict__ tw2, int f, int k1, float2 (&v)[20]) {
-    const bool lo = k1 == 0, hi = k1 == 10;                   // the two real rows packed into row 0
-    const float *y = ybuf + kYFrameStride * f + 40 * (hi ? 0 : k1);
+    if (k1 == 0) {                       // real row packed in the .x slots of row 0, twiddle = 1
+        const float *y = ybuf + kYFrameStride * f;
 #pragma unroll
-    for (int j = 0; j < 10; ++j) {
-        float4 q = *reinterpret_cast<const float4 *>(y + 4 * j);
-        if (lo) q = make_float4(q.x, 0.f, q.z, 0.f);
-        if (hi) q = make_float4(q.y, 0.f, q.w, 0.f);
-        const float2 w0 = tw2[2 * j], w1 = tw2[2 * j + 1];
-        // q * w = q.x * (w.x, w.y) + q.y * (-w.y, w.x)
-        v[2 * j] = cfma2(bc2(q.y), make_float2(-w0.y, w0.x), cmul2(bc2(q.x), w0));
-        v[2 * j + 1] = cfma2(bc2(q.w), make_float2(-w1.y, w1.x), cmul2(bc2(q.z), w1));
+        for (int j = 0; j < 10; ++j) {
+            const float4 q = *reinterpret_cast<const float4 *>(y + 4 * j);
+            v[2 * j] = make_float2(q.x, 0.f);
+            v[2 * j + 1] = make_float2(q.z, 0.f);
+        }
+    } else if (k1 == 10) {               // real row packed in the .y slots of row 0
+        const float *y = ybuf + kYFrameStride * f;
+#pragma unroll
+        for (int j = 0; j < 10; ++j) {
+            const float4 q = *reinterpret_cast<const float4 *>(y + 4 * j);
+            v[2 * j] = cmul2(bc2(q.y), tw2[2 * j]);
+            v[2 * j + 1] = cmul2(bc2(q.w), tw2[2 * j + 1]);
+        }
+    } else {
+        const float *y = ybuf + kYFrameStride * f + 40 * k1;
+#pragma unroll
+        for (int j = 0; j < 10; ++j) {
+            const float4 q = *reinterpret_cast<const float4 *>(y + 4 * j);
+            const float2 w0 = tw2[2 * j], w1 = tw2[2 * j + 1];
+            // q * w = q.x * (w.x, w.y) + q.y * (-w.y, w.x)
+            v[2 * j] = cfma2(bc2(q.y), make_float2(-w0.y, w0.x), cmul2(bc2(q.x), w0));
+            v[2 * j + 1] = cfma2(bc2(q.w), make_float2(-w1.y, w1.x), cmul2(bc2(q.z), w1));
+        }
     }
 }
 

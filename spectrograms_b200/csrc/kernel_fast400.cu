@@ -71,6 +71,21 @@ __device__ __forceinline__ void load_tile(float *sig, const float *x, long long 
     }
 }
 
+// Interior-tile prefetch by ONE warp, hop block by hop block: block b (160 samples = 80 float2 units) goes to word 162 b,
+// so source and destination advance by constants and each block costs three cp.async per lane (the third on 16 lanes).
+__device__ __forceinline__ void prefetch_tile_by_warp(float *sig, const float *src, int lane) {
+    const float *s = src + 2 * lane;
+    float *d = sig + 2 * lane;
+#pragma unroll 3
+    for (int b = 0; b < kTileSamples / kHop; ++b, s += kHop, d += kSigBlockStride) {      // 33 full blocks
+        cp_async8(d, s, 8);
+        cp_async8(d + 64, s + 64, 8);
+        if (lane < 16) cp_async8(d + 128, s + 128, 8);
+    }
+    cp_async8(d, s, 8);                                                                   // last block: 80 samples
+    if (lane < 8) cp_async8(d + 64, s + 64, 8);
+}
+
 // lg2.approx.ftz: the argument is clamped to eps > 0 first, so the denormal fix-up of __log2f is dead weight
 __device__ __forceinline__ float fast_lg2(float v) {
     float r;
@@ -107,9 +122,9 @@ __device__ __forceinline__ float finish_value(float acc, float eps) {
 
 // TO_SMEM: instead of storing to global memory, leave the scaled rows in a shared tile mtile[row][32] (same permuted
 // frame order as the power tile) for the fused DCT.
-template <int AMP, bool TO_SMEM>
-__device__ __forceinline__ void sparse_quads_epilogue(const KParams &p, const float *ptile, const int4 *s_quads, const int *s_qinfo,
-                                                      float *out_clip_frame, float *mtile, int nf, int warp, int lane) {
+template <int AMP, bool TO_SMEM, bool FULL>
+__device__ __forceinline__ void sparse_quads_epilogue_impl(const KParams &p, const float *ptile, const int4 *s_quads, const int *s_qinfo,
+                                                           float *out_clip_frame, float *mtile, int nf, int warp, int lane) {
     const float eps = static_cast<float>(p.eps);
     const int s = lane >> 3, j = lane & 7;
     const unsigned pbase = smem_u32(ptile) + 16u * j;             // columns 4j..4j+3 = frames j, j+8, j+16, j+24
@@ -145,21 +160,28 @@ __device__ __forceinline__ void sparse_quads_epilogue(const KParams &p, const fl
                 continue;
             }
             char *orow = ob + static_cast<size_t>(static_cast<unsigned>(row)) * ors4;
-            if (j < nf) *reinterpret_cast<float *>(orow) = v0;
-            if (j + 8 < nf) *reinterpret_cast<float *>(orow + 32) = v1;
-            if (j + 16 < nf) *reinterpret_cast<float *>(orow + 64) = v2;
-            if (j + 24 < nf) *reinterpret_cast<float *>(orow + 96) = v3;
+            if (FULL || j < nf) *reinterpret_cast<float *>(orow) = v0;
+            if (FULL || j + 8 < nf) *reinterpret_cast<float *>(orow + 32) = v1;
+            if (FULL || j + 16 < nf) *reinterpret_cast<float *>(orow + 64) = v2;
+            if (FULL || j + 24 < nf) *reinterpret_cast<float *>(orow + 96) = v3;
         }
     }
+}
+
+template <int AMP, bool TO_SMEM>
+__device__ __forceinline__ void sparse_quads_epilogue(const KParams &p, const float *ptile, const int4 *s_quads, const int *s_qinfo,
+                                                      float *out_clip_frame, float *mtile, int nf, int warp, int lane) {
+    if (nf == kFT) sparse_quads_epilogue_impl<AMP, TO_SMEM, true>(p, ptile, s_quads, s_qinfo, out_clip_frame, mtile, nf, warp, lane);
+    else sparse_quads_epilogue_impl<AMP, TO_SMEM, false>(p, ptile, s_quads, s_qinfo, out_clip_frame, mtile, nf, warp, lane);
 }
 
 // Fused DCT-II + lifter on the log-mel tile mtile[n][32] (mfcc_from_log_mel, src/mfcc.rs:224-273) using the basis
 // symmetry B[c][n-1-i] = (-1)^c B[c][i]: fold the tile in place into E[i] = m[i] + m[n-1-i] (kept in row i) and
 // O[i] = m[i] - m[n-1-i] (kept in row n-1-i), then every coefficient needs n/2 instead of n multiply-adds. One warp
-// task = 4 coefficients of one parity x 32 frames (lane = frame); the half basis streams through the read-only path
-// as one warp-uniform 16-byte load per step. Requires n even (host falls back to the general epilogue otherwise).
-__device__ __forceinline__ void folded_dct_epilogue(const KParams &p, float *mtile, float *out_clip_frame, int nf, int warp, int lane,
-                                                    int tid) {
+// task = 4 coefficients of one parity x 32 frames (lane = frame); `basis` is the half basis [task][n/2][4], staged by the
+// caller into shared memory (cp.async, overlapped with the mel rows), read as one warp-uniform 16-byte broadcast per step. Requires n even (host falls back to the general epilogue otherwise).
+__device__ __forceinline__ void folded_dct_epilogue(const KParams &p, float *mtile, const float4 *basis, float *out_clip_frame, int nf,
+                                                    int warp, int lane, int tid) {
     const int n = p.n_bins, half = n >> 1;
     for (int idx = tid; idx < half * kFT; idx += kThreads) {
         const int i = idx >> 5, c = idx & 31;
@@ -168,7 +190,6 @@ __device__ __forceinline__ void folded_dct_epilogue(const KParams &p, float *mti
         mtile[(n - 1 - i) * kFT + c] = a - b;
     }
     __syncthreads();
-    const float4 *basis = static_cast<const float4 *>(p.dct_folded);
     const float *lift = static_cast<const float *>(p.lifter);
     const int col = frame_col(lane);
     const bool live = lane < nf;
@@ -183,7 +204,7 @@ __device__ __forceinline__ void folded_dct_epilogue(const KParams &p, float *mti
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll 8
         for (int i = 0; i < half; ++i) {
-            const float4 w = __ldg(b + i);
+            const float4 w = b[i];
             const float x = m[i * mstep];
             a0 = fmaf(x, w.x, a0);
             a1 = fmaf(x, w.y, a1);
@@ -264,17 +285,19 @@ __global__ void __launch_bounds__(kThreads, 2) k_r2c_fused_n400(const __grid_con
         clip += step_clip;                     // next tile of this CTA
         tile += step_tile;
         if (tile >= tpc) { tile -= tpc; ++clip; }
-        // Prefetch of the next tile into the other buffer, overlapped with pass 1. Warp 10 has no pass-1 role and takes
-        // the first kPrefetchSplit float2 units; warps 0..9 share the rest, sized so that both kinds of warp issue about
-        // the same number of instructions in this phase.
+        // Prefetch of the next tile into the other buffer, overlapped with pass 1: warp 10 has no pass-1 role and issues
+        // the whole tile (about as many instructions as one pass-1 task). Edge tiles (first / last of a clip, or unaligned
+        // input) take the general path, shared by all warps.
         const bool more = clip < p.n_clips;
         const float *xn = xbase + static_cast<long long>(more ? clip : 0) * p.clip_stride;
         const long long sn = (p.frame_begin + static_cast<long long>(tile) * kFT) * kHop - p.pad;
+        const bool interior = vec_ok && sn >= 0 && sn + kTileSamples <= p.n_samples;
         if (warp < 10) {
             pass1_task(sig, ybuf, s_win, lane, warp);
-            if (more) load_tile(buf ? sig0 : sig1, xn, sn, p.n_samples, vec_ok, kPrefetchSplit + tid, 320, kTileSamples / 2);
+            if (more && !interior) load_tile(buf ? sig0 : sig1, xn, sn, p.n_samples, vec_ok, kPrefetchSplit + tid, 320, kTileSamples / 2);
         } else if (more) {
-            load_tile(buf ? sig0 : sig1, xn, sn, p.n_samples, vec_ok, lane, 32, kPrefetchSplit);
+            if (interior) prefetch_tile_by_warp(buf ? sig0 : sig1, xn + sn, lane);
+            else load_tile(buf ? sig0 : sig1, xn, sn, p.n_samples, vec_ok, lane, 32, kPrefetchSplit);
         }
         __syncthreads();
 
@@ -292,10 +315,18 @@ __global__ void __launch_bounds__(kThreads, 2) k_r2c_fused_n400(const __grid_con
             else sparse_quads_epilogue<0, false>(p, ptile, s_quads, s_qinfo, ocf, nullptr, nf, warp, lane);
         } else if (SPARSE && p.dct_folded != nullptr) {
             // fused mfcc(): mel -> dB (always has a floor here, src/mfcc.rs:371) -> folded DCT-II -> lifter
+            // stage the half basis behind the log-mel tile (the Y buffer is dead after pass 2) while the mel rows run
+            float4 *s_basis = reinterpret_cast<float4 *>(scratch + p.n_bins * kFT);
+            const int n_basis = p.dct_tasks * (p.n_bins >> 1);
+            for (int i = tid; i < n_basis; i += kThreads) {
+                const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(s_basis + i));
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(static_cast<const float4 *>(p.dct_folded) + i) : "memory");
+            }
             if (p.apply_db) sparse_quads_epilogue<2, true>(p, ptile, s_quads, s_qinfo, ocf, scratch, nf, warp, lane);
             else sparse_quads_epilogue<0, true>(p, ptile, s_quads, s_qinfo, ocf, scratch, nf, warp, lane);
+            cp_async_commit_wait_all();
             __syncthreads();
-            folded_dct_epilogue(p, scratch, ocf, nf, warp, lane, tid);
+            folded_dct_epilogue(p, scratch, s_basis, ocf, nf, warp, lane, tid);
         } else {
             epilogue_lane_frames<float>(p, ptile, scratch, cur_clip, f0, nf, frame_col(lane));
         }

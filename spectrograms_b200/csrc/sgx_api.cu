@@ -276,7 +276,9 @@ void select_family(sgx_plan &pl) {
     // one parity: [task][i < n/2][4], even-coefficient tasks first
     pl.dct_folded.clear();
     pl.dct_tasks = 0;
-    if (pl.fast400_sparse && d.output == SGX_OUT_MFCC && pl.tab.n_bins % 2 == 0) {
+    const size_t dct_tasks_wanted = ((d.n_mfcc + 1) / 2 + 3) / 4 + (d.n_mfcc / 2 + 3) / 4;
+    if (pl.fast400_sparse && d.output == SGX_OUT_MFCC && pl.tab.n_bins % 2 == 0 &&
+        pl.tab.n_bins * 32 + dct_tasks_wanted * (pl.tab.n_bins / 2) * 4 <= static_cast<size_t>(fast400_max_scratch_rows()) * 32) {
         const size_t n = pl.tab.n_bins, half = n / 2, nm = d.n_mfcc;
         const size_t ge = ((nm + 1) / 2 + 3) / 4, go = (nm / 2 + 3) / 4;
         pl.dct_tasks = static_cast<int>(ge + go);
