@@ -197,6 +197,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--generic", action="store_true", help="force the generic kernel family")
+    ap.add_argument("--gather", action="store_true", help="also time the optional NCCL gather of results to rank 0 (off the hot path, reported separately)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3        # timing rule: W >= 3
@@ -286,6 +287,25 @@ def main():
                "check": "host result equals device result: %s" % bool(torch.equal(h_out[:4].to(dev), out[:4]))}
         del h_in, h_out
 
+    # ---- optional result gather to rank 0 over NCCL (NVLink / NVSwitch): NOT part of the hot path or of `value`
+    gather = None
+    if args.gather and world > 1:
+        from spectrograms_b200.sharding import gather_to_rank0
+        n_g = min(w["n_clips"], 128)                  # bounded: rank 0 receives world * n_g clips
+        gather_to_rank0(out[:n_g], world * n_g)       # warm-up (NCCL communicator setup)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        full = gather_to_rank0(out[:n_g], world * n_g)
+        g1.record()
+        barrier()
+        gms = torch.tensor([g0.elapsed_time(g1)], device=dev, dtype=torch.float64)
+        dist.all_reduce(gms, op=dist.ReduceOp.MAX)
+        gbytes = (world - 1) * n_g * rows * n_frames * (4 if w["dtype"] == "float32" else 8)
+        ok = bool(rank != 0 or (full is not None and torch.equal(full[:n_g], out[:n_g])))
+        gather = {"clips_per_rank": n_g, "ms": float(gms.item()), "bytes_into_rank0": gbytes,
+                  "GBps_into_rank0": gbytes / (float(gms.item()) * 1e-3) / 1e9, "rank0_block_intact": ok}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -327,6 +347,8 @@ def main():
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
         "clocks": cs.summary(),
     }
+    if gather is not None:
+        line["optional_gather"] = gather
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -576,14 +576,18 @@ sgx_status sgx_plan_compute_batch(sgx_plan *plan, const void *samples, size_t n_
             const size_t nc = std::min(chunk, n_clips - c0);
             sgx_plan::Slot &s = pl.slot[si];
             ensure_slot(s, chunk * in_clip_bytes, chunk * out_clip_bytes);
-            ck(cudaMemcpy2DAsync(s.d_in, in_clip_bytes, static_cast<const char *>(samples) + c0 * clip_stride * pl.esize,
-                                 clip_stride * pl.esize, in_clip_bytes, nc, cudaMemcpyHostToDevice, s.s), "H2D copy");
-            const size_t saved = pl.last_launches;
+            const char *src = static_cast<const char *>(samples) + c0 * clip_stride * pl.esize;
+            if (clip_stride == n_samples)      // contiguous clips: one linear copy (faster than the strided 2-D path)
+                ck(cudaMemcpyAsync(s.d_in, src, nc * in_clip_bytes, cudaMemcpyHostToDevice, s.s), "H2D copy");
+            else
+                ck(cudaMemcpy2DAsync(s.d_in, in_clip_bytes, src, clip_stride * pl.esize, in_clip_bytes, nc, cudaMemcpyHostToDevice, s.s), "H2D copy");
             run_device(pl, s.d_in, nc, n_samples, n_samples, s.d_out, static_cast<long long>(n_frames),
                        static_cast<long long>(out_rows * out_cols), 0, static_cast<long long>(n_frames), s.s);
-            (void)saved;
-            ck(cudaMemcpy2DAsync(static_cast<char *>(out) + c0 * out_clip_stride * oes, out_clip_stride * oes, s.d_out,
-                                 out_clip_bytes, out_clip_bytes, nc, cudaMemcpyDeviceToHost, s.s), "D2H copy");
+            char *dst = static_cast<char *>(out) + c0 * out_clip_stride * oes;
+            if (out_clip_stride == out_rows * out_cols)
+                ck(cudaMemcpyAsync(dst, s.d_out, nc * out_clip_bytes, cudaMemcpyDeviceToHost, s.s), "D2H copy");
+            else
+                ck(cudaMemcpy2DAsync(dst, out_clip_stride * oes, s.d_out, out_clip_bytes, out_clip_bytes, nc, cudaMemcpyDeviceToHost, s.s), "D2H copy");
         }
         for (auto &s : pl.slot) if (s.s) ck(cudaStreamSynchronize(s.s), "cudaStreamSynchronize");
     });
