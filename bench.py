@@ -87,26 +87,35 @@ class ClockSampler:
         self._stop = threading.Event()
         self._t = None
 
-    def _run_nvml(self):
+    def _init_nvml(self):
         import pynvml
         pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
-        self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        self._nv = pynvml
+        self._h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+
+    def _sample_nvml(self):
+        nv, h = self._nv, self._h
         names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
                  0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+        self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+        try:
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        for bit, nm in names.items():
+            if r & bit:
+                self.reasons.add(nm)
+
+    def _run_nvml(self):
         while not self._stop.is_set():
-            self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
-            try:
-                r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
-            except Exception:
-                r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-            for bit, nm in names.items():
-                if r & bit:
-                    self.reasons.add(nm)
-            time.sleep(0.002)
+            self._sample_nvml()
+            time.sleep(0.001)
 
     def _run(self):
         try:
+            if self._nv is None:
+                raise RuntimeError("nvml unavailable")
             self._run_nvml()
         except Exception:
             import subprocess
@@ -123,6 +132,11 @@ class ClockSampler:
                     break
 
     def __enter__(self):
+        self._nv = None
+        try:
+            self._init_nvml()          # initialise before the timed region so that sampling starts immediately
+        except Exception:
+            self._nv = None
         self._t = threading.Thread(target=self._run, daemon=True)
         self._t.start()
         return self
