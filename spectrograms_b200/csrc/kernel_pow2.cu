@@ -140,6 +140,14 @@ __device__ __forceinline__ void pass_store(Cx<T> *z, int t, Cx<T> *v) {
     }
 }
 
+// Barrier among the TPF threads that share one frame's buffer: frames of a tile progress independently of each other
+// through the FFT passes (warp-level sync when a frame fits a warp, a named barrier per frame otherwise).
+template <int TPF, int FT> __device__ __forceinline__ void frame_sync(int fl) {
+    if (TPF <= 32) __syncwarp();
+    else if (FT == 1) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(fl + 1), "n"(TPF) : "memory");
+}
+
 template <int M> struct Radices {          // M = 16^P16 * LAST, LAST in {1, 2, 4, 8}
     static constexpr int P16 = M >= 4096 ? 3 : (M >= 256 ? 2 : 1);
     static constexpr int LAST = M / (P16 == 3 ? 4096 : (P16 == 2 ? 256 : 16));
@@ -195,25 +203,25 @@ __global__ void __launch_bounds__(FT *(M / 16), sizeof(T) == 4 ? 4 : 2) k_r2c_fu
         }
         pass_store<T, M, 16, 1>(z, t, v);
     }
-    __syncthreads();
+    frame_sync<TPF, FT>(fl);
     if constexpr (Radices<M>::P16 >= 2) {
         pass_load<T, M, 16, 16>(z, tw, t, v);
-        __syncthreads();
+        frame_sync<TPF, FT>(fl);
         pass_store<T, M, 16, 16>(z, t, v);
-        __syncthreads();
+        frame_sync<TPF, FT>(fl);
     }
     if constexpr (Radices<M>::P16 >= 3) {
         pass_load<T, M, 16, 256>(z, tw, t, v);
-        __syncthreads();
+        frame_sync<TPF, FT>(fl);
         pass_store<T, M, 16, 256>(z, t, v);
-        __syncthreads();
+        frame_sync<TPF, FT>(fl);
     }
     if constexpr (Radices<M>::LAST > 1) {
         constexpr int CUR = M / Radices<M>::LAST;
         pass_load<T, M, Radices<M>::LAST, CUR>(z, tw, t, v);
-        __syncthreads();
+        frame_sync<TPF, FT>(fl);
         pass_store<T, M, Radices<M>::LAST, CUR>(z, t, v);
-        __syncthreads();
+        frame_sync<TPF, FT>(fl);
     }
 
     // ---- post pass: X[k] = E + W_N^k O, X[M-k] = conj(E - W_N^k O); thread owns k = t + TPF*u (u < 8), plus k = M/2
