@@ -167,7 +167,10 @@ class _NativePlan:
     def __del__(self):
         h = getattr(self, "_h", None)
         if h is not None and h.value:
-            _native.lib().sgx_plan_destroy(h)
+            try:
+                _native.lib().sgx_plan_destroy(h)
+            except Exception:          # interpreter shutdown: module globals may already be gone
+                pass
             self._h = C.c_void_p()
 
     # -- queries
