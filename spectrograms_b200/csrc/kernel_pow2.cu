@@ -115,9 +115,11 @@ __device__ __forceinline__ void pass_load(const Cx<T> *z, const Cx<T> *__restric
             if (R > 4) wh[1] = ldg_cx<T>(tw + 4 * q * MM);
             if (R > 8) { wh[2] = wh[1] * wh[1]; wh[3] = wh[2] * wh[1]; }
         }
+        // B is a multiple of 16, so pad16(j*B + b) = j*pad16(B) + pad16(b): one base address, constant strides
+        const Cx<T> *zb = z + pad16(b);
 #pragma unroll
         for (int j = 0; j < R; ++j) {
-            Cx<T> x = z[pad16(j * B + b)];
+            Cx<T> x = zb[j * pad16(B)];
             if (CUR > 1 && j > 0) {
                 const int hi = j >> 2, lo = j & 3;
                 const Cx<T> wj = hi == 0 ? wl[lo] : (lo == 0 ? wh[hi] : wh[hi] * wl[lo]);
@@ -135,8 +137,17 @@ __device__ __forceinline__ void pass_store(Cx<T> *z, int t, Cx<T> *v) {
         const int b = t + TPF * u;
         const int q = b & (CUR - 1), i = b / CUR;
         Dft<T, R>::run(v + u * R);
+        if (CUR >= 16) {
+            // k*CUR is a multiple of 16: pad16((i*R + k)*CUR + q) = pad16(i*R*CUR + q) + k*pad16(CUR)
+            Cx<T> *zo = z + pad16(i * R * CUR + q);
 #pragma unroll
-        for (int k = 0; k < R; ++k) z[pad16((i * R + k) * CUR + q)] = v[u * R + k];
+            for (int k = 0; k < R; ++k) zo[k * pad16(CUR)] = v[u * R + k];
+        } else {
+            // first pass (CUR = 1, R = 16): outputs 16 b + k, i.e. 17 b + k after padding
+            Cx<T> *zo = z + pad16(i * R * CUR + q);
+#pragma unroll
+            for (int k = 0; k < R; ++k) zo[pad16(k * CUR)] = v[u * R + k];
+        }
     }
 }
 
@@ -266,7 +277,7 @@ __global__ void __launch_bounds__(FT *(M / 16), sizeof(T) == 4 ? 4 : 2) k_r2c_fu
         return;
     }
     T *P = reinterpret_cast<T *>(zbuf);
-    const bool rows_per_thread = FT <= 8 && p.output == SGX_OUT_SPECTROGRAM && (p.mapping == SGX_MAP_MEL || p.mapping == SGX_MAP_LOGHZ);
+    const bool rows_per_thread = FT <= 8 && p.output == SGX_OUT_SPECTROGRAM && p.mapping != SGX_MAP_LINEAR;
     if (rows_per_thread) {
         // Small tiles, sparse mapping: power tile transposed to P[bin][FT] so that one filterbank row = one thread reads all
         // FT frames of a column with a single vector load, and every weight / column index is loaded once per FT outputs.
@@ -282,14 +293,16 @@ __global__ void __launch_bounds__(FT *(M / 16), sizeof(T) == 4 ? 4 : 2) k_r2c_fu
         const T eps = static_cast<T>(p.eps);
         const T *val = static_cast<const T *>(p.val);
         T *out = static_cast<T *>(p.out) + static_cast<long long>(clip) * p.out_clip_stride + (f0 - p.out_frame_origin);
+        const bool dense = p.mapping == SGX_MAP_ERB;       // ErbFilterbank::apply_to_power_spectrum (src/erb.rs:384-398)
         for (int row = tid; row < p.n_bins; row += FT * TPF) {
-            const int e0 = __ldg(p.row_ptr + row), e1 = __ldg(p.row_ptr + row + 1);
+            const int e0 = dense ? 0 : __ldg(p.row_ptr + row), e1 = dense ? p.out_len : __ldg(p.row_ptr + row + 1);
+            const T *wrow = dense ? static_cast<const T *>(p.dense) + static_cast<long long>(row) * p.out_len : val;
             T acc[FT];
 #pragma unroll
             for (int f = 0; f < FT; ++f) acc[f] = T(0);
             for (int e = e0; e < e1; ++e) {
-                const T w = __ldg(val + e);
-                const T *pc = P + __ldg(p.col + e) * FT;
+                const T w = __ldg(wrow + e);
+                const T *pc = P + (dense ? e : __ldg(p.col + e)) * FT;
                 T x[FT];
 #pragma unroll
                 for (int f = 0; f < FT; ++f) x[f] = pc[f];

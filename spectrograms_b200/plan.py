@@ -72,6 +72,18 @@ class Spectrogram:
     def __len__(self):
         return self.n_bins
 
+    # DLPack (reference: src/python/dlpack.rs, python/spectrograms/torch.py). Device-resident results export as
+    # kDLCUDA without a host round trip -- the reference can only offer CPU tensors.
+    def to_torch(self):
+        return self.data if _is_torch(self.data) else _torch().from_numpy(self.data)
+
+    def __dlpack__(self, stream=None):
+        t = self.to_torch()
+        return t.__dlpack__(stream=stream) if stream is not None else t.__dlpack__()
+
+    def __dlpack_device__(self):
+        return self.to_torch().__dlpack_device__()
+
 
 class StftResult:
     """``StftResult<T>`` (:534-630)."""

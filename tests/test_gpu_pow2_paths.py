@@ -80,3 +80,15 @@ def test_fused_mfcc_erb_loghz_on_pow2(dtype):
     l = sg.SpectrogramPlanner().log_hz_plan(params, sg.LogHzParams(72, 50.0, 7800.0), None, "magnitude", dtype).compute(t).data.cpu().numpy()
     rl = oracle.Plan(oracle.Desc(dtype="f64", n_fft=512, hop=160, mapping="loghz", n_bands=72, f_min=50.0, f_max=7800.0, amp="magnitude")).compute(x.astype(np.float64))
     assert rel_l2(l, rl) <= tol(dtype)
+
+
+def test_dlpack_export_is_device_resident():
+    torch = _torch()
+    x = torch.randn(16000, device="cuda", dtype=torch.float32)
+    params = sg.SpectrogramParams(sg.StftParams(512, 160), 16000.0)
+    spec = sg.SpectrogramPlanner().mel_plan(params, sg.MelParams(40, 0.0, 8000.0), sg.LogParams(-80.0), "db", "float32").compute(x)
+    assert spec.__dlpack_device__()[0] == 2          # kDLCUDA
+    t = torch.from_dlpack(spec)
+    assert t.is_cuda and t.data_ptr() == spec.data.data_ptr() and tuple(t.shape) == (40, 101)
+    host = sg.SpectrogramPlanner().mel_plan(params, sg.MelParams(40, 0.0, 8000.0), sg.LogParams(-80.0), "db", "float32").compute(x.cpu().numpy())
+    assert torch.from_dlpack(host).device.type == "cpu" and np.array_equal(host.data, spec.data.cpu().numpy())
