@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_r2c_fused_n400(const __grid_con
     float *sig1 = sig0 + kBufWords;
     float *ybuf = sig1 + kBufWords;
     float *scratch = ybuf;                     // log-mel tile of the MFCC path: Y is dead once pass 2 is done
-    const int nq_smem = SPARSE ? __ldg(reinterpret_cast<const int *>(P.k.dense)) : 0;
+    const int nq_smem = SPARSE ? __ldg(reinterpret_cast<const int *>(P.k.sched)) : 0;
     int4 *s_quads = reinterpret_cast<int4 *>(ybuf + kYWords);        // [4 * n_quads] {byte offset of P[c0], cnt, weights address, row}
     int *s_qinfo = reinterpret_cast<int *>(s_quads + 4 * nq_smem);   // [kWarps + 1] quad ranges per warp, then [n_quads] max cnt
     // the window is read with warp-uniform addresses in pass 1: a shared-memory broadcast measurably beats the indexed
@@ -239,13 +239,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_r2c_fused_n400(const __grid_con
     const KParams &p = P.k;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const bool vec_ok = p.buf_elems != 0;
+    const bool vec_ok = p.vec_ok != 0;
 
     for (int i = tid; i < kN; i += kThreads) s_win[i] = P.c.win[i];
     if (SPARSE) {
-        // p.dense carries the host-built schedule blob: int n_quads; int qrange[kWarps + 1]; int maxcnt[n_quads];
+        // p.sched is the host-built schedule blob: int n_quads; int qrange[kWarps + 1]; int maxcnt[n_quads];
         // (16-byte aligned) int4 {c0, cnt, padded weight offset, row or -1}[4 * n_quads]
-        const int *blob = reinterpret_cast<const int *>(p.dense);
+        const int *blob = reinterpret_cast<const int *>(p.sched);
         const int nq = __ldg(blob);
         const int hdr = (1 + kWarps + 1 + nq + 3) & ~3;
         const int4 *quads = reinterpret_cast<const int4 *>(blob + hdr);

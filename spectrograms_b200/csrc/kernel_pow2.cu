@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(FT *(M / 16), sizeof(T) == 4 ? 4 : 2) k_r2c_fu
     {
         constexpr int R = 16, B = M / R;
         const long long base = (f0 + fl) * p.hop - p.pad;
-        const bool vec_ok = p.buf_elems != 0;
+        const bool vec_ok = p.vec_ok != 0;
         if (vec_ok && base >= 0 && base + N <= p.n_samples) {
             // interior frame (all but the first / last few of a clip): no bounds logic
             const C *xf = reinterpret_cast<const C *>(x + base) + t;

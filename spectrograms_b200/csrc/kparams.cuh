@@ -42,6 +42,7 @@ struct KParams {
     const int *col;
     const void *val;      // T[nnz]              T::from_f64(value) (:113)
     const void *dense;    // T[n_bins][out_len]  (erb)
+    const void *sched;    // r2c_fused_n400: host-built quad schedule of the sparse mapping (see sgx_api.cu), else null
     // ---- amplitude scaling (AmplitudeScaling :2043-2081)
     int amp;              // sgx_amp
     int apply_db;         // amp == Decibels && db_floor.is_some()
@@ -55,7 +56,8 @@ struct KParams {
     const void *dct_folded;   // T[tasks][n_bins/2][4]: even/odd-symmetric half basis, 4 coefficients per task (n_bins even), or null
     int dct_tasks;            // number of (parity, 4-coefficient group) tasks
     // ---- shared-memory geometry chosen by the host
-    int buf_elems;        // complex elements per ping-pong buffer
+    int buf_elems;        // complex elements per ping-pong buffer (generic family)
+    int vec_ok;           // input base / strides allow the 8- or 16-byte vector (async) load path
     int frame_stride;     // complex elements between frames in a buffer (>= L+1)
     int tile_stride;      // T elements between frames in the power / mel tile
 };

@@ -14,7 +14,7 @@ namespace sgx {
 cudaError_t launch_generic(const KParams &p, bool f64, size_t smem_bytes, cudaStream_t stream);
 
 // r2c_fused_n400: n_fft = 400, hop = 160, f32, any spectrogram / MFCC output (kernel_fast400.cu).
-// p.buf_elems is reused as the "8-byte aligned input" flag; window_f32 is the host copy of the plan window.
+// p.vec_ok says whether the input allows 8-byte async loads; window_f32 is the host copy of the plan window.
 // sparse_table: serve mel / loghz rows from a shared-memory copy of the CSR table (needs rows <= max_sparse_rows and
 // nnz <= max_sparse_nnz); sm_count sizes the persistent grid (2 CTAs per SM).
 cudaError_t launch_fast400(const KParams &p, const float *window_f32, bool sparse_table, int n_quads, int padded_weights,
@@ -25,7 +25,7 @@ int fast400_max_scratch_rows();
 int fast400_warps();
 
 // r2c_fused_pow2: n_fft = 256 .. 8192 (powers of two), f32 / f64 (kernel_pow2.cu). p.FT, p.frame_stride, p.tile_stride and
-// p.tiles_per_clip must be set from the helpers below; p.buf_elems is the "vector loads allowed" flag.
+// p.tiles_per_clip must be set from the helpers below; p.vec_ok is the "vector loads allowed" flag.
 bool pow2_supported(size_t n_fft);
 int pow2_frames_per_tile(size_t n_fft, bool f64);
 int pow2_frame_elems(size_t n_fft);

@@ -129,7 +129,7 @@ struct sgx_plan {
     std::vector<double> dct_folded;  // [tasks][n_mels/2][4]
     int dct_tasks = 0;
     int *d_row_ptr = nullptr, *d_col = nullptr, *d_wofs = nullptr;
-    std::vector<int> wofs;           // padded weight offset per row (fast sparse table)
+    std::vector<int> wofs;           // quad schedule blob of the sparse mapping (r2c_fused_n400)
     // generic-family geometry
     int FT = 1, buf_elems = 0, frame_stride = 0, tile_stride = 0;
     size_t smem_bytes = 0;
@@ -402,15 +402,15 @@ void run_device(sgx_plan &pl, const void *d_samples, size_t n_clips, size_t n_sa
                                                  (pl.desc.output == SGX_OUT_COMPLEX_STFT ? 2 : 1);
         if (pl.fast400 && !pl.force_generic) {
             // 8-byte vector loads need an 8-byte aligned base and an even clip stride
-            q.buf_elems = (reinterpret_cast<uintptr_t>(q.samples) % 8 == 0 && clip_stride % 2 == 0) ? 1 : 0;
-            if (pl.fast400_sparse) q.dense = pl.d_wofs;      // sparse mappings do not use `dense`: it carries the quad schedule
+            q.vec_ok = (reinterpret_cast<uintptr_t>(q.samples) % 8 == 0 && clip_stride % 2 == 0) ? 1 : 0;
+            q.sched = pl.fast400_sparse ? pl.d_wofs : nullptr;
             ck(launch_fast400(q, pl.window_f32.data(), pl.fast400_sparse, pl.sparse_quads, pl.sparse_weights, pl.sm_count, stream), "kernel launch (r2c_fused_n400)");
         } else if (pl.pow2 && !pl.force_generic) {
             q.FT = pl.pow2_ft;
             q.frame_stride = pl.pow2_frame_stride;
             q.tile_stride = pl.pow2_tile_stride;
             // vector loads of (x[2n], x[2n+1]) pairs need pair-aligned addresses: aligned base, even stride, even hop and pad
-            q.buf_elems = (reinterpret_cast<uintptr_t>(q.samples) % (2 * pl.esize) == 0 && clip_stride % 2 == 0 &&
+            q.vec_ok = (reinterpret_cast<uintptr_t>(q.samples) % (2 * pl.esize) == 0 && clip_stride % 2 == 0 &&
                            pl.desc.hop_size % 2 == 0 && q.pad % 2 == 0) ? 1 : 0;
             ck(launch_pow2(q, pl.f64, pl.pow2_smem, stream), "kernel launch (r2c_fused_pow2)");
         } else {
