@@ -316,6 +316,27 @@ __global__ void __launch_bounds__(FT *(M / 16), sizeof(T) == 4 ? 4 : 2) k_r2c_fu
         }
         return;
     }
+    if (p.output == SGX_OUT_SPECTROGRAM && p.mapping == SGX_MAP_LINEAR) {
+        // Identity mapping (FrequencyMapping::apply, Identity arm :1829-1844): scale in registers, transpose through the
+        // tile so that a thread stores the FT consecutive frames of one bin, no index division anywhere.
+        const T eps = static_cast<T>(p.eps);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int k = t + TPF * u;
+            P[k * FT + fl] = amp_scale<T>(xa[u].x * xa[u].x + xa[u].y * xa[u].y, p.amp, p.apply_db, eps);
+            P[(M - k) * FT + fl] = amp_scale<T>(xb[u].x * xb[u].x + xb[u].y * xb[u].y, p.amp, p.apply_db, eps);
+        }
+        if (t == 0) P[(M / 2) * FT + fl] = amp_scale<T>(xm.x * xm.x + xm.y * xm.y, p.amp, p.apply_db, eps);
+        __syncthreads();
+        T *out = static_cast<T *>(p.out) + static_cast<long long>(clip) * p.out_clip_stride + (f0 - p.out_frame_origin);
+        for (int k = tid; k <= M; k += FT * TPF) {
+            T *orow = out + static_cast<long long>(k) * p.out_row_stride;
+#pragma unroll
+            for (int f = 0; f < FT; ++f)
+                if (f < nf) orow[f] = P[k * FT + f];
+        }
+        return;
+    }
     T *pf = P + fl * p.tile_stride;
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
