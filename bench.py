@@ -234,6 +234,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    from spectrograms_b200.sharding import bind_host_to_device
+    numa_bound = bind_host_to_device(local_rank) if world > 1 and not os.environ.get("SGX_BENCH_NO_BIND") else False
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -356,7 +358,7 @@ def main():
         "metric": "log-mel frames/sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if w["dtype"] == "float32" else "f64", "data": "synthetic (seeded white noise, generated on device)",
-        "config": {"workload": w["label"], "clips_per_gpu": w["n_clips"], "frames_per_clip": n_frames, "sharding": f"clips x{world}, no collective",
+        "config": {"workload": w["label"], "clips_per_gpu": w["n_clips"], "frames_per_clip": n_frames, "sharding": f"clips x{world}, no collective", "host_numa_bound": bool(numa_bound),
                    "l2": f"inputs per step {w['n_clips'] * w['n_samples'] * (4 if w['dtype'] == 'float32' else 8) / 1e9:.2f} GB > 126 MB L2 (no flush needed)"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
         "clocks": cs.summary(),

@@ -135,21 +135,19 @@ __device__ __forceinline__ void sparse_quads_epilogue_impl(const KParams &p, con
 #pragma unroll 1
     for (int qi = q0; qi < q1; ++qi) {
         const float4 rf = lds_v4(qbase + 16u * (4 * qi + s));      // {byte offset of P[c0], cnt, weights address, row}
-        const int maxc = s_qinfo[kWarps + 1 + qi];
         const int cnt = __float_as_int(rf.y);
-        unsigned pe = pbase + __float_as_uint(rf.x);
-        unsigned wa = __float_as_uint(rf.z);
+        const unsigned pe = pbase + __float_as_uint(rf.x);
+        const unsigned wa = __float_as_uint(rf.z);
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 1
-        for (int e = 0; e < maxc; ++e, wa += 4, pe += kFT * 4) {
-            const float w = lds_f32(wa);
-            const float4 x = lds_v4(pe);
-            if (e < cnt) {
-                a0 = __fadd_rn(a0, __fmul_rn(w, x.x));
-                a1 = __fadd_rn(a1, __fmul_rn(w, x.y));
-                a2 = __fadd_rn(a2, __fmul_rn(w, x.z));
-                a3 = __fadd_rn(a3, __fmul_rn(w, x.w));
-            }
+        // per-lane trip count: the divergent loop branch masks finished rows, no predicate inside the body
+#pragma unroll 4
+        for (int e = 0; e < cnt; ++e) {
+            const float w = lds_f32(wa + 4u * e);
+            const float4 x = lds_v4(pe + (kFT * 4u) * e);
+            a0 = __fadd_rn(a0, __fmul_rn(w, x.x));
+            a1 = __fadd_rn(a1, __fmul_rn(w, x.y));
+            a2 = __fadd_rn(a2, __fmul_rn(w, x.z));
+            a3 = __fadd_rn(a3, __fmul_rn(w, x.w));
         }
         const int row = __float_as_int(rf.w);
         if (row >= 0) {

@@ -19,6 +19,20 @@ def shard_range(n_clips: int, rank: int, world_size: int) -> Tuple[int, int]:
     return lo, hi
 
 
+def bind_host_to_device(device_index: int) -> bool:
+    """Pin the calling process to the CPU cores NVML reports as local to GPU ``device_index`` (its NUMA node), so that
+    the pinned host buffers a rank allocates afterwards are first-touched next to its own GPU's PCIe root. One process
+    per GPU otherwise leaves placement to chance and the ranks' host<->device copies share one socket's memory and
+    fabric. Returns False (and changes nothing) when NVML or the affinity call is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(int(device_index)))
+        return True
+    except Exception:
+        return False
+
+
 def gather_to_rank0(local, n_clips: int, group=None):
     """Optional result gather (torch.distributed; backend nccl on GPUs, gloo on CPU): rank 0 receives every rank's
     block, concatenated in clip order; other ranks get ``None``. ``local`` is a torch tensor (n_local, rows, frames).
