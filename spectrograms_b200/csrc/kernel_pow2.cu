@@ -165,7 +165,7 @@ template <int M> struct Radices {          // M = 16^P16 * LAST, LAST in {1, 2, 
 };
 
 template <typename T, int M, int FT>
-__global__ void __launch_bounds__(FT *(M / 16), sizeof(T) == 4 ? 4 : 2) k_r2c_fused_pow2(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(FT *(M / 16), (sizeof(T) == 4 ? 4 : 2) * 256 / (FT * (M / 16) > 256 ? FT * (M / 16) : 256)) k_r2c_fused_pow2(const __grid_constant__ KParams p) {
     constexpr int TPF = M / 16, N = 2 * M;
     constexpr int ZS = pad16(M) + 2;                 // complex elements per frame buffer (M+1 spectrum bins fit too)
     using C = Cx<T>;
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(FT *(M / 16), sizeof(T) == 4 ? 4 : 2) k_r2c_fu
                 v[j] = {v[j].x * w.x, v[j].y * w.y};
             }
         } else {
-#pragma unroll 1
+#pragma unroll                      // (static indices only: a rolled loop would push v[] into local memory)
             for (int j = 0; j < R; ++j) {
                 const int n = j * B + t;
                 const long long s0 = base + 2 * n;
@@ -238,32 +238,32 @@ __global__ void __launch_bounds__(FT *(M / 16), sizeof(T) == 4 ? 4 : 2) k_r2c_fu
     // ---- post pass: X[k] = E + W_N^k O, X[M-k] = conj(E - W_N^k O); thread owns k = t + TPF*u (u < 8), plus k = M/2
     //      and k = 0 / M on thread 0. Values are held in registers across the barrier because the tile may alias z.
     const C *post = static_cast<const C *>(p.post);
-    C xa[8], xb[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    auto post_pair = [&](int u, C &xa, C &xb) {
         const int k = t + TPF * u;                 // 0 .. M/2 - 1
         if (k == 0) {
             const C z0 = z[0];
-            xa[u] = {z0.x + z0.y, T(0)};           // bin 0
-            xb[u] = {z0.x - z0.y, T(0)};           // bin M
+            xa = {z0.x + z0.y, T(0)};              // bin 0
+            xb = {z0.x - z0.y, T(0)};              // bin M
         } else {
             const C a = z[pad16(k)], b = z[pad16(M - k)];
             const C ev = {T(0.5) * (a.x + b.x), T(0.5) * (a.y - b.y)};
             const C od = {T(0.5) * (a.y + b.y), T(0.5) * (b.x - a.x)};
             const C wo = od * ldg_cx<T>(post + k);
-            xa[u] = ev + wo;                       // bin k
+            xa = ev + wo;                          // bin k
             const C d = ev - wo;
-            xb[u] = {d.x, -d.y};                   // bin M - k
+            xb = {d.x, -d.y};                      // bin M - k
         }
-    }
-    C xm = {T(0), T(0)};
-    if (t == 0) {                                  // bin M/2: E and O are both Z[M/2]-derived, W_N^(M/2) = -i
-        const C a = z[pad16(M / 2)];
-        xm = {a.x, -a.y};
-    }
-    __syncthreads();
-
+    };
     if (p.output == SGX_OUT_COMPLEX_STFT) {
+        C xa[8], xb[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) post_pair(u, xa[u], xb[u]);
+        C xm = {T(0), T(0)};
+        if (t == 0) {                              // bin M/2: E and O are both Z[M/2]-derived, W_N^(M/2) = -i
+            const C a = z[pad16(M / 2)];
+            xm = {a.x, -a.y};
+        }
+        __syncthreads();
         typename Cplx<T>::type *S = reinterpret_cast<typename Cplx<T>::type *>(zbuf) + fl * p.frame_stride;
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
@@ -276,6 +276,22 @@ __global__ void __launch_bounds__(FT *(M / 16), sizeof(T) == 4 ? 4 : 2) k_r2c_fu
         epilogue_complex<T>(p, reinterpret_cast<typename Cplx<T>::type *>(zbuf), clip, f0, nf);
         return;
     }
+    // every other output starts from the power spectrum (norm_sqr, src/spectrogram.rs:1332-1334): square before the
+    // barrier, so only one value per bin stays live across it
+    T pa[8], pb[8], pm = T(0);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        C xa, xb;
+        post_pair(u, xa, xb);
+        pa[u] = xa.x * xa.x + xa.y * xa.y;
+        pb[u] = xb.x * xb.x + xb.y * xb.y;
+    }
+    if (t == 0) {
+        const C a = z[pad16(M / 2)];
+        pm = a.x * a.x + a.y * a.y;
+    }
+    __syncthreads();
+
     T *P = reinterpret_cast<T *>(zbuf);
     const bool rows_per_thread = FT <= 8 && p.output == SGX_OUT_SPECTROGRAM && p.mapping != SGX_MAP_LINEAR;
     if (rows_per_thread) {
@@ -285,10 +301,10 @@ __global__ void __launch_bounds__(FT *(M / 16), sizeof(T) == 4 ? 4 : 2) k_r2c_fu
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int k = t + TPF * u;
-            P[k * FT + fl] = xa[u].x * xa[u].x + xa[u].y * xa[u].y;
-            P[(M - k) * FT + fl] = xb[u].x * xb[u].x + xb[u].y * xb[u].y;
+            P[k * FT + fl] = pa[u];
+            P[(M - k) * FT + fl] = pb[u];
         }
-        if (t == 0) P[(M / 2) * FT + fl] = xm.x * xm.x + xm.y * xm.y;
+        if (t == 0) P[(M / 2) * FT + fl] = pm;
         __syncthreads();
         const T eps = static_cast<T>(p.eps);
         const T *val = static_cast<const T *>(p.val);
@@ -300,14 +316,31 @@ __global__ void __launch_bounds__(FT *(M / 16), sizeof(T) == 4 ? 4 : 2) k_r2c_fu
             T acc[FT];
 #pragma unroll
             for (int f = 0; f < FT; ++f) acc[f] = T(0);
-            for (int e = e0; e < e1; ++e) {
-                const T w = __ldg(wrow + e);
-                const T *pc = P + (dense ? e : __ldg(p.col + e)) * FT;
-                T x[FT];
+            if (dense || p.rows_contig) {
+                // consecutive columns: no per-entry index load, and the weight / tile loads of an unrolled group are
+                // independent of each other (the accumulation order stays ascending)
+                const int cnt = e1 - e0;
+                const T *pc = P + ((dense || cnt == 0) ? 0 : __ldg(p.col + e0)) * FT;
+                wrow += e0;
+#pragma unroll 4
+                for (int i = 0; i < cnt; ++i) {
+                    const T w = __ldg(wrow + i);
+                    T x[FT];
 #pragma unroll
-                for (int f = 0; f < FT; ++f) x[f] = pc[f];
+                    for (int f = 0; f < FT; ++f) x[f] = pc[i * FT + f];
 #pragma unroll
-                for (int f = 0; f < FT; ++f) acc[f] = t_add_rn(acc[f], t_mul_rn(w, x[f]));
+                    for (int f = 0; f < FT; ++f) acc[f] = t_add_rn(acc[f], t_mul_rn(w, x[f]));
+                }
+            } else {
+                for (int e = e0; e < e1; ++e) {
+                    const T w = __ldg(wrow + e);
+                    const T *pc = P + __ldg(p.col + e) * FT;
+                    T x[FT];
+#pragma unroll
+                    for (int f = 0; f < FT; ++f) x[f] = pc[f];
+#pragma unroll
+                    for (int f = 0; f < FT; ++f) acc[f] = t_add_rn(acc[f], t_mul_rn(w, x[f]));
+                }
             }
             T *orow = out + static_cast<long long>(row) * p.out_row_stride;
 #pragma unroll
@@ -317,23 +350,25 @@ __global__ void __launch_bounds__(FT *(M / 16), sizeof(T) == 4 ? 4 : 2) k_r2c_fu
         return;
     }
     if (p.output == SGX_OUT_SPECTROGRAM && p.mapping == SGX_MAP_LINEAR) {
-        // Identity mapping (FrequencyMapping::apply, Identity arm :1829-1844): scale in registers, transpose through the
-        // tile so that a thread stores the FT consecutive frames of one bin, no index division anywhere.
+        // Identity mapping (FrequencyMapping::apply, Identity arm :1829-1844): scale in registers, park the tile frame-major
+        // (stride PS chosen so that both sides are conflict free), then store with lanes = (bin, frame), frame fastest:
+        // every bin row receives its FT consecutive frames from adjacent lanes, i.e. one contiguous run per row.
+        constexpr int PS = ((M + 1 + 31) & ~31) + ((32 / FT) / (int(sizeof(T)) / 4) > 0 ? (32 / FT) / (int(sizeof(T)) / 4) : 1);
+        static_assert(PS <= 2 * ZS, "frame-major tile must fit the FFT buffer");
         const T eps = static_cast<T>(p.eps);
+        T *pfm = P + fl * PS;
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int k = t + TPF * u;
-            P[k * FT + fl] = amp_scale<T>(xa[u].x * xa[u].x + xa[u].y * xa[u].y, p.amp, p.apply_db, eps);
-            P[(M - k) * FT + fl] = amp_scale<T>(xb[u].x * xb[u].x + xb[u].y * xb[u].y, p.amp, p.apply_db, eps);
+            pfm[k] = amp_scale<T>(pa[u], p.amp, p.apply_db, eps);
+            pfm[M - k] = amp_scale<T>(pb[u], p.amp, p.apply_db, eps);
         }
-        if (t == 0) P[(M / 2) * FT + fl] = amp_scale<T>(xm.x * xm.x + xm.y * xm.y, p.amp, p.apply_db, eps);
+        if (t == 0) pfm[M / 2] = amp_scale<T>(pm, p.amp, p.apply_db, eps);
         __syncthreads();
         T *out = static_cast<T *>(p.out) + static_cast<long long>(clip) * p.out_clip_stride + (f0 - p.out_frame_origin);
-        for (int k = tid; k <= M; k += FT * TPF) {
-            T *orow = out + static_cast<long long>(k) * p.out_row_stride;
-#pragma unroll
-            for (int f = 0; f < FT; ++f)
-                if (f < nf) orow[f] = P[k * FT + f];
+        for (int idx = tid; idx < (M + 1) * FT; idx += FT * TPF) {
+            const int k = idx / FT, f = idx % FT;
+            if (f < nf) out[static_cast<long long>(k) * p.out_row_stride + f] = P[f * PS + k];
         }
         return;
     }
@@ -341,10 +376,10 @@ __global__ void __launch_bounds__(FT *(M / 16), sizeof(T) == 4 ? 4 : 2) k_r2c_fu
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
         const int k = t + TPF * u;
-        pf[k] = xa[u].x * xa[u].x + xa[u].y * xa[u].y;      // norm_sqr (src/spectrogram.rs:1332-1334)
-        pf[M - k] = xb[u].x * xb[u].x + xb[u].y * xb[u].y;
+        pf[k] = pa[u];
+        pf[M - k] = pb[u];
     }
-    if (t == 0) pf[M / 2] = xm.x * xm.x + xm.y * xm.y;
+    if (t == 0) pf[M / 2] = pm;
     __syncthreads();
     // scratch for the fused-MFCC log-mel tile sits behind the power tile (host sizes the buffer for it)
     epilogue_from_power<T>(p, P, P + FT * p.tile_stride, clip, f0, nf);
@@ -362,10 +397,12 @@ cudaError_t launch_one(const KParams &p, size_t smem, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
-// frames per tile: ~256 threads per CTA (f32) / 128-256 (f64)
+// frames per tile: 256 threads per CTA. (512-thread f64 tiles for n_fft >= 4096 store wider rows but leave one CTA per
+// SM with nothing to overlap its load and drain phases with: 3.52 ms against 3.20 ms on BASELINE configs[4].)
 constexpr int ft_of(int M, bool f64) {
     const int tpf = M / 16;
-    const int want = f64 ? 256 : 256;
+    const int want = 256;
+    (void)f64;
     const int ft = want / tpf;
     return ft < 1 ? 1 : (ft > 32 ? 32 : ft);
 }

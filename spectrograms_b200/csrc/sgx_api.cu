@@ -144,6 +144,7 @@ struct sgx_plan {
     size_t pow2_smem = 0;
     bool fast400_sparse = false;     // ... with the shared-memory sparse table
     int sparse_quads = 0, sparse_weights = 0;
+    bool rows_contig = false;        // CSR rows have consecutive columns
     int sm_count = 148;
     std::vector<float> window_f32;
     // staging for host-pointer calls
@@ -270,6 +271,7 @@ void select_family(sgx_plan &pl) {
         pl.sparse_quads = nq;
         pl.sparse_weights = padded;
     }
+    pl.rows_contig = csr && contiguous;
     pl.fast400_sparse = pl.fast400 && csr && contiguous && fast400_sparse_fits(pl.sparse_quads, pl.sparse_weights);
     pl.kernel_name = pl.fast400 ? "r2c_fused_n400" : pl.pow2 ? "r2c_fused_pow2" : "r2c_fused_generic";
     // folded DCT basis for the fused MFCC epilogue: B[c][n-1-i] = (-1)^c B[c][i] -> half basis, tasks of 4 coefficients of
@@ -309,7 +311,6 @@ void choose_generic_geometry(sgx_plan &pl) {
     if (ft < 1) backend("n_fft too large for the CUDA plan (one frame exceeds shared memory)");
     if (ft > 32) ft = 32;
     pl.FT = static_cast<int>(ft);
-    pl.frame_stride = static_cast<int>(per_frame_cplx >= fs ? per_frame_cplx : fs);
     pl.tile_stride = static_cast<int>(ts);
     pl.buf_elems = static_cast<int>(per_frame_cplx * ft);
     pl.frame_stride = static_cast<int>(fs);
@@ -361,6 +362,7 @@ void fill_params(const sgx_plan &pl, KParams &p) {
     p.window = pl.d_window; p.tw = pl.d_tw; p.post = pl.d_post;
     p.mapping = d.mapping;
     p.n_bins = static_cast<int>(pl.tab.n_bins);
+    p.rows_contig = pl.rows_contig ? 1 : 0;
     p.row_ptr = pl.d_row_ptr; p.col = pl.d_col; p.val = pl.d_val; p.dense = pl.d_dense;
     p.amp = d.amp;
     p.apply_db = (d.amp == SGX_AMP_DECIBELS && d.has_floor_db) ? 1 : 0;     // quirk F7: Decibels + None = raw power
