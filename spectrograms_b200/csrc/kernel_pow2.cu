@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(FT *(M / 16), (sizeof(T) == 4 ? 4 : 2) * 256 /
     __syncthreads();
 
     T *P = reinterpret_cast<T *>(zbuf);
-    const bool rows_per_thread = FT <= 8 && p.output == SGX_OUT_SPECTROGRAM && p.mapping != SGX_MAP_LINEAR;
+    const bool rows_per_thread = FT <= 8 && p.output == SGX_OUT_SPECTROGRAM && p.mapping != SGX_MAP_LINEAR && p.n_lane_slots > 0;
     if (rows_per_thread) {
         // Small tiles, sparse mapping: power tile transposed to P[bin][FT] so that one filterbank row = one thread reads all
         // FT frames of a column with a single vector load, and every weight / column index is loaded once per FT outputs.
@@ -307,42 +307,28 @@ __global__ void __launch_bounds__(FT *(M / 16), (sizeof(T) == 4 ? 4 : 2) * 256 /
         if (t == 0) P[(M / 2) * FT + fl] = pm;
         __syncthreads();
         const T eps = static_cast<T>(p.eps);
-        const T *val = static_cast<const T *>(p.val);
+        const T *lw = static_cast<const T *>(p.lane_w);
         T *out = static_cast<T *>(p.out) + static_cast<long long>(clip) * p.out_clip_stride + (f0 - p.out_frame_origin);
-        const bool dense = p.mapping == SGX_MAP_ERB;       // ErbFilterbank::apply_to_power_spectrum (src/erb.rs:384-398)
-        for (int row = tid; row < p.n_bins; row += FT * TPF) {
-            const int e0 = dense ? 0 : __ldg(p.row_ptr + row), e1 = dense ? p.out_len : __ldg(p.row_ptr + row + 1);
-            const T *wrow = dense ? static_cast<const T *>(p.dense) + static_cast<long long>(row) * p.out_len : val;
+        // lane slots from the host-built schedule (sgx_api.cu, build_lane_rows): rows of similar length share a warp, the
+        // weight of entry i of the warp's 32 rows is one coalesced line, the tile read is a 16-byte vector per column
+        for (int slot = tid; slot < p.n_lane_slots; slot += FT * TPF) {
+            const int4 d = __ldg(p.lane_rows + slot);            // {row, first column, count, weight block}
+            const T *wl = lw + d.w + (slot & 31);
+            const T *pc = P + d.y * FT;
             T acc[FT];
 #pragma unroll
             for (int f = 0; f < FT; ++f) acc[f] = T(0);
-            if (dense || p.rows_contig) {
-                // consecutive columns: no per-entry index load, and the weight / tile loads of an unrolled group are
-                // independent of each other (the accumulation order stays ascending)
-                const int cnt = e1 - e0;
-                const T *pc = P + ((dense || cnt == 0) ? 0 : __ldg(p.col + e0)) * FT;
-                wrow += e0;
 #pragma unroll 4
-                for (int i = 0; i < cnt; ++i) {
-                    const T w = __ldg(wrow + i);
-                    T x[FT];
+            for (int i = 0; i < d.z; ++i) {
+                const T w = __ldg(wl + i * 32);
+                T x[FT];
 #pragma unroll
-                    for (int f = 0; f < FT; ++f) x[f] = pc[i * FT + f];
+                for (int f = 0; f < FT; ++f) x[f] = pc[i * FT + f];
 #pragma unroll
-                    for (int f = 0; f < FT; ++f) acc[f] = t_add_rn(acc[f], t_mul_rn(w, x[f]));
-                }
-            } else {
-                for (int e = e0; e < e1; ++e) {
-                    const T w = __ldg(wrow + e);
-                    const T *pc = P + __ldg(p.col + e) * FT;
-                    T x[FT];
-#pragma unroll
-                    for (int f = 0; f < FT; ++f) x[f] = pc[f];
-#pragma unroll
-                    for (int f = 0; f < FT; ++f) acc[f] = t_add_rn(acc[f], t_mul_rn(w, x[f]));
-                }
+                for (int f = 0; f < FT; ++f) acc[f] = t_add_rn(acc[f], t_mul_rn(w, x[f]));
             }
-            T *orow = out + static_cast<long long>(row) * p.out_row_stride;
+            if (d.x < 0) continue;
+            T *orow = out + static_cast<long long>(d.x) * p.out_row_stride;
 #pragma unroll
             for (int f = 0; f < FT; ++f)
                 if (f < nf) orow[f] = amp_scale<T>(acc[f], p.amp, p.apply_db, eps);

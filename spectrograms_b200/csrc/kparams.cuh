@@ -42,7 +42,9 @@ struct KParams {
     const int *col;
     const void *val;      // T[nnz]              T::from_f64(value) (:113)
     const void *dense;    // T[n_bins][out_len]  (erb)
-    int rows_contig;      // every CSR row's columns are consecutive (mel triangles, loghz pairs): col[e] = col[e0] + (e - e0)
+    const int4 *lane_rows;    // r2c_fused_pow2 rows epilogue: per lane slot {row or -1, first column, count, weight block offset}
+    const void *lane_w;       // T: weights, lane-major per warp block: [block offset + i * 32 + lane]
+    int n_lane_slots;         // multiple of 32 (0: table absent)
     const void *sched;    // r2c_fused_n400: host-built quad schedule of the sparse mapping (see sgx_api.cu), else null
     // ---- amplitude scaling (AmplitudeScaling :2043-2081)
     int amp;              // sgx_amp

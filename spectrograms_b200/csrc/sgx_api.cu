@@ -145,6 +145,10 @@ struct sgx_plan {
     bool fast400_sparse = false;     // ... with the shared-memory sparse table
     int sparse_quads = 0, sparse_weights = 0;
     bool rows_contig = false;        // CSR rows have consecutive columns
+    std::vector<int> lane_rows;      // r2c_fused_pow2 rows epilogue: int4 per lane slot
+    std::vector<double> lane_w;      // ... and its lane-major weights
+    int *d_lane_rows = nullptr;
+    void *d_lane_w = nullptr;
     int sm_count = 148;
     std::vector<float> window_f32;
     // staging for host-pointer calls
@@ -158,6 +162,8 @@ struct sgx_plan {
         if (d_row_ptr) cudaFree(d_row_ptr);
         if (d_col) cudaFree(d_col);
         if (d_wofs) cudaFree(d_wofs);
+        if (d_lane_rows) cudaFree(d_lane_rows);
+        if (d_lane_w) cudaFree(d_lane_w);
         for (auto &s : slot) {
             if (s.d_in) cudaFree(s.d_in);
             if (s.d_out) cudaFree(s.d_out);
@@ -183,6 +189,62 @@ void factorise(sgx_plan &pl) {
     while (rem % 5 == 0) { pl.radix.push_back(5); rem /= 5; }
     if (rem > 1) pl.radix.insert(pl.radix.begin(), static_cast<int>(rem));   // cofactor stage (primes >= 7), evaluated directly
     if (static_cast<int>(pl.radix.size()) > kMaxStages) backend("too many FFT stages");
+}
+
+
+// Lane-major schedule of the filterbank rows for the rows-per-thread epilogue of r2c_fused_pow2 (one lane = one row, all
+// frames of the tile): rows sorted by length so that a warp's 32 rows finish together, quarter-warps arranged so that
+// their first columns differ modulo 8 (the 16-byte tile reads of 8 lanes then hit 8 different bank groups), and the
+// weights transposed per warp block to [entry][lane] so that one warp-wide weight load is one 128-byte line instead of
+// 32 lines. Dense ERB rows are the same thing with first column 0 and length out_len.
+void build_lane_rows(sgx_plan &pl) {
+    pl.lane_rows.clear();
+    pl.lane_w.clear();
+    const sgx_plan_desc &d = pl.desc;
+    const bool dense = d.mapping == SGX_MAP_ERB;
+    if (!(dense || pl.rows_contig) || d.output != SGX_OUT_SPECTROGRAM) return;
+    const size_t nb = pl.tab.n_bins, ol = pl.tab.out_len;
+    std::vector<int> c0(nb), cnt(nb);
+    for (size_t r = 0; r < nb; ++r) {
+        if (dense) { c0[r] = 0; cnt[r] = static_cast<int>(ol); continue; }
+        const int e0 = pl.tab.row_ptr[r], e1 = pl.tab.row_ptr[r + 1];
+        cnt[r] = e1 - e0;
+        c0[r] = cnt[r] ? pl.tab.col[e0] : 0;
+    }
+    std::vector<int> order(nb);
+    for (size_t r = 0; r < nb; ++r) order[r] = static_cast<int>(r);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cnt[a] > cnt[b]; });
+    while (order.size() % 32) order.push_back(-1);
+    for (size_t w0 = 0; w0 < order.size(); w0 += 32) {
+        // greedy: fill each group of 8 lanes with rows whose (first column mod 8) is not in the group yet
+        std::vector<int> pool(order.begin() + w0, order.begin() + w0 + 32), arranged;
+        while (!pool.empty()) {
+            bool used[8] = {false, false, false, false, false, false, false, false};
+            for (int k = 0; k < 8 && !pool.empty(); ++k) {
+                size_t pick = 0;
+                for (size_t i = 0; i < pool.size(); ++i)
+                    if (pool[i] >= 0 && !used[c0[pool[i]] & 7]) { pick = i; break; }
+                if (pool[pick] >= 0) used[c0[pool[pick]] & 7] = true;
+                arranged.push_back(pool[pick]);
+                pool.erase(pool.begin() + pick);
+            }
+        }
+        int maxc = 0;
+        for (int r : arranged) if (r >= 0) maxc = std::max(maxc, cnt[r]);
+        const size_t wofs = pl.lane_w.size();
+        pl.lane_w.resize(wofs + static_cast<size_t>(maxc) * 32, 0.0);
+        for (int lane = 0; lane < 32; ++lane) {
+            const int r = arranged[lane];
+            pl.lane_rows.push_back(r);
+            pl.lane_rows.push_back(r >= 0 ? c0[r] : 0);
+            pl.lane_rows.push_back(r >= 0 ? cnt[r] : 0);
+            pl.lane_rows.push_back(static_cast<int>(wofs));
+            if (r < 0) continue;
+            for (int i = 0; i < cnt[r]; ++i)
+                pl.lane_w[wofs + static_cast<size_t>(i) * 32 + lane] =
+                    dense ? pl.tab.dense[static_cast<size_t>(r) * ol + i] : pl.tab.val[pl.tab.row_ptr[r] + i];
+        }
+    }
 }
 
 void select_family(sgx_plan &pl) {
@@ -272,6 +334,7 @@ void select_family(sgx_plan &pl) {
         pl.sparse_weights = padded;
     }
     pl.rows_contig = csr && contiguous;
+    build_lane_rows(pl);
     pl.fast400_sparse = pl.fast400 && csr && contiguous && fast400_sparse_fits(pl.sparse_quads, pl.sparse_weights);
     pl.kernel_name = pl.fast400 ? "r2c_fused_n400" : pl.pow2 ? "r2c_fused_pow2" : "r2c_fused_generic";
     // folded DCT basis for the fused MFCC epilogue: B[c][n-1-i] = (-1)^c B[c][i] -> half basis, tasks of 4 coefficients of
@@ -337,6 +400,8 @@ void ensure_device(sgx_plan &pl) {
     pl.d_row_ptr = upload_int(pl.tab.row_ptr);
     pl.d_col = upload_int(pl.tab.col);
     pl.d_wofs = upload_int(pl.wofs);
+    pl.d_lane_rows = upload_int(pl.lane_rows);
+    pl.d_lane_w = upload(pl.lane_w, pl.f64);
     pl.d_val = upload(pl.tab.val, pl.f64);
     pl.d_dense = upload(pl.tab.dense, pl.f64);
     pl.d_dct = upload(pl.tab.dct, pl.f64);
@@ -362,7 +427,9 @@ void fill_params(const sgx_plan &pl, KParams &p) {
     p.window = pl.d_window; p.tw = pl.d_tw; p.post = pl.d_post;
     p.mapping = d.mapping;
     p.n_bins = static_cast<int>(pl.tab.n_bins);
-    p.rows_contig = pl.rows_contig ? 1 : 0;
+    p.lane_rows = reinterpret_cast<const int4 *>(pl.d_lane_rows);
+    p.lane_w = pl.d_lane_w;
+    p.n_lane_slots = static_cast<int>(pl.lane_rows.size() / 4);
     p.row_ptr = pl.d_row_ptr; p.col = pl.d_col; p.val = pl.d_val; p.dense = pl.d_dense;
     p.amp = d.amp;
     p.apply_db = (d.amp == SGX_AMP_DECIBELS && d.has_floor_db) ? 1 : 0;     // quirk F7: Decibels + None = raw power
