@@ -151,13 +151,32 @@ __device__ __forceinline__ void pass_store(Cx<T> *z, int t, Cx<T> *v) {
     }
 }
 
-// Barrier among the TPF threads that share one frame's buffer: frames of a tile progress independently of each other
-// through the FFT passes (warp-level sync when a frame fits a warp, a named barrier per frame otherwise).
-template <int TPF, int FT> __device__ __forceinline__ void frame_sync(int fl) {
+// Thread -> (frame, thread-in-frame) map. Frames that fit a warp (TPF <= 32) keep their threads together and need only
+// warp-level syncs between passes. Bigger frames (TPF >= 64, FT <= 4) are INTERLEAVED: every warp holds 32 / FT
+// consecutive threads of each of the tile's FT frames, so that the transposed tile writes P[bin][FT] of a warp cover 32
+// consecutive words (they were FT-way bank conflicts with one frame per warp), the window load of a warp is one line
+// shared by its FT frames, and the frame-strided FFT accesses stay conflict free because the frame stride is 8 mod 16
+// complex elements. The price is a CTA-wide barrier between passes instead of a per-frame one.
+template <int TPF, int FT> struct ThreadMap {
+    static constexpr bool kInterleaved = TPF >= 64 && FT > 1;
+    static constexpr int LPF = kInterleaved ? 32 / FT : TPF;        // lanes of one frame inside a warp
+    static __device__ __forceinline__ void get(int tid, int &fl, int &t) {
+        if (kInterleaved) {
+            const int lane = tid & 31, w = tid >> 5;
+            fl = lane / LPF;
+            t = (lane % LPF) + LPF * w;
+        } else {
+            fl = tid / TPF;
+            t = tid - fl * TPF;
+        }
+    }
+};
+template <int TPF, int FT> __device__ __forceinline__ void frame_sync(int) {
     if (TPF <= 32) __syncwarp();
-    else if (FT == 1) __syncthreads();
-    else asm volatile("bar.sync %0, %1;" ::"r"(fl + 1), "n"(TPF) : "memory");
+    else __syncthreads();
 }
+
+constexpr int zs_of(int M) { return pad16(M) + 8; }   // complex elements per frame buffer: >= M + 1 bins, 8 mod 16 for M >= 256
 
 template <int M> struct Radices {          // M = 16^P16 * LAST, LAST in {1, 2, 4, 8}
     static constexpr int P16 = M >= 4096 ? 3 : (M >= 256 ? 2 : 1);
@@ -167,13 +186,14 @@ template <int M> struct Radices {          // M = 16^P16 * LAST, LAST in {1, 2, 
 template <typename T, int M, int FT>
 __global__ void __launch_bounds__(FT *(M / 16), (sizeof(T) == 4 ? 4 : 2) * 256 / (FT * (M / 16) > 256 ? FT * (M / 16) : 256)) k_r2c_fused_pow2(const __grid_constant__ KParams p) {
     constexpr int TPF = M / 16, N = 2 * M;
-    constexpr int ZS = pad16(M) + 2;                 // complex elements per frame buffer (M+1 spectrum bins fit too)
+    constexpr int ZS = zs_of(M);                     // complex elements per frame buffer (M+1 spectrum bins fit too)
     using C = Cx<T>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C *zbuf = reinterpret_cast<C *>(smem_raw);
 
     const int tid = threadIdx.x;
-    const int fl = tid / TPF, t = tid - fl * TPF;    // frame within the tile, thread within the frame
+    int fl, t;                                       // frame within the tile, thread within the frame
+    ThreadMap<TPF, FT>::get(tid, fl, t);
     const int clip = blockIdx.x / p.tiles_per_clip;
     const int tile = blockIdx.x - clip * p.tiles_per_clip;
     const long long f0 = p.frame_begin + static_cast<long long>(tile) * FT;
@@ -399,7 +419,7 @@ bool pow2_supported(size_t n_fft) {
     return n_fft >= 256 && n_fft <= 8192 && (n_fft & (n_fft - 1)) == 0;
 }
 int pow2_frames_per_tile(size_t n_fft, bool f64) { return ft_of(static_cast<int>(n_fft / 2), f64); }
-int pow2_frame_elems(size_t n_fft) { return pad16(static_cast<int>(n_fft / 2)) + 2; }
+int pow2_frame_elems(size_t n_fft) { return zs_of(static_cast<int>(n_fft / 2)); }
 
 cudaError_t launch_pow2(const KParams &p, bool f64, size_t smem, cudaStream_t stream) {
 #define SGX_POW2_CASE(MM)                                                                         \
