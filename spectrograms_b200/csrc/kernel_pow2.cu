@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(FT *(M / 16), (sizeof(T) == 4 ? 4 : 2) * 256 /
         return;
     }
     if (p.output == SGX_OUT_SPECTROGRAM && p.mapping == SGX_MAP_LINEAR) {
-        // Identity mapping (FrequencyMapping::apply, Identity arm :1829-1844): scale in registers, park the tile frame-major
+        // Identity mapping (FrequencyMapping::apply, Identity arm :1829-1844): park the power tile frame-major
         // (stride PS chosen so that both sides are conflict free), then store with lanes = (bin, frame), frame fastest:
         // every bin row receives its FT consecutive frames from adjacent lanes, i.e. one contiguous run per row.
         constexpr int PS = ((M + 1 + 31) & ~31) + ((32 / FT) / (int(sizeof(T)) / 4) > 0 ? (32 / FT) / (int(sizeof(T)) / 4) : 1);
@@ -366,15 +366,18 @@ __global__ void __launch_bounds__(FT *(M / 16), (sizeof(T) == 4 ? 4 : 2) * 256 /
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int k = t + TPF * u;
-            pfm[k] = amp_scale<T>(pa[u], p.amp, p.apply_db, eps);
-            pfm[M - k] = amp_scale<T>(pb[u], p.amp, p.apply_db, eps);
+            pfm[k] = pa[u];
+            pfm[M - k] = pb[u];
         }
-        if (t == 0) pfm[M / 2] = amp_scale<T>(pm, p.amp, p.apply_db, eps);
+        if (t == 0) pfm[M / 2] = pm;
         __syncthreads();
+        // the scaling sits in the (rolled) store loop: one inlined sqrt / log instead of 17 copies -- the f64 square
+        // root is long enough that the unrolled form ran out of instruction cache
         T *out = static_cast<T *>(p.out) + static_cast<long long>(clip) * p.out_clip_stride + (f0 - p.out_frame_origin);
+#pragma unroll 2
         for (int idx = tid; idx < (M + 1) * FT; idx += FT * TPF) {
             const int k = idx / FT, f = idx % FT;
-            if (f < nf) out[static_cast<long long>(k) * p.out_row_stride + f] = P[f * PS + k];
+            if (f < nf) out[static_cast<long long>(k) * p.out_row_stride + f] = amp_scale<T>(P[f * PS + k], p.amp, p.apply_db, eps);
         }
         return;
     }
