@@ -342,8 +342,24 @@ def main():
             traffic = json.load(open(tpath)).get(args.workload, {}).get(plan.kernel_name())
         except Exception:
             traffic = None
+    # FP roofline next to the HBM one (the path is FFT arithmetic, not a copy): executed FP lane-operations per frame
+    # (profiles/fp_ops.json, from the ncu SASS opcode mix) x frames/s against lanes/clk/SM x SMs x the sampled SM clock
+    fp = None
+    fpath = os.path.join(ROOT, "profiles", "fp_ops.json")
+    clk = cs.summary()
+    if os.path.exists(fpath) and clk.get("sm_mhz"):
+        try:
+            ent = json.load(open(fpath)).get(args.workload, {}).get(plan.kernel_name())
+            if ent:
+                sms = torch.cuda.get_device_properties(dev).multi_processor_count
+                fp_peak = ent["lanes_per_clk_per_sm"] * sms * clk["sm_mhz"] * 1e6 / 1e12
+                fp_ach = ent["lane_ops_per_frame"] * frames_per_step / (kernel_ms * 1e-3) / 1e12
+                fp = {"pipe": ent["pipe"], "achieved": fp_ach, "peak": fp_peak, "unit": "T lane-op/s", "frac": fp_ach / fp_peak,
+                      "lane_ops_per_frame": ent["lane_ops_per_frame"], "peak_source": ent["peak_source"]}
+        except Exception:
+            fp = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": plan.kernel_name(), "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src}
+                "kernel": plan.kernel_name(), "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src, "fp": fp}
 
     cpu = None
     if not args.no_cpu and world == 1:
@@ -361,7 +377,7 @@ def main():
         "config": {"workload": w["label"], "clips_per_gpu": w["n_clips"], "frames_per_clip": n_frames, "sharding": f"clips x{world}, no collective", "host_numa_bound": bool(numa_bound),
                    "l2": f"inputs per step {w['n_clips'] * w['n_samples'] * (4 if w['dtype'] == 'float32' else 8) / 1e9:.2f} GB > 126 MB L2 (no flush needed)"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
-        "clocks": cs.summary(),
+        "clocks": clk,
     }
     if gather is not None:
         line["optional_gather"] = gather
