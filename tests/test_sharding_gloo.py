@@ -49,3 +49,25 @@ def test_two_rank_shard_and_gather(tmp_path, n_clips):
     mp.spawn(_worker, args=(2, _free_port(), n_clips, out), nprocs=2, join=True)
     err, n = np.load(out)
     assert n == n_clips and err == 0.0
+
+
+def test_shard_range_partitions_every_clip_once():
+    from spectrograms_b200.sharding import shard_range
+    for n in (1, 5, 8, 1024, 1025):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))          # contiguous, no overlap, no gap
+    with pytest.raises(ValueError):
+        shard_range(8, 2, 2)
+
+
+def test_bind_host_to_device_degrades_without_nvml():
+    # On a box without NVML (this container) or without the affinity call it must return False and leave the process
+    # affinity untouched; on a GPU box it returns True and the affinity is whatever NVML reports for that GPU.
+    from spectrograms_b200.sharding import bind_host_to_device
+    before = os.sched_getaffinity(0)
+    ok = bind_host_to_device(0)
+    assert isinstance(ok, bool)
+    if not ok:
+        assert os.sched_getaffinity(0) == before
