@@ -359,7 +359,10 @@ def main():
         except Exception:
             fp = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": plan.kernel_name(), "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src, "fp": fp}
+                "kernel": plan.kernel_name(), "kernel_ms": kernel_ms, "kernel_ms_median": float(np.median(per_launch_ms)) / max(1, launches_per_step),
+                "kernel_ms_best": float(np.min(per_launch_ms)) / max(1, launches_per_step),
+                "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                "frac_of_nominal_8000_GBps": achieved / 8000.0, "fp": fp}
 
     cpu = None
     if not args.no_cpu and world == 1:
