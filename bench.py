@@ -39,6 +39,8 @@ WORKLOADS = {
                   label="configs[2] music mel-dB per-GPU shard: 512 clips x 30 s @22.05 kHz, n_fft=2048 hop=512 128 mels dB f32"),
     "mfcc": dict(n_clips=1024, n_samples=160000, sr=16000.0, n_fft=400, hop=160, dtype="float32", kind="mfcc",
                  label="configs[3] MFCC per-GPU shard: 1024 clips x 10 s @16 kHz, n_fft=400 hop=160 128 mels -> 40 MFCC f32"),
+    "chroma": dict(n_clips=512, n_samples=661500, sr=22050.0, n_fft=2048, hop=512, dtype="float32", kind="chroma",
+                   label="SURVEY 8f rank 2, chromagram() on the configs[2] shard: 512 clips x 30 s @22.05 kHz, n_fft=2048 hop=512 -> 12 pitch classes (L2) f32"),
     "multichannel": dict(n_clips=64, n_samples=2880000, sr=48000.0, n_fft=4096, hop=1024, dtype="float64", kind="linear_mag",
                          label="configs[4] multichannel STFT magnitude: 64 ch x 60 s @48 kHz, n_fft=4096 hop=1024 f64"),
 }
@@ -50,7 +52,7 @@ def frames_of(w):
 
 
 def out_rows(w):
-    return {"mel_db": 128, "mfcc": 40, "linear_mag": w["n_fft"] // 2 + 1}[w["kind"]]
+    return {"mel_db": 128, "mfcc": 40, "chroma": 12, "linear_mag": w["n_fft"] // 2 + 1}[w["kind"]]
 
 
 def algorithmic_bytes(w):
@@ -66,6 +68,8 @@ def make_plan(w, device=None):
         return sg.SpectrogramPlanner(device).mel_plan(params, sg.MelParams(128, 0.0, w["sr"] / 2), sg.LogParams(-80.0), "db", w["dtype"])
     if w["kind"] == "mfcc":
         return sg.MfccPlan(params.stft, w["sr"], 128, sg.MfccParams(40), w["dtype"], device)
+    if w["kind"] == "chroma":
+        return sg.ChromaPlan(params.stft, w["sr"], sg.ChromaParams.music_standard(), w["dtype"], device)
     return sg.SpectrogramPlanner(device).linear_plan(params, None, "magnitude", w["dtype"])
 
 
@@ -224,6 +228,12 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
+    if w["kind"] == "chroma":
+        args.no_cpu = True          # the oracle has no batched chroma driver (parity: tests/test_chroma.py)
+        if args.impl == "reference":
+            if rank == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "no batched CPU driver for the chroma workload; it is not a BASELINE config"}))
+            return
     if args.impl == "reference":
         run_reference(args, w, rank, world)
         return

@@ -50,8 +50,14 @@ typedef enum {
     SGX_WIN_CUSTOM = 6    /* custom_window[custom_window_len] */
 } sgx_window;
 
-/* frequency scales: LinearHz / Mel / Erb / LogHz marker types (MappingKind :1639-1656; Cqt is out of scope) */
-typedef enum { SGX_MAP_LINEAR = 0, SGX_MAP_MEL = 1, SGX_MAP_ERB = 2, SGX_MAP_LOGHZ = 3 } sgx_mapping;
+/* frequency scales: LinearHz / Mel / Erb / LogHz marker types (MappingKind :1639-1656; Cqt is out of scope).
+ * SGX_MAP_CHROMA is the fused chromagram() (src/chroma.rs:487-503): linear magnitude spectrogram -> 12 x bins chroma
+ * filterbank (build_chroma_filterbank, src/chroma.rs:279-346) -> per-frame normalisation (:406-453); it requires
+ * amp = SGX_AMP_MAGNITUDE, no dB floor, output = SGX_OUT_SPECTROGRAM and yields 12 rows. */
+typedef enum { SGX_MAP_LINEAR = 0, SGX_MAP_MEL = 1, SGX_MAP_ERB = 2, SGX_MAP_LOGHZ = 3, SGX_MAP_CHROMA = 4 } sgx_mapping;
+
+/* ChromaNorm (src/chroma.rs:31-45) */
+typedef enum { SGX_CHROMANORM_NONE = 0, SGX_CHROMANORM_L1 = 1, SGX_CHROMANORM_L2 = 2, SGX_CHROMANORM_MAX = 3 } sgx_chroma_norm;
 
 /* AmpScaleSpec implementors Power / Magnitude / Decibels (:1986-2037) */
 typedef enum { SGX_AMP_POWER = 0, SGX_AMP_MAGNITUDE = 1, SGX_AMP_DECIBELS = 2 } sgx_amp;
@@ -100,6 +106,10 @@ typedef struct {
     size_t lifter;
 
     int device;                 /* CUDA ordinal; -1 = current device */
+
+    /* SGX_MAP_CHROMA only: ChromaParams (src/chroma.rs:18-30); f_min / f_max above are its frequency range */
+    double chroma_tuning;       /* A4 reference in Hz, finite and > 0 (:82-86) */
+    sgx_chroma_norm chroma_norm;
 } sgx_plan_desc;
 
 typedef struct sgx_plan sgx_plan;
@@ -172,6 +182,20 @@ sgx_status sgx_plan_compute_frame(sgx_plan *plan, const void *samples, size_t n_
 sgx_status sgx_mfcc_from_log_mel(sgx_dtype dtype, const void *log_mel, size_t n_clips, size_t n_mels,
                                  size_t n_frames, size_t n_mfcc, int include_c0, size_t lifter, void *out,
                                  int device, void *cuda_stream);
+
+/*
+ * chromagram_from_spectrogram (src/chroma.rs:365-404): spec is (n_clips, n_bins, n_frames) of T with
+ * n_bins == n_fft/2 + 1 (DimensionMismatch otherwise, :376-379), any amplitude scale; out is (n_clips, 12, n_frames).
+ * The filterbank is built in f64 and cast per element (T::from_f64), rows accumulate in ascending bin order, then the
+ * per-frame normalisation. Host or device pointers (both the same kind).
+ */
+sgx_status sgx_chroma_from_spectrogram(sgx_dtype dtype, const void *spec, size_t n_clips, size_t n_bins, size_t n_frames,
+                                       double sample_rate_hz, size_t n_fft, double tuning, double f_min, double f_max,
+                                       sgx_chroma_norm norm, void *out, int device, void *cuda_stream);
+
+/* build_chroma_filterbank (src/chroma.rs:279-346) into dense_out[12][n_fft/2 + 1] (f64, host). */
+sgx_status sgx_chroma_filterbank(double sample_rate_hz, size_t n_fft, double tuning, double f_min, double f_max,
+                                 double *dense_out);
 
 /* free fn fft() / rfft helpers (:4490-4520): one unnormalised R2C of n_in <= n_fft samples (zero padded), no window.
  * out: n_fft/2+1 Complex<T>. n_in > n_fft -> SGX_INVALID_INPUT "Input length (..) exceeds FFT size (..)". */

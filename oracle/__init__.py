@@ -83,6 +83,11 @@ def lib():
         L.orc_mfcc_from_log_mel.restype = C.c_int
         L.orc_mfcc_from_log_mel.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int,
                                             C.c_size_t, C.c_int, C.c_void_p]
+        L.orc_chroma_filterbank.restype = C.c_int
+        L.orc_chroma_filterbank.argtypes = [C.c_double, C.c_size_t, C.c_double, C.c_double, C.c_double, C.c_void_p]
+        L.orc_chroma_from_spectrogram.restype = C.c_int
+        L.orc_chroma_from_spectrogram.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_double, C.c_size_t,
+                                                  C.c_double, C.c_double, C.c_double, C.c_int, C.c_void_p]
         L.orc_rfft.restype = C.c_int
         L.orc_rfft.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]
         L.orc_compute_batch.restype = C.c_int
@@ -230,6 +235,39 @@ def mfcc_from_log_mel(log_mel: np.ndarray, n_mfcc: int, include_c0: bool = True,
     if rc:
         raise OracleError(lib().orc_last_error().decode())
     return out
+
+
+CHROMA_NORMS = {"none": 0, "l1": 1, "l2": 2, "max": 3}
+
+
+def chroma_filterbank(sample_rate: float, n_fft: int, tuning: float = 440.0, f_min: float = 32.7, f_max: float = 4186.0) -> np.ndarray:
+    """build_chroma_filterbank (src/chroma.rs:279-346): (12, n_fft//2 + 1) f64."""
+    out = np.empty((12, n_fft // 2 + 1), dtype=np.float64)
+    if lib().orc_chroma_filterbank(sample_rate, n_fft, tuning, f_min, f_max, out.ctypes.data):
+        raise OracleError(lib().orc_last_error().decode())
+    return out
+
+
+def chroma_from_spectrogram(spec: np.ndarray, sample_rate: float, n_fft: int, tuning: float = 440.0, f_min: float = 32.7,
+                            f_max: float = 4186.0, norm: str = "l2") -> np.ndarray:
+    """chromagram_from_spectrogram (src/chroma.rs:365-404): (n_bins, n_frames) -> (12, n_frames), same dtype."""
+    spec = np.ascontiguousarray(spec)
+    assert spec.dtype in (np.float32, np.float64) and spec.ndim == 2
+    out = np.empty((12, spec.shape[1]), dtype=spec.dtype)
+    rc = lib().orc_chroma_from_spectrogram(F32 if spec.dtype == np.float32 else F64, spec.ctypes.data, spec.shape[0], spec.shape[1],
+                                           sample_rate, n_fft, tuning, f_min, f_max, CHROMA_NORMS[norm], out.ctypes.data)
+    if rc:
+        raise OracleError(lib().orc_last_error().decode())
+    return out
+
+
+def chromagram(x: np.ndarray, n_fft: int, hop: int, sample_rate: float, window: str = "hanning", centre: bool = True,
+               tuning: float = 440.0, f_min: float = 32.7, f_max: float = 4186.0, norm: str = "l2") -> np.ndarray:
+    """chromagram() (src/chroma.rs:487-503): Spectrogram::<LinearHz, Magnitude, T>::compute, then the function above."""
+    x = np.ascontiguousarray(x)
+    d = Desc(dtype="f32" if x.dtype == np.float32 else "f64", n_fft=n_fft, hop=hop, sample_rate=sample_rate, window=window,
+             centre=centre, mapping="linear", amp="magnitude")
+    return chroma_from_spectrogram(Plan(d).compute(x), sample_rate, n_fft, tuning, f_min, f_max, norm)
 
 
 def rfft(x: np.ndarray, n_fft: int) -> np.ndarray:

@@ -11,7 +11,7 @@
  *       (tests/golden/ + tests/test_oracle_*.py list them with file:line), and
  *   (2) outputs of the reference's own NumPy restatement python/examples/numpy_impls.py (stft, power,
  *       magnitude, dB, hann_window), imported from /root/reference by tests/golden/make_golden.py.
- * The mel/ERB/LogHz/MFCC numerics have no reference-side vectors: they are restated line by line and
+ * The mel/ERB/LogHz/MFCC/chroma numerics have no reference-side vectors: they are restated line by line and
  * cross-checked by an independent NumPy restatement (oracle/oracle_np.py); "parity unpinned" for those values.
  *
  * All citations are relative to the reference checkout (src/spectrogram.rs unless a file is named).
@@ -461,6 +461,79 @@ int orc_mfcc_from_log_mel(int dtype, const void *log_mel, size_t n_mels, size_t 
         rc = mfcc_from_log_mel_f64((const double *)log_mel, n_mels, n_frames, n_mfcc, include_c0, lifter, faithful, (double *)out);
     if (rc) snprintf(g_err, sizeof(g_err), "n_mfcc must be <= n_mels");       /* src/mfcc.rs:231-233 */
     return rc;
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/* Chroma (src/chroma.rs). ChromaParams::new checks :81-97; build_chroma_filterbank :279-346.        */
+static int chroma_check(double sample_rate, double tuning, double f_min, double f_max) {
+    if (!(sample_rate > 0.0 && isfinite(sample_rate))) { snprintf(g_err, sizeof(g_err), "sample_rate must be finite and > 0"); return 1; }
+    if (!(tuning > 0.0 && isfinite(tuning))) { snprintf(g_err, sizeof(g_err), "tuning must be finite and > 0"); return 1; }
+    if (!(f_min > 0.0 && isfinite(f_min))) { snprintf(g_err, sizeof(g_err), "f_min must be finite and > 0"); return 1; }
+    if (f_max <= f_min) { snprintf(g_err, sizeof(g_err), "f_max must be > f_min"); return 1; }
+    return 0;
+}
+
+int orc_chroma_filterbank(double sample_rate, size_t n_fft, double tuning, double f_min, double f_max, double *out) {
+    g_err[0] = 0;
+    if (chroma_check(sample_rate, tuning, f_min, f_max)) return 1;
+    const size_t n_bins = n_fft / 2 + 1;
+    const double freq_resolution = sample_rate / (double)n_fft;                      /* :293 */
+    memset(out, 0, sizeof(double) * 12 * n_bins);
+    for (size_t bin = 0; bin < n_bins; ++bin) {
+        const double freq = (double)bin * freq_resolution;                           /* :296 */
+        if (freq < f_min || freq > f_max || freq <= 0.0) continue;                   /* :308-310 */
+        const double midi_note = 69.0 + 12.0 * log(freq / tuning) / M_LN2;           /* :313 */
+        double pitch_class = fmod(midi_note, 12.0);                                  /* rem_euclid :316 */
+        if (pitch_class < 0.0) pitch_class += 12.0;
+        for (size_t c = 0; c < 12; ++c) {
+            const double dist = fabs(pitch_class - (double)c);                       /* :324 */
+            const double circular_dist = fmin(dist, 12.0 - dist);
+            const double q = circular_dist / 1.0;                                    /* sigma = 1 semitone :328 */
+            out[c * n_bins + bin] = exp(-0.5 * (q * q));                             /* :329 */
+        }
+    }
+    for (size_t c = 0; c < 12; ++c) {                                                /* rows to unit sum :336-343 */
+        double row_sum = 0.0;
+        for (size_t i = 0; i < n_bins; ++i) row_sum += out[c * n_bins + i];
+        if (row_sum > 0.0)
+            for (size_t i = 0; i < n_bins; ++i) out[c * n_bins + i] /= row_sum;
+    }
+    return 0;
+}
+
+#define ORC_CHROMA_APPLY(NAME, REAL, SQRT, FMAXF)                                                                     \
+    static void NAME(const REAL *spec, size_t n_bins, size_t n_frames, const double *fb, int norm, REAL *out) {       \
+        for (size_t f = 0; f < n_frames; ++f) {                                                                       \
+            REAL c[12];                                                                                               \
+            for (size_t r = 0; r < 12; ++r) {                      /* :384-394: sum += T::from_f64(w) * x, ascending */ \
+                REAL sum = (REAL)0;                                                                                   \
+                for (size_t k = 0; k < n_bins; ++k) sum += (REAL)fb[r * n_bins + k] * spec[k * n_frames + f];         \
+                c[r] = sum;                                                                                           \
+            }                                                                                                         \
+            REAL d = (REAL)0;                                      /* apply_chroma_normalization :406-453 */          \
+            if (norm == ORC_CHROMANORM_L1) { for (int i = 0; i < 12; ++i) d = d + c[i]; }                             \
+            else if (norm == ORC_CHROMANORM_L2) { for (int i = 0; i < 12; ++i) d = d + c[i] * c[i]; d = SQRT(d); }    \
+            else if (norm == ORC_CHROMANORM_MAX) { for (int i = 0; i < 12; ++i) d = FMAXF(d, c[i]); }                 \
+            if (norm != ORC_CHROMANORM_NONE && d > (REAL)0) for (int i = 0; i < 12; ++i) c[i] /= d;                   \
+            for (size_t r = 0; r < 12; ++r) out[r * n_frames + f] = c[r];                                             \
+        }                                                                                                             \
+    }
+ORC_CHROMA_APPLY(chroma_apply_f32, float, sqrtf, fmaxf)
+ORC_CHROMA_APPLY(chroma_apply_f64, double, sqrt, fmax)
+
+int orc_chroma_from_spectrogram(int dtype, const void *spec, size_t n_bins, size_t n_frames, double sample_rate,
+                                size_t n_fft, double tuning, double f_min, double f_max, int norm, void *out) {
+    g_err[0] = 0;
+    if (n_bins != n_fft / 2 + 1) {                                                   /* :376-379 */
+        snprintf(g_err, sizeof(g_err), "Dimension mismatch: expected %zu, got %zu", n_fft / 2 + 1, n_bins);
+        return 2;
+    }
+    double *fb = (double *)malloc(sizeof(double) * 12 * n_bins);
+    if (orc_chroma_filterbank(sample_rate, n_fft, tuning, f_min, f_max, fb)) { free(fb); return 1; }
+    if (dtype == ORC_F32) chroma_apply_f32((const float *)spec, n_bins, n_frames, fb, norm, (float *)out);
+    else chroma_apply_f64((const double *)spec, n_bins, n_frames, fb, norm, (double *)out);
+    free(fb);
+    return 0;
 }
 
 /* single-frame R2C of <= n_fft samples, zero padded: free fn fft() (:4490-4520) */

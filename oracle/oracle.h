@@ -64,6 +64,12 @@ void orc_compute_stft(orc_plan *p, const void *samples, size_t n_samples, void *
 void orc_compute_frame(orc_plan *p, const void *samples, size_t n_samples, size_t frame_idx, void *out);
 int orc_mfcc_from_log_mel(int dtype, const void *log_mel, size_t n_mels, size_t n_frames, size_t n_mfcc,
                           int include_c0, size_t lifter, int faithful, void *out);
+enum { ORC_CHROMANORM_NONE = 0, ORC_CHROMANORM_L1 = 1, ORC_CHROMANORM_L2 = 2, ORC_CHROMANORM_MAX = 3 };
+/* src/chroma.rs: build_chroma_filterbank (:279-346) into out[12][n_fft/2+1]; chromagram_from_spectrogram (:365-404)
+ * with apply_chroma_normalization (:406-453): spec (n_bins, n_frames) of dtype -> out (12, n_frames). 0 = ok. */
+int orc_chroma_filterbank(double sample_rate, size_t n_fft, double tuning, double f_min, double f_max, double *out);
+int orc_chroma_from_spectrogram(int dtype, const void *spec, size_t n_bins, size_t n_frames, double sample_rate,
+                                size_t n_fft, double tuning, double f_min, double f_max, int norm, void *out);
 int orc_rfft(int dtype, const void *x, size_t n_in, size_t n_fft, void *out);
 int orc_compute_batch(const orc_desc *d, const void *samples, size_t n_clips, size_t n_samples, size_t clip_stride,
                       void *out, size_t out_stride, int n_threads,

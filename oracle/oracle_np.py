@@ -183,3 +183,31 @@ def mfcc_from_log_mel(log_mel, n_mfcc, include_c0=True, lifter=22):   # src/mfcc
     if not include_c0 and n_mfcc > 1:
         out = out[1:]
     return out
+
+
+def chroma_filterbank(sample_rate, n_fft, tuning=440.0, f_min=32.7, f_max=4186.0):   # src/chroma.rs:279-346, vectorised
+    n_bins = n_fft // 2 + 1
+    freqs = np.arange(n_bins, dtype=np.float64) * (sample_rate / n_fft)
+    fb = np.zeros((12, n_bins))
+    ok = (freqs >= f_min) & (freqs <= f_max) & (freqs > 0.0)
+    midi = 69.0 + 12.0 * np.log(freqs[ok] / tuning) / np.log(2.0)
+    pc = np.mod(midi, 12.0)
+    dist = np.abs(pc[None, :] - np.arange(12, dtype=np.float64)[:, None])
+    circ = np.minimum(dist, 12.0 - dist)
+    fb[:, ok] = np.exp(-0.5 * circ ** 2)
+    s = fb.sum(axis=1, keepdims=True)
+    return np.where(s > 0.0, fb / np.where(s > 0.0, s, 1.0), fb)
+
+
+def chroma_from_spectrogram(spec, sample_rate, n_fft, tuning=440.0, f_min=32.7, f_max=4186.0, norm="l2"):   # :365-453
+    dt = spec.dtype
+    c = (chroma_filterbank(sample_rate, n_fft, tuning, f_min, f_max).astype(dt) @ spec).astype(dt)   # summation order differs
+    if norm == "l1":
+        d = c.sum(axis=0, keepdims=True)
+    elif norm == "l2":
+        d = np.sqrt((c * c).sum(axis=0, keepdims=True))
+    elif norm == "max":
+        d = np.maximum(c.max(axis=0, keepdims=True), 0)
+    else:
+        return c
+    return np.where(d > 0, c / np.where(d > 0, d, 1), c).astype(dt)

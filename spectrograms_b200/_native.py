@@ -17,7 +17,7 @@ EXPORTS = [
     "sgx_last_error_message", "sgx_last_dimension_mismatch", "sgx_version", "sgx_plan_create", "sgx_plan_destroy",
     "sgx_plan_output_shape", "sgx_plan_axes", "sgx_plan_window", "sgx_plan_filterbank", "sgx_plan_kernel_name",
     "sgx_plan_last_launch_count", "sgx_plan_force_generic", "sgx_plan_compute_batch", "sgx_plan_compute_frame",
-    "sgx_mfcc_from_log_mel", "sgx_rfft",
+    "sgx_mfcc_from_log_mel", "sgx_rfft", "sgx_chroma_from_spectrogram", "sgx_chroma_filterbank",
 ]
 
 
@@ -33,6 +33,7 @@ class PlanDesc(C.Structure):
         ("amp", C.c_int), ("has_floor_db", C.c_int), ("floor_db", C.c_double),
         ("output", C.c_int), ("n_mfcc", C.c_size_t), ("include_c0", C.c_int), ("lifter", C.c_size_t),
         ("device", C.c_int),
+        ("chroma_tuning", C.c_double), ("chroma_norm", C.c_int),
     ]
 
 
@@ -68,6 +69,8 @@ def lib() -> C.CDLL:
     L.sgx_plan_compute_frame.argtypes = [vp, vp, sz, sz, vp, vp]
     L.sgx_mfcc_from_log_mel.argtypes = [i, vp, sz, sz, sz, sz, i, sz, vp, i, vp]
     L.sgx_rfft.argtypes = [i, vp, sz, sz, vp, i, vp]
+    L.sgx_chroma_from_spectrogram.argtypes = [i, vp, sz, sz, sz, d, sz, d, d, d, i, vp, i, vp]
+    L.sgx_chroma_filterbank.argtypes = [d, sz, d, d, d, vp]
     for name in EXPORTS:
         getattr(L, name)
     _lib = L

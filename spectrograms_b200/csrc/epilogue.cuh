@@ -19,7 +19,7 @@ namespace sgx {
 // P: power tile, P[f * p.tile_stride + k], f < nf valid frames (rows beyond nf are not read)
 // scratch: second tile region with at least FT * tile_stride elements (used for the log-mel tile when output == MFCC)
 template <typename T>
-__device__ __forceinline__ void epilogue_from_power(const KParams &p, const T *__restrict__ P, T *__restrict__ scratch,
+__device__ __forceinline__ void epilogue_from_power(const KParams &p, T *__restrict__ P, T *__restrict__ scratch,
                                                     int clip, long long f0, int nf) {
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int FT = p.FT;
@@ -27,6 +27,35 @@ __device__ __forceinline__ void epilogue_from_power(const KParams &p, const T *_
     T *out = static_cast<T *>(p.out) + static_cast<long long>(clip) * p.out_clip_stride + (f0 - p.out_frame_origin);
     const bool to_mfcc = (p.output == SGX_OUT_MFCC);
     const int ts = p.tile_stride;
+
+    if (p.mapping == SGX_MAP_CHROMA) {
+        // chromagram() (src/chroma.rs:487-503): magnitude tile -> 12 dense rows in ascending bin order (:384-394) ->
+        // per-frame normalisation (:406-453). scratch holds the un-normalised rows [f * ts + c].
+        for (int idx = tid; idx < p.out_len * FT; idx += nthr) {
+            const int f = idx / p.out_len, k = idx - f * p.out_len;
+            if (f < nf) P[f * ts + k] = t_sqrt(P[f * ts + k]);
+        }
+        __syncthreads();
+        for (int idx = tid; idx < 12 * FT; idx += nthr) {
+            const int row = idx / FT, f = idx - row * FT;
+            if (f >= nf) continue;
+            const T *w = static_cast<const T *>(p.dense) + static_cast<long long>(row) * p.out_len;
+            const T *pf = P + f * ts;
+            T acc = T(0);
+            for (int k = 0; k < p.out_len; ++k) acc = t_add_rn(acc, t_mul_rn(__ldg(w + k), pf[k]));
+            scratch[f * ts + row] = acc;
+        }
+        __syncthreads();
+        for (int f = tid; f < nf; f += nthr) {
+            T c[12];
+#pragma unroll
+            for (int i = 0; i < 12; ++i) c[i] = scratch[f * ts + i];
+            chroma_normalise<T>(c, p.chroma_norm);
+#pragma unroll
+            for (int i = 0; i < 12; ++i) out[static_cast<long long>(i) * p.out_row_stride + f] = c[i];
+        }
+        return;
+    }
 
     // rows x frames, frames fastest
     const int total = p.n_bins * FT;
@@ -93,7 +122,7 @@ __device__ __forceinline__ void epilogue_complex(const KParams &p, const typenam
 // and every store is a 128-byte run of one output row. scratch: [row * 32 + f], >= n_bins * 32 elements (MFCC only).
 // lane_col: the column of this lane's frame inside a tile row (identity unless the family permutes frames in a row).
 template <typename T>
-__device__ __forceinline__ void epilogue_lane_frames(const KParams &p, const T *__restrict__ P, T *__restrict__ scratch,
+__device__ __forceinline__ void epilogue_lane_frames(const KParams &p, T *__restrict__ P, T *__restrict__ scratch,
                                                      int clip, long long f0, int nf, int lane_col) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const T eps = static_cast<T>(p.eps);
@@ -101,6 +130,30 @@ __device__ __forceinline__ void epilogue_lane_frames(const KParams &p, const T *
     const bool to_mfcc = (p.output == SGX_OUT_MFCC);
     const bool live = lane < nf;
     const T *pl = P + lane_col;
+
+    if (p.mapping == SGX_MAP_CHROMA) {
+        // same three steps as in epilogue_from_power; scratch rows are [c * 32 + lane]
+        for (int idx = threadIdx.x; idx < p.out_len * 32; idx += blockDim.x) P[idx] = t_sqrt(P[idx]);
+        __syncthreads();
+        for (int row = warp; row < 12; row += nwarps) {
+            const T *w = static_cast<const T *>(p.dense) + static_cast<long long>(row) * p.out_len;
+            T acc = T(0);
+            for (int k = 0; k < p.out_len; ++k) acc = t_add_rn(acc, t_mul_rn(__ldg(w + k), pl[k * 32]));
+            scratch[row * 32 + lane] = acc;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            T c[12];
+#pragma unroll
+            for (int i = 0; i < 12; ++i) c[i] = scratch[i * 32 + lane];
+            chroma_normalise<T>(c, p.chroma_norm);
+            if (live) {
+#pragma unroll
+                for (int i = 0; i < 12; ++i) out[static_cast<long long>(i) * p.out_row_stride] = c[i];
+            }
+        }
+        return;
+    }
     for (int row = warp; row < p.n_bins; row += nwarps) {
         T acc;
         if (p.mapping == SGX_MAP_LINEAR) {

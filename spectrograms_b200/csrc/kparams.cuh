@@ -46,6 +46,7 @@ struct KParams {
     const void *lane_w;       // T: weights, lane-major per warp block: [block offset + i * 32 + lane]
     int n_lane_slots;         // multiple of 32 (0: table absent)
     const void *sched;    // r2c_fused_n400: host-built quad schedule of the sparse mapping (see sgx_api.cu), else null
+    int chroma_norm;      // sgx_chroma_norm (SGX_MAP_CHROMA: dense holds the 12 x out_len chroma filterbank)
     // ---- amplitude scaling (AmplitudeScaling :2043-2081)
     int amp;              // sgx_amp
     int apply_db;         // amp == Decibels && db_floor.is_some()
@@ -101,6 +102,28 @@ template <typename T> __device__ __forceinline__ T amp_scale(T v, int amp, int a
     if (amp == 1) v = t_sqrt(v);
     if (apply_db) v = t_ten_log10(t_max(v, eps));
     return v;
+}
+
+// apply_chroma_normalization (src/chroma.rs:406-453) on one frame's 12 pitch classes, in the reference's fold order
+template <typename T> __device__ __forceinline__ void chroma_normalise(T (&c)[12], int norm) {
+    T d = T(0);
+    if (norm == SGX_CHROMANORM_L1) {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) d = t_add_rn(d, c[i]);
+    } else if (norm == SGX_CHROMANORM_L2) {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) d = t_add_rn(d, t_mul_rn(c[i], c[i]));
+        d = t_sqrt(d);
+    } else if (norm == SGX_CHROMANORM_MAX) {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) d = t_max(d, c[i]);
+    } else {
+        return;
+    }
+    if (d > T(0)) {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) c[i] = c[i] / d;
+    }
 }
 
 }  // namespace sgx

@@ -35,4 +35,9 @@ cudaError_t launch_pow2(const KParams &p, bool f64, size_t smem_bytes, cudaStrea
 cudaError_t launch_mfcc(bool f64, const void *log_mel, void *out, long long n_clips, int n_mels, long long n_frames,
                         int n_mfcc, int row0, const void *dct, const void *lifter, cudaStream_t stream);
 
+// standalone chromagram_from_spectrogram (kernel_chroma.cu): spec [n_clips][n_bins][n_frames] -> out [n_clips][12][n_frames];
+// w_transposed is the chroma filterbank as T[n_bins][12]
+cudaError_t launch_chroma(bool f64, const void *spec, void *out, long long n_clips, int n_bins, long long n_frames,
+                          const void *w_transposed, int norm, cudaStream_t stream);
+
 }  // namespace sgx

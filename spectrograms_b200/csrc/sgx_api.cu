@@ -431,6 +431,7 @@ void fill_params(const sgx_plan &pl, KParams &p) {
     p.lane_w = pl.d_lane_w;
     p.n_lane_slots = static_cast<int>(pl.lane_rows.size() / 4);
     p.row_ptr = pl.d_row_ptr; p.col = pl.d_col; p.val = pl.d_val; p.dense = pl.d_dense;
+    p.chroma_norm = d.chroma_norm;
     p.amp = d.amp;
     p.apply_db = (d.amp == SGX_AMP_DECIBELS && d.has_floor_db) ? 1 : 0;     // quirk F7: Decibels + None = raw power
     p.eps = d.has_floor_db ? std::pow(10.0, d.floor_db / 10.0) : 0.0;
@@ -583,12 +584,13 @@ sgx_status sgx_plan_filterbank(const sgx_plan *plan, double *dense_out, size_t *
         if (!plan) invalid("null plan");
         const HostTables &t = plan->tab;
         const size_t nb = t.n_bins, ol = t.out_len;
-        if (nnz) *nnz = plan->desc.mapping == SGX_MAP_ERB ? nb * ol : plan->desc.mapping == SGX_MAP_LINEAR ? ol : t.val.size();
+        const bool dense_map = plan->desc.mapping == SGX_MAP_ERB || plan->desc.mapping == SGX_MAP_CHROMA;
+        if (nnz) *nnz = dense_map ? nb * ol : plan->desc.mapping == SGX_MAP_LINEAR ? ol : t.val.size();
         if (!dense_out) return;
         std::fill(dense_out, dense_out + nb * ol, 0.0);
         if (plan->desc.mapping == SGX_MAP_LINEAR) {
             for (size_t r = 0; r < nb; ++r) dense_out[r * ol + r] = 1.0;
-        } else if (plan->desc.mapping == SGX_MAP_ERB) {
+        } else if (dense_map) {
             std::memcpy(dense_out, t.dense.data(), sizeof(double) * nb * ol);
         } else {
             for (size_t r = 0; r < nb; ++r)
@@ -746,6 +748,65 @@ sgx_status sgx_mfcc_from_log_mel(sgx_dtype dtype, const void *log_mel, size_t n_
             }
         } catch (...) { cleanup(); throw; }
         cleanup();
+    });
+}
+
+sgx_status sgx_chroma_filterbank(double sample_rate_hz, size_t n_fft, double tuning, double f_min, double f_max, double *dense_out) {
+    return guarded([&] {
+        if (!dense_out) invalid("null argument");
+        if (n_fft == 0) invalid("n_fft must be set");
+        validate_chroma(sample_rate_hz, tuning, f_min, f_max);
+        std::vector<double> fb;
+        build_chroma_filterbank(sample_rate_hz, n_fft, tuning, f_min, f_max, fb);
+        std::memcpy(dense_out, fb.data(), sizeof(double) * fb.size());
+    });
+}
+
+sgx_status sgx_chroma_from_spectrogram(sgx_dtype dtype, const void *spec, size_t n_clips, size_t n_bins, size_t n_frames,
+                                       double sample_rate_hz, size_t n_fft, double tuning, double f_min, double f_max,
+                                       sgx_chroma_norm norm, void *out, int device, void *cuda_stream) {
+    return guarded([&] {
+        if (!spec || !out) invalid("null argument");
+        if (dtype != SGX_F32 && dtype != SGX_F64) invalid("dtype must be f32 or f64");
+        if (n_fft == 0) invalid("n_fft must be set");
+        if (n_clips == 0 || n_frames == 0) invalid("empty spectrogram");
+        if (n_bins != n_fft / 2 + 1) mismatch(n_fft / 2 + 1, n_bins);                 // src/chroma.rs:376-379
+        validate_chroma(sample_rate_hz, tuning, f_min, f_max);
+        if (norm < SGX_CHROMANORM_NONE || norm > SGX_CHROMANORM_MAX) invalid("unknown chroma normalisation");
+        const bool f64 = dtype == SGX_F64;
+        const size_t es = f64 ? 8 : 4;
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+            cudaGetLastError();
+            backend("no CUDA device available (this library has no CPU fallback)");
+        }
+        int dev = device;
+        if (dev < 0) ck(cudaGetDevice(&dev), "cudaGetDevice");
+        DeviceGuard g(dev);
+        std::vector<double> fb, fbT(12 * n_bins);
+        build_chroma_filterbank(sample_rate_hz, n_fft, tuning, f_min, f_max, fb);
+        for (size_t c = 0; c < 12; ++c)
+            for (size_t k = 0; k < n_bins; ++k) fbT[k * 12 + c] = fb[c * n_bins + k];
+        const PtrKind ki = ptr_kind(spec), ko = ptr_kind(out);
+        if (ki != ko) invalid("spec and out must both be host pointers or both be device pointers");
+        void *d_w = upload(fbT, f64);
+        cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+        void *d_in = nullptr, *d_out = nullptr;
+        cudaError_t e = cudaSuccess;
+        if (ki == PtrKind::Device) {
+            e = launch_chroma(f64, spec, out, static_cast<long long>(n_clips), static_cast<int>(n_bins), static_cast<long long>(n_frames), d_w, norm, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);                       // the table is freed below
+        } else {
+            const size_t ib = n_clips * n_bins * n_frames * es, ob = n_clips * 12 * n_frames * es;
+            e = cudaMalloc(&d_in, ib);
+            if (e == cudaSuccess) e = cudaMalloc(&d_out, ob);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(d_in, spec, ib, cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) e = launch_chroma(f64, d_in, d_out, static_cast<long long>(n_clips), static_cast<int>(n_bins), static_cast<long long>(n_frames), d_w, norm, st);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, ob, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        }
+        cudaFree(d_in); cudaFree(d_out); cudaFree(d_w);
+        ck(e, "chroma_from_spectrogram");
     });
 }
 

@@ -227,6 +227,43 @@ void build_erb(const sgx_plan_desc &d, HostTables &t) {
 
 }  // namespace
 
+// ChromaParams::new (src/chroma.rs:81-112)
+void validate_chroma(double sample_rate_hz, double tuning, double f_min, double f_max) {
+    if (!(sample_rate_hz > 0.0 && std::isfinite(sample_rate_hz))) invalid("sample_rate must be finite and > 0");   // :286-290
+    if (!(tuning > 0.0 && std::isfinite(tuning))) invalid("tuning must be finite and > 0");
+    if (!(f_min > 0.0 && std::isfinite(f_min))) invalid("f_min must be finite and > 0");
+    if (f_max <= f_min) invalid("f_max must be > f_min");
+}
+
+// build_chroma_filterbank (src/chroma.rs:279-346): Gaussian (sigma = 1 semitone) weights on the circular pitch-class
+// distance of every FFT bin inside [f_min, f_max], rows normalised to unit sum. dense: [12][n_fft/2 + 1].
+void build_chroma_filterbank(double sample_rate_hz, size_t n_fft, double tuning, double f_min, double f_max,
+                             std::vector<double> &dense) {
+    const size_t n_bins = n_fft / 2 + 1;
+    const double freq_resolution = sample_rate_hz / static_cast<double>(n_fft);
+    const double ln2 = 0.693147180559945309417232121458176568;     // std::f64::consts::LN_2
+    dense.assign(12 * n_bins, 0.0);
+    for (size_t bin = 0; bin < n_bins; ++bin) {
+        const double freq = static_cast<double>(bin) * freq_resolution;
+        if (freq < f_min || freq > f_max || freq <= 0.0) continue;
+        const double midi_note = 69.0 + 12.0 * std::log(freq / tuning) / ln2;
+        double pitch_class = std::fmod(midi_note, 12.0);           // f64::rem_euclid
+        if (pitch_class < 0.0) pitch_class += 12.0;
+        for (size_t c = 0; c < 12; ++c) {
+            const double dist = std::fabs(pitch_class - static_cast<double>(c));
+            const double circular = std::fmin(dist, 12.0 - dist);
+            const double q = circular / 1.0;
+            dense[c * n_bins + bin] = std::exp(-0.5 * (q * q));
+        }
+    }
+    for (size_t c = 0; c < 12; ++c) {
+        double row_sum = 0.0;
+        for (size_t i = 0; i < n_bins; ++i) row_sum += dense[c * n_bins + i];
+        if (row_sum > 0.0)
+            for (size_t i = 0; i < n_bins; ++i) dense[c * n_bins + i] /= row_sum;
+    }
+}
+
 size_t frame_count(size_t n_samples, size_t n_fft, size_t hop, bool centre) {
     const size_t pad = centre ? n_fft / 2 : 0;
     const size_t padded = n_samples + 2 * pad;
@@ -281,6 +318,13 @@ void validate_desc(const sgx_plan_desc &d) {
             }
             if (d.n_bands > 10000) invalid("n_bins is unreasonably large");           // :1732
             break;
+        case SGX_MAP_CHROMA:
+            validate_chroma(d.sample_rate_hz, d.chroma_tuning, d.f_min, d.f_max);
+            if (d.chroma_norm < SGX_CHROMANORM_NONE || d.chroma_norm > SGX_CHROMANORM_MAX) invalid("unknown chroma normalisation");
+            // chromagram() always runs on Spectrogram::<LinearHz, Magnitude, T> with no dB stage (src/chroma.rs:493-499)
+            if (d.amp != SGX_AMP_MAGNITUDE || d.has_floor_db) invalid("chroma plans take the magnitude spectrogram (amp = magnitude, no dB floor)");
+            if (d.output != SGX_OUT_SPECTROGRAM) invalid("chroma plans produce a (12, n_frames) matrix (output = spectrogram)");
+            break;
         default:
             invalid("unknown frequency mapping");
     }
@@ -331,6 +375,12 @@ void build_tables(const sgx_plan_desc &d, HostTables &t) {
         case SGX_MAP_ERB:
             t.n_bins = d.n_bands;
             build_erb(d, t);
+            break;
+        case SGX_MAP_CHROMA:
+            t.n_bins = 12;
+            build_chroma_filterbank(d.sample_rate_hz, d.n_fft, d.chroma_tuning, d.f_min, d.f_max, t.dense);
+            t.freq_axis.resize(12);
+            for (size_t c = 0; c < 12; ++c) t.freq_axis[c] = static_cast<double>(c);   // pitch classes C .. B (Chromagram::labels, src/chroma.rs:238-242)
             break;
     }
     if (d.output == SGX_OUT_MFCC) build_dct(d.n_mfcc, d.n_bands, d.lifter, t.dct, t.lifter);

@@ -40,6 +40,11 @@ size_t frame_count(size_t n_samples, size_t n_fft, size_t hop, bool centre);
 void validate_desc(const sgx_plan_desc &d);
 void build_tables(const sgx_plan_desc &d, HostTables &t);
 
+// chroma (src/chroma.rs:81-112, :279-346): validation (throws) and the dense [12][n_fft/2 + 1] filterbank
+void validate_chroma(double sample_rate_hz, double tuning, double f_min, double f_max);
+void build_chroma_filterbank(double sample_rate_hz, size_t n_fft, double tuning, double f_min, double f_max,
+                             std::vector<double> &dense);
+
 // DCT-II basis and lifter weights (src/mfcc.rs:278-316)
 void build_dct(size_t n_mfcc, size_t n_mels, size_t lifter, std::vector<double> &basis, std::vector<double> &lift);
 

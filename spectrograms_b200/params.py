@@ -304,6 +304,50 @@ class MfccParams:
         return MfccParams(self._n, self._c0, lifter)
 
 
+class ChromaNorm:
+    """``ChromaNorm`` (src/chroma.rs:31-45): none | l1 | l2 (default) | max."""
+    NONE, L1, L2, MAX = "none", "l1", "l2", "max"
+    ALL = ("none", "l1", "l2", "max")
+
+
+class ChromaParams:
+    """``ChromaParams`` (src/chroma.rs:18-182): defaults tuning=440, f_min=32.7 (C1), f_max=4186 (C8), norm=L2."""
+
+    def __init__(self, tuning: float = 440.0, f_min: float = 32.7, f_max: float = 4186.0, norm: Optional[str] = None):
+        tuning, f_min, f_max = float(tuning), float(f_min), float(f_max)
+        if not (tuning > 0.0 and math.isfinite(tuning)):                      # :82-86
+            raise InvalidInputError("tuning must be finite and > 0")
+        if not (f_min > 0.0 and math.isfinite(f_min)):                        # :87-91
+            raise InvalidInputError("f_min must be finite and > 0")
+        if f_max <= f_min:                                                    # :92-94
+            raise InvalidInputError("f_max must be > f_min")
+        norm = ChromaNorm.L2 if norm is None else str(norm).lower()
+        if norm not in ChromaNorm.ALL:
+            raise InvalidInputError("norm must be one of none, l1, l2, max")
+        self._tuning, self._f_min, self._f_max, self._norm = tuning, f_min, f_max, norm
+        self._n_octaves = max(int(math.ceil(math.log2(f_max / f_min))), 1)    # :97
+
+    tuning = property(lambda s: s._tuning)
+    f_min = property(lambda s: s._f_min)
+    f_max = property(lambda s: s._f_max)
+    norm = property(lambda s: s._norm)
+    n_octaves = property(lambda s: s._n_octaves)
+
+    @classmethod
+    def music_standard(cls) -> "ChromaParams":
+        p = cls(440.0, 32.7, 4186.0, ChromaNorm.L2)
+        p._n_octaves = 7                                                      # the const constructor's literal (:114-122)
+        return p
+
+    def with_norm(self, norm: str) -> "ChromaParams":
+        p = ChromaParams(self._tuning, self._f_min, self._f_max, norm)
+        p._n_octaves = self._n_octaves
+        return p
+
+    def __repr__(self) -> str:
+        return f"ChromaParams(tuning={self._tuning}, f_min={self._f_min}, f_max={self._f_max}, norm={self._norm})"
+
+
 def normalise_dtype(dtype) -> str:
     """dtype strings of the reference's Python layer (src/python/dtype.rs:34-42)."""
     if dtype in ("float32", "f32", np.float32) or (hasattr(dtype, "name") and getattr(dtype, "name", "") == "float32"):

@@ -16,11 +16,12 @@ import numpy as np
 
 from . import _native
 from .errors import InvalidInputError
-from .params import (ErbParams, LogHzParams, LogParams, MelParams, MfccParams, SpectrogramParams, StftParams,
-                     WindowType, normalise_dtype)
+from .params import (ChromaParams, ErbParams, LogHzParams, LogParams, MelParams, MfccParams, SpectrogramParams,
+                     StftParams, WindowType, normalise_dtype)
 
 _WIN = {"rectangular": 0, "hanning": 1, "hamming": 2, "blackman": 3, "kaiser": 4, "gaussian": 5, "custom": 6}
-_MAP = {"linear": 0, "mel": 1, "erb": 2, "loghz": 3}
+_MAP = {"linear": 0, "mel": 1, "erb": 2, "loghz": 3, "chroma": 4}
+_CHROMA_NORM = {"none": 0, "l1": 1, "l2": 2, "max": 3}
 _AMP = {"power": 0, "magnitude": 1, "db": 2, "decibels": 2}
 _NORM = {"none": 0, "slaney": 1, "l1": 2, "l2": 3}
 _OUT_SPEC, _OUT_STFT, _OUT_MFCC = 0, 1, 2
@@ -163,6 +164,9 @@ class _NativePlan:
             d.erb_spacing = 0 if scale.spacing == "linear" else 1
         elif mapping == "loghz":
             d.n_bands, d.f_min, d.f_max = scale.n_bins, scale.f_min, scale.f_max
+        elif mapping == "chroma":
+            d.n_bands, d.f_min, d.f_max = 12, scale.f_min, scale.f_max
+            d.chroma_tuning, d.chroma_norm = scale.tuning, _CHROMA_NORM[scale.norm]
         d.amp = _AMP[self.amp]
         d.has_floor_db = int(db is not None)
         d.floor_db = db.floor_db if db is not None else 0.0
@@ -442,6 +446,54 @@ class MfccPlan:
     def force_generic(self, force: bool = True) -> None: self._n.force_generic(force)
 
 
+class Chromagram:
+    """``Chromagram<T>`` (src/chroma.rs:186-260): (12, n_frames) pitch-class profile; ``data`` is a NumPy array or a
+    CUDA ``torch.Tensor`` depending on what went in."""
+
+    LABELS = ("C", "C#", "D", "D#", "E", "F", "F#", "G", "G#", "A", "A#", "B")      # :238-242
+
+    def __init__(self, data, params: ChromaParams):
+        self.data = data
+        self.params = params
+
+    n_bins = property(lambda s: int(s.data.shape[-2]))
+    n_frames = property(lambda s: int(s.data.shape[-1]))
+    shape = property(lambda s: tuple(s.data.shape))
+
+    @staticmethod
+    def labels() -> Tuple[str, ...]:
+        return Chromagram.LABELS
+
+    def __array__(self, dtype=None):
+        a = self.data.detach().cpu().numpy() if _is_torch(self.data) else self.data
+        return a.astype(dtype) if dtype is not None else a
+
+
+class ChromaPlan:
+    """Fused ``chromagram()`` (src/chroma.rs:487-503): STFT -> magnitude -> 12 x bins chroma filterbank -> per-frame
+    normalisation in one kernel; the magnitude spectrogram never reaches HBM. Reusable and batched like every plan."""
+
+    def __init__(self, stft: StftParams, sample_rate: float, chroma_params: ChromaParams, dtype="float64",
+                 device: Optional[int] = None):
+        self.chroma_params = chroma_params
+        self._n = _NativePlan(SpectrogramParams(stft, sample_rate), dtype, "chroma", chroma_params, "magnitude", None,
+                              device=device)
+
+    def output_shape(self, signal_length: int) -> Tuple[int, int]:
+        return self._n.output_shape(signal_length)
+
+    def compute(self, samples) -> Chromagram:
+        return Chromagram(self._n.compute_one(samples), self.chroma_params)
+
+    def compute_batch(self, clips, out=None):
+        return self._n.compute_batch(clips, out)
+
+    def filterbank(self): return self._n.filterbank()
+    def kernel_name(self) -> str: return self._n.kernel_name()
+    def last_launch_count(self) -> int: return self._n.last_launch_count()
+    def force_generic(self, force: bool = True) -> None: self._n.force_generic(force)
+
+
 class SpectrogramPlanner:
     """``SpectrogramPlanner`` (:640-1153): a stateless factory; all state lives in the returned plan."""
 
@@ -555,6 +607,63 @@ def mfcc(samples, stft_params: StftParams, sample_rate: float, n_mels: int, mfcc
     return MfccPlan(stft_params, sample_rate, n_mels, mfcc_params, dtype or _infer_dtype(samples)).compute(samples)
 
 
+def build_chroma_filterbank(sample_rate: float, n_fft: int, params: ChromaParams) -> np.ndarray:
+    """``build_chroma_filterbank`` (src/chroma.rs:279-346): (12, n_fft // 2 + 1) f64, built by the library's host code."""
+    n_fft = int(n_fft)
+    if n_fft <= 0:
+        raise InvalidInputError("n_fft must be set")
+    out = np.empty((12, n_fft // 2 + 1), dtype=np.float64)
+    _native.check(_native.lib().sgx_chroma_filterbank(float(sample_rate), n_fft, params.tuning, params.f_min, params.f_max,
+                                                      out.ctypes.data))
+    return out
+
+
+def chromagram_from_spectrogram(spectrogram, sample_rate: float, n_fft: int, params: ChromaParams) -> Chromagram:
+    """``chromagram_from_spectrogram`` (src/chroma.rs:365-404). spectrogram: (n_bins, n_frames) or
+    (n_clips, n_bins, n_frames) with n_bins == n_fft // 2 + 1 (``DimensionMismatchError`` otherwise)."""
+    L = _native.lib()
+    norm = _CHROMA_NORM[params.norm]
+    squeeze = False
+    if _is_torch(spectrogram):
+        torch = _torch()
+        x = spectrogram
+        if not x.is_cuda:
+            raise InvalidInputError("torch inputs must be CUDA tensors (use NumPy arrays for host data)")
+        if x.dim() == 2:
+            x, squeeze = x.unsqueeze(0), True
+        if x.dim() != 3 or x.numel() == 0:
+            raise InvalidInputError("spectrogram must be (n_bins, n_frames) or (n_clips, n_bins, n_frames)")
+        x = x.contiguous()
+        dt = normalise_dtype(x.dtype)
+        nc, nb, nf = x.shape
+        out = torch.empty((nc, 12, nf), dtype=x.dtype, device=x.device)
+        with torch.cuda.device(x.device):
+            _native.check(L.sgx_chroma_from_spectrogram(0 if dt == "f32" else 1, x.data_ptr(), nc, nb, nf, float(sample_rate),
+                                                        int(n_fft), params.tuning, params.f_min, params.f_max, norm,
+                                                        out.data_ptr(), x.device.index,
+                                                        torch.cuda.current_stream(x.device).cuda_stream))
+        return Chromagram(out[0] if squeeze else out, params)
+    x = np.asarray(spectrogram)
+    if x.dtype not in (np.float32, np.float64):
+        x = x.astype(np.float64)
+    if x.ndim == 2:
+        x, squeeze = x[None], True
+    if x.ndim != 3 or x.size == 0:
+        raise InvalidInputError("spectrogram must be (n_bins, n_frames) or (n_clips, n_bins, n_frames)")
+    x = np.ascontiguousarray(x)
+    nc, nb, nf = x.shape
+    out = np.empty((nc, 12, nf), dtype=x.dtype)
+    _native.check(L.sgx_chroma_from_spectrogram(0 if x.dtype == np.float32 else 1, x.ctypes.data, nc, nb, nf, float(sample_rate),
+                                                int(n_fft), params.tuning, params.f_min, params.f_max, norm, out.ctypes.data,
+                                                -1, None))
+    return Chromagram(out[0] if squeeze else out, params)
+
+
+def chromagram(samples, stft_params: StftParams, sample_rate: float, chroma_params: ChromaParams, dtype=None) -> Chromagram:
+    """``chromagram<T>()`` (src/chroma.rs:487-503), fused on the GPU."""
+    return ChromaPlan(stft_params, sample_rate, chroma_params, dtype or _infer_dtype(samples)).compute(samples)
+
+
 def rfft(samples, n_fft: int, dtype=None):
     """free ``fft()`` (:4490-4520): one unnormalised R2C of <= n_fft samples, zero padded; no window."""
     L = _native.lib()
@@ -621,3 +730,4 @@ def compute_loghz_power_spectrogram(samples, params, loghz_params, dtype=None): 
 def compute_loghz_magnitude_spectrogram(samples, params, loghz_params, dtype=None): return _one_shot("loghz", "magnitude")(samples, params, loghz_params, None, dtype)
 def compute_loghz_db_spectrogram(samples, params, loghz_params, db_params=None, dtype=None): return _one_shot("loghz", "db")(samples, params, loghz_params, db_params, dtype)
 def compute_mfcc(samples, stft_params, sample_rate, n_mels, mfcc_params, dtype=None): return mfcc(samples, stft_params, sample_rate, n_mels, mfcc_params, dtype)
+def compute_chromagram(samples, stft_params, sample_rate, chroma_params, dtype=None): return chromagram(samples, stft_params, sample_rate, chroma_params, dtype)
