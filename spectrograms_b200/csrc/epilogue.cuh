@@ -41,8 +41,8 @@ __device__ __forceinline__ void epilogue_from_power(const KParams &p, T *__restr
             if (f >= nf) continue;
             const T *w = static_cast<const T *>(p.dense) + static_cast<long long>(row) * p.out_len;
             const T *pf = P + f * ts;
-            T acc = T(0);
-            for (int k = 0; k < p.out_len; ++k) acc = t_add_rn(acc, t_mul_rn(__ldg(w + k), pf[k]));
+            T acc = T(0);                                  // columns outside [dense_c0, dense_c1) are exact zeros
+            for (int k = p.dense_c0; k < p.dense_c1; ++k) acc = t_add_rn(acc, t_mul_rn(__ldg(w + k), pf[k]));
             scratch[f * ts + row] = acc;
         }
         __syncthreads();
@@ -138,7 +138,7 @@ __device__ __forceinline__ void epilogue_lane_frames(const KParams &p, T *__rest
         for (int row = warp; row < 12; row += nwarps) {
             const T *w = static_cast<const T *>(p.dense) + static_cast<long long>(row) * p.out_len;
             T acc = T(0);
-            for (int k = 0; k < p.out_len; ++k) acc = t_add_rn(acc, t_mul_rn(__ldg(w + k), pl[k * 32]));
+            for (int k = p.dense_c0; k < p.dense_c1; ++k) acc = t_add_rn(acc, t_mul_rn(__ldg(w + k), pl[k * 32]));
             scratch[row * 32 + lane] = acc;
         }
         __syncthreads();

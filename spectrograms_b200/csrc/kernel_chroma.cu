@@ -14,7 +14,7 @@ namespace {
 
 template <typename T>
 __global__ void __launch_bounds__(128) k_chroma_rows(const T *__restrict__ spec, T *__restrict__ out, int n_bins,
-                                                     long long n_frames, const T *__restrict__ wT, int norm, int tiles_per_clip) {
+                                                     long long n_frames, const T *__restrict__ wT, int norm, int tiles_per_clip, int k0, int k1) {
     const int clip = blockIdx.x / tiles_per_clip;
     const long long f = static_cast<long long>(blockIdx.x - clip * tiles_per_clip) * blockDim.x + threadIdx.x;
     if (f >= n_frames) return;
@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(128) k_chroma_rows(const T *__restrict__ spec,
 #pragma unroll
     for (int i = 0; i < 12; ++i) c[i] = T(0);
 #pragma unroll 2
-    for (int k = 0; k < n_bins; ++k) {
+    for (int k = k0; k < k1; ++k) {                   // bins outside [k0, k1) carry exactly zero weight in every row
         const T x = src[static_cast<long long>(k) * n_frames];
         const T *w = wT + 12 * k;
 #pragma unroll
@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(128) k_chroma_rows(const T *__restrict__ spec,
 }  // namespace
 
 cudaError_t launch_chroma(bool f64, const void *spec, void *out, long long n_clips, int n_bins, long long n_frames,
-                          const void *w_transposed, int norm, cudaStream_t stream) {
+                          const void *w_transposed, int norm, int k0, int k1, cudaStream_t stream) {
     const long long tiles = (n_frames + 127) / 128;
     const long long grid = n_clips * tiles;
     if (grid <= 0) return cudaSuccess;
@@ -46,11 +46,11 @@ cudaError_t launch_chroma(bool f64, const void *spec, void *out, long long n_cli
     if (f64)
         k_chroma_rows<double><<<static_cast<unsigned>(grid), 128, 0, stream>>>(static_cast<const double *>(spec), static_cast<double *>(out),
                                                                               n_bins, n_frames, static_cast<const double *>(w_transposed),
-                                                                              norm, static_cast<int>(tiles));
+                                                                              norm, static_cast<int>(tiles), k0, k1);
     else
         k_chroma_rows<float><<<static_cast<unsigned>(grid), 128, 0, stream>>>(static_cast<const float *>(spec), static_cast<float *>(out),
                                                                              n_bins, n_frames, static_cast<const float *>(w_transposed),
-                                                                             norm, static_cast<int>(tiles));
+                                                                             norm, static_cast<int>(tiles), k0, k1);
     return cudaGetLastError();
 }
 

@@ -313,6 +313,61 @@ __global__ void __launch_bounds__(FT *(M / 16), (sizeof(T) == 4 ? 4 : 2) * 256 /
     __syncthreads();
 
     T *P = reinterpret_cast<T *>(zbuf);
+    if (FT <= 8 && p.mapping == SGX_MAP_CHROMA && p.dense_t != nullptr) {
+        // chromagram() (src/chroma.rs:487-503) on a small tile. Magnitude tile transposed to P[bin][FT]; thread (r, c) sums
+        // pitch class r over bin chunk c for all FT frames (one 16-byte tile read per bin, shared by the 12 rows of a
+        // chunk; the filterbank is passed transposed, [bin][12], so a chunk's 12 weights are one 48-byte run); the chunk
+        // partials are then added in ascending chunk order. Only the bins inside [f_min, f_max] carry weight (:308-310);
+        // the reference adds exact zeros for the others. Chunked summation is not the reference's strictly sequential
+        // order -- it stays inside the f32 1e-5 / f64 1e-12 budgets (tests/test_chroma.py).
+        constexpr int NT = FT * TPF, CH = NT / 12;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int k = t + TPF * u;
+            P[k * FT + fl] = t_sqrt(pa[u]);
+            P[(M - k) * FT + fl] = t_sqrt(pb[u]);
+        }
+        if (t == 0) P[(M / 2) * FT + fl] = t_sqrt(pm);
+        __syncthreads();
+        T *part = P + (M + 1) * FT;                          // [CH][12][FT] behind the tile (second tile region)
+        const int r = tid % 12, c = tid / 12;
+        if (c < CH) {
+            const int span = p.dense_c1 - p.dense_c0, per = (span + CH - 1) / CH;
+            const int k0 = p.dense_c0 + c * per, k1 = min(k0 + per, p.dense_c1);
+            const T *w = static_cast<const T *>(p.dense_t) + r;
+            T acc[FT];
+#pragma unroll
+            for (int f = 0; f < FT; ++f) acc[f] = T(0);
+#pragma unroll 4
+            for (int k = k0; k < k1; ++k) {
+                const T wk = __ldg(w + 12 * k);
+                T x[FT];
+#pragma unroll
+                for (int f = 0; f < FT; ++f) x[f] = P[k * FT + f];
+#pragma unroll
+                for (int f = 0; f < FT; ++f) acc[f] = t_add_rn(acc[f], t_mul_rn(wk, x[f]));
+            }
+#pragma unroll
+            for (int f = 0; f < FT; ++f) part[(c * 12 + r) * FT + f] = acc[f];
+        }
+        __syncthreads();
+        if (tid < 12 * FT) {                                  // (row, frame): chunk partials in ascending order
+            T sum = T(0);
+            for (int cc = 0; cc < CH; ++cc) sum = t_add_rn(sum, part[cc * 12 * FT + tid]);
+            P[tid] = sum;                                     // the tile is dead: chroma[r][f] at P[r * FT + f]
+        }
+        __syncthreads();
+        if (tid < nf) {
+            T cv[12];
+#pragma unroll
+            for (int i = 0; i < 12; ++i) cv[i] = P[i * FT + tid];
+            chroma_normalise<T>(cv, p.chroma_norm);
+            T *out = static_cast<T *>(p.out) + static_cast<long long>(clip) * p.out_clip_stride + (f0 - p.out_frame_origin) + tid;
+#pragma unroll
+            for (int i = 0; i < 12; ++i) out[static_cast<long long>(i) * p.out_row_stride] = cv[i];
+        }
+        return;
+    }
     const bool rows_per_thread = FT <= 8 && p.output == SGX_OUT_SPECTROGRAM && p.mapping != SGX_MAP_LINEAR && p.n_lane_slots > 0;
     if (rows_per_thread) {
         // Small tiles, sparse mapping: power tile transposed to P[bin][FT] so that one filterbank row = one thread reads all

@@ -46,6 +46,8 @@ struct KParams {
     const void *lane_w;       // T: weights, lane-major per warp block: [block offset + i * 32 + lane]
     int n_lane_slots;         // multiple of 32 (0: table absent)
     const void *sched;    // r2c_fused_n400: host-built quad schedule of the sparse mapping (see sgx_api.cu), else null
+    const void *dense_t;  // T[out_len][n_bins]  the dense matrix transposed (chroma; null otherwise)
+    int dense_c0, dense_c1;   // columns outside [dense_c0, dense_c1) of the dense matrix are exactly zero in every row
     int chroma_norm;      // sgx_chroma_norm (SGX_MAP_CHROMA: dense holds the 12 x out_len chroma filterbank)
     // ---- amplitude scaling (AmplitudeScaling :2043-2081)
     int amp;              // sgx_amp

@@ -36,8 +36,8 @@ cudaError_t launch_mfcc(bool f64, const void *log_mel, void *out, long long n_cl
                         int n_mfcc, int row0, const void *dct, const void *lifter, cudaStream_t stream);
 
 // standalone chromagram_from_spectrogram (kernel_chroma.cu): spec [n_clips][n_bins][n_frames] -> out [n_clips][12][n_frames];
-// w_transposed is the chroma filterbank as T[n_bins][12]
+// w_transposed is the chroma filterbank as T[n_bins][12], non-zero only for bins in [k0, k1)
 cudaError_t launch_chroma(bool f64, const void *spec, void *out, long long n_clips, int n_bins, long long n_frames,
-                          const void *w_transposed, int norm, cudaStream_t stream);
+                          const void *w_transposed, int norm, int k0, int k1, cudaStream_t stream);
 
 }  // namespace sgx

@@ -148,6 +148,9 @@ struct sgx_plan {
     std::vector<int> lane_rows;      // r2c_fused_pow2 rows epilogue: int4 per lane slot
     std::vector<double> lane_w;      // ... and its lane-major weights
     int *d_lane_rows = nullptr;
+    std::vector<double> dense_t;     // chroma: dense matrix transposed to [out_len][n_bins]
+    void *d_dense_t = nullptr;
+    int dense_c0 = 0, dense_c1 = 0;  // nonzero column range of the dense matrix
     void *d_lane_w = nullptr;
     int sm_count = 148;
     std::vector<float> window_f32;
@@ -164,6 +167,7 @@ struct sgx_plan {
         if (d_wofs) cudaFree(d_wofs);
         if (d_lane_rows) cudaFree(d_lane_rows);
         if (d_lane_w) cudaFree(d_lane_w);
+        if (d_dense_t) cudaFree(d_dense_t);
         for (auto &s : slot) {
             if (s.d_in) cudaFree(s.d_in);
             if (s.d_out) cudaFree(s.d_out);
@@ -334,6 +338,23 @@ void select_family(sgx_plan &pl) {
         pl.sparse_weights = padded;
     }
     pl.rows_contig = csr && contiguous;
+    // dense mappings: the column range outside which every row is exactly zero (chroma: bins outside [f_min, f_max]),
+    // and, for chroma, the matrix transposed to [bin][12] for the chunked row sums of r2c_fused_pow2
+    pl.dense_c0 = 0;
+    pl.dense_c1 = static_cast<int>(pl.tab.out_len);
+    pl.dense_t.clear();
+    if (d.mapping == SGX_MAP_CHROMA) {
+        const size_t nb = pl.tab.n_bins, ol = pl.tab.out_len;
+        auto col_zero = [&](size_t k) { for (size_t r = 0; r < nb; ++r) if (pl.tab.dense[r * ol + k] != 0.0) return false; return true; };
+        size_t lo = 0, hi = ol;
+        while (lo < hi && col_zero(lo)) ++lo;
+        while (hi > lo && col_zero(hi - 1)) --hi;
+        pl.dense_c0 = static_cast<int>(lo);
+        pl.dense_c1 = static_cast<int>(hi);
+        pl.dense_t.resize(ol * nb);
+        for (size_t r = 0; r < nb; ++r)
+            for (size_t k = 0; k < ol; ++k) pl.dense_t[k * nb + r] = pl.tab.dense[r * ol + k];
+    }
     build_lane_rows(pl);
     pl.fast400_sparse = pl.fast400 && csr && contiguous && fast400_sparse_fits(pl.sparse_quads, pl.sparse_weights);
     pl.kernel_name = pl.fast400 ? "r2c_fused_n400" : pl.pow2 ? "r2c_fused_pow2" : "r2c_fused_generic";
@@ -402,6 +423,7 @@ void ensure_device(sgx_plan &pl) {
     pl.d_wofs = upload_int(pl.wofs);
     pl.d_lane_rows = upload_int(pl.lane_rows);
     pl.d_lane_w = upload(pl.lane_w, pl.f64);
+    pl.d_dense_t = upload(pl.dense_t, pl.f64);
     pl.d_val = upload(pl.tab.val, pl.f64);
     pl.d_dense = upload(pl.tab.dense, pl.f64);
     pl.d_dct = upload(pl.tab.dct, pl.f64);
@@ -432,6 +454,9 @@ void fill_params(const sgx_plan &pl, KParams &p) {
     p.n_lane_slots = static_cast<int>(pl.lane_rows.size() / 4);
     p.row_ptr = pl.d_row_ptr; p.col = pl.d_col; p.val = pl.d_val; p.dense = pl.d_dense;
     p.chroma_norm = d.chroma_norm;
+    p.dense_t = pl.d_dense_t;
+    p.dense_c0 = pl.dense_c0;
+    p.dense_c1 = pl.dense_c1;
     p.amp = d.amp;
     p.apply_db = (d.amp == SGX_AMP_DECIBELS && d.has_floor_db) ? 1 : 0;     // quirk F7: Decibels + None = raw power
     p.eps = d.has_floor_db ? std::pow(10.0, d.floor_db / 10.0) : 0.0;
@@ -787,6 +812,10 @@ sgx_status sgx_chroma_from_spectrogram(sgx_dtype dtype, const void *spec, size_t
         build_chroma_filterbank(sample_rate_hz, n_fft, tuning, f_min, f_max, fb);
         for (size_t c = 0; c < 12; ++c)
             for (size_t k = 0; k < n_bins; ++k) fbT[k * 12 + c] = fb[c * n_bins + k];
+        auto bin_zero = [&](size_t k) { for (size_t c = 0; c < 12; ++c) if (fbT[k * 12 + c] != 0.0) return false; return true; };
+        size_t k0 = 0, k1 = n_bins;
+        while (k0 < k1 && bin_zero(k0)) ++k0;
+        while (k1 > k0 && bin_zero(k1 - 1)) --k1;
         const PtrKind ki = ptr_kind(spec), ko = ptr_kind(out);
         if (ki != ko) invalid("spec and out must both be host pointers or both be device pointers");
         void *d_w = upload(fbT, f64);
@@ -794,14 +823,14 @@ sgx_status sgx_chroma_from_spectrogram(sgx_dtype dtype, const void *spec, size_t
         void *d_in = nullptr, *d_out = nullptr;
         cudaError_t e = cudaSuccess;
         if (ki == PtrKind::Device) {
-            e = launch_chroma(f64, spec, out, static_cast<long long>(n_clips), static_cast<int>(n_bins), static_cast<long long>(n_frames), d_w, norm, st);
+            e = launch_chroma(f64, spec, out, static_cast<long long>(n_clips), static_cast<int>(n_bins), static_cast<long long>(n_frames), d_w, norm, static_cast<int>(k0), static_cast<int>(k1), st);
             if (e == cudaSuccess) e = cudaStreamSynchronize(st);                       // the table is freed below
         } else {
             const size_t ib = n_clips * n_bins * n_frames * es, ob = n_clips * 12 * n_frames * es;
             e = cudaMalloc(&d_in, ib);
             if (e == cudaSuccess) e = cudaMalloc(&d_out, ob);
             if (e == cudaSuccess) e = cudaMemcpyAsync(d_in, spec, ib, cudaMemcpyHostToDevice, st);
-            if (e == cudaSuccess) e = launch_chroma(f64, d_in, d_out, static_cast<long long>(n_clips), static_cast<int>(n_bins), static_cast<long long>(n_frames), d_w, norm, st);
+            if (e == cudaSuccess) e = launch_chroma(f64, d_in, d_out, static_cast<long long>(n_clips), static_cast<int>(n_bins), static_cast<long long>(n_frames), d_w, norm, static_cast<int>(k0), static_cast<int>(k1), st);
             if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, ob, cudaMemcpyDeviceToHost, st);
             if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         }
