@@ -183,6 +183,35 @@ sgx_status sgx_mfcc_from_log_mel(sgx_dtype dtype, const void *log_mel, size_t n_
                                  size_t n_frames, size_t n_mfcc, int include_c0, size_t lifter, void *out,
                                  int device, void *cuda_stream);
 
+/* Interaural cues (src/binaural.rs): ITD seconds, IPD radians, ILD dB, ILR ratio */
+typedef enum { SGX_CUE_ITD = 0, SGX_CUE_IPD = 1, SGX_CUE_ILD = 2, SGX_CUE_ILR = 3 } sgx_binaural_cue;
+
+/*
+ * The element-wise half of compute_{itd,ipd,ild,ilr}_spectrogram (src/binaural.rs:472-580, :830-917, :1187-1262,
+ * :1530-1620) on STFTs the caller already holds (StftPlan::compute of the left and the right channel, i.e.
+ * sgx_plan_compute_batch of a SGX_OUT_COMPLEX_STFT plan): left / right are (n_pairs, n_bins, n_frames) of Complex<T>,
+ * out is (n_pairs, stop_bin - start_bin, n_frames) of T for the band [start_bin, stop_bin) =
+ * [round(start_freq / bin_width), round(end_freq / bin_width)) (:478-481). magphase_power is ITD's weighting exponent
+ * (ITDSpectrogramParams, :386-391; the other cues use 1), wrapped is IPD's flag (:755-760). ILD / ILR are NaN where a
+ * channel has no energy, ITD is 0 there. Host or device pointers (all three the same kind).
+ */
+sgx_status sgx_binaural_from_stft(sgx_dtype dtype, sgx_binaural_cue cue, const void *left, const void *right, size_t n_pairs,
+                                  size_t n_bins, size_t n_frames, size_t start_bin, size_t stop_bin, double bin_width_hz,
+                                  size_t magphase_power, int wrapped, void *out, int device, void *cuda_stream);
+
+/*
+ * compute_{itd,ipd,ild,ilr}_spectrogram(audio: [left, right], params, plan: &mut StftPlan) (src/binaural.rs:472, :830,
+ * :1187, :1530), batched over stereo pairs: plan must be a SGX_OUT_COMPLEX_STFT plan (the reference's "force reuse"
+ * StftPlan argument); left / right are (n_pairs, clip_stride) sample matrices, out is (n_pairs, out_bins, out_frames) with
+ * out_bins = round(end_freq / bw) - round(start_freq / bw), bw = sample_rate / n_fft (:476-481) and out_frames the plan's
+ * frame count (SGX_DIMENSION_MISMATCH otherwise). Both STFTs stay in device memory; only the cue matrix is written.
+ * Host or device pointers (all three the same kind); device calls are asynchronous on cuda_stream.
+ */
+sgx_status sgx_plan_compute_binaural(sgx_plan *plan, sgx_binaural_cue cue, const void *left, const void *right,
+                                     size_t n_pairs, size_t n_samples, size_t clip_stride, double start_freq, double end_freq,
+                                     size_t magphase_power, int wrapped, void *out, size_t out_bins, size_t out_frames,
+                                     void *cuda_stream);
+
 /*
  * chromagram_from_spectrogram (src/chroma.rs:365-404): spec is (n_clips, n_bins, n_frames) of T with
  * n_bins == n_fft/2 + 1 (DimensionMismatch otherwise, :376-379), any amplitude scale; out is (n_clips, 12, n_frames).

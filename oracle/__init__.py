@@ -88,6 +88,9 @@ def lib():
         L.orc_chroma_from_spectrogram.restype = C.c_int
         L.orc_chroma_from_spectrogram.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_double, C.c_size_t,
                                                   C.c_double, C.c_double, C.c_double, C.c_int, C.c_void_p]
+        L.orc_binaural_from_stft.restype = C.c_int
+        L.orc_binaural_from_stft.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
+                                             C.c_size_t, C.c_double, C.c_size_t, C.c_int, C.c_void_p]
         L.orc_rfft.restype = C.c_int
         L.orc_rfft.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]
         L.orc_compute_batch.restype = C.c_int
@@ -268,6 +271,40 @@ def chromagram(x: np.ndarray, n_fft: int, hop: int, sample_rate: float, window: 
     d = Desc(dtype="f32" if x.dtype == np.float32 else "f64", n_fft=n_fft, hop=hop, sample_rate=sample_rate, window=window,
              centre=centre, mapping="linear", amp="magnitude")
     return chroma_from_spectrogram(Plan(d).compute(x), sample_rate, n_fft, tuning, f_min, f_max, norm)
+
+
+CUES = {"itd": 0, "ipd": 1, "ild": 2, "ilr": 3}
+
+
+def binaural_band(start_freq: float, end_freq: float, sample_rate: float, n_fft: int):
+    """(start_bin, stop_bin, bin_width) of src/binaural.rs:476-481: Rust `f64::round` (half away from zero) `as usize`."""
+    bw = sample_rate / n_fft
+    rnd = lambda v: int(np.floor(abs(v) + 0.5) * (1 if v >= 0 else -1))
+    return max(rnd(start_freq / bw), 0), max(rnd(end_freq / bw), 0), bw
+
+
+def binaural_from_stft(cue: str, left: np.ndarray, right: np.ndarray, start_bin: int, stop_bin: int, bin_width: float,
+                       magphase_power: int = 1, wrapped: bool = True) -> np.ndarray:
+    """Element-wise half of compute_{itd,ipd,ild,ilr}_spectrogram on two complex (n_bins, n_frames) STFTs."""
+    left, right = np.ascontiguousarray(left), np.ascontiguousarray(right)
+    assert left.dtype == right.dtype and left.dtype in (np.complex64, np.complex128) and left.shape == right.shape
+    rdt = np.float32 if left.dtype == np.complex64 else np.float64
+    out = np.empty((stop_bin - start_bin, left.shape[1]), dtype=rdt)
+    rc = lib().orc_binaural_from_stft(F32 if rdt == np.float32 else F64, CUES[cue], left.ctypes.data, right.ctypes.data,
+                                      left.shape[0], left.shape[1], start_bin, stop_bin, bin_width, magphase_power,
+                                      int(wrapped), out.ctypes.data)
+    if rc:
+        raise OracleError(lib().orc_last_error().decode())
+    return out
+
+
+def binaural(cue: str, left: np.ndarray, right: np.ndarray, n_fft: int, hop: int, sample_rate: float, start_freq: float,
+             end_freq: float, window: str = "hanning", centre: bool = True, magphase_power: int = 1, wrapped: bool = True):
+    """compute_{itd,ipd,ild,ilr}_spectrogram: StftPlan::compute of both channels, then the function above."""
+    d = Desc(dtype="f32" if left.dtype == np.float32 else "f64", n_fft=n_fft, hop=hop, sample_rate=sample_rate, window=window, centre=centre)
+    p = Plan(d)
+    b0, b1, bw = binaural_band(start_freq, end_freq, sample_rate, n_fft)
+    return binaural_from_stft(cue, p.stft(left), p.stft(right), b0, b1, bw, magphase_power, wrapped)
 
 
 def rfft(x: np.ndarray, n_fft: int) -> np.ndarray:

@@ -11,7 +11,7 @@
  *       (tests/golden/ + tests/test_oracle_*.py list them with file:line), and
  *   (2) outputs of the reference's own NumPy restatement python/examples/numpy_impls.py (stft, power,
  *       magnitude, dB, hann_window), imported from /root/reference by tests/golden/make_golden.py.
- * The mel/ERB/LogHz/MFCC/chroma numerics have no reference-side vectors: they are restated line by line and
+ * The mel/ERB/LogHz/MFCC/chroma/binaural numerics have no reference-side vectors: they are restated line by line and
  * cross-checked by an independent NumPy restatement (oracle/oracle_np.py); "parity unpinned" for those values.
  *
  * All citations are relative to the reference checkout (src/spectrogram.rs unless a file is named).
@@ -533,6 +533,72 @@ int orc_chroma_from_spectrogram(int dtype, const void *spec, size_t n_bins, size
     if (dtype == ORC_F32) chroma_apply_f32((const float *)spec, n_bins, n_frames, fb, norm, (float *)out);
     else chroma_apply_f64((const double *)spec, n_bins, n_frames, fb, norm, (double *)out);
     free(fb);
+    return 0;
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/* Binaural cues (src/binaural.rs). pow_mag :60-83, np_mod :85-87, magphase :106-180.               */
+#define ORC_BINAURAL(NAME, REAL, FMA, SQRT, ATAN2, FMOD, LOG10, PI_T)                                                  \
+    static REAL NAME##_pow_mag(REAL mag, REAL mag_sq, size_t power) {                                                  \
+        switch (power) {                                                                                               \
+        case 1: return mag;                                                                                            \
+        case 2: return mag_sq;                                                                                         \
+        case 3: return mag_sq * mag;                                                                                   \
+        case 4: return mag_sq * mag_sq;                                                                                \
+        default: {                                                                                                     \
+            REAL base = mag, acc = (REAL)1; size_t e = power;                                                          \
+            while (e > 0) { if (e & 1) acc *= base; e >>= 1; if (e > 0) base *= base; }                                \
+            return acc; }                                                                                              \
+        }                                                                                                              \
+    }                                                                                                                  \
+    static void NAME##_magphase(REAL re, REAL im, size_t power, REAL *m, REAL *pr, REAL *pi) {                         \
+        const REAL mag_sq = FMA(re, re, im * im);                        /* c.re.mul_add(c.re, c.im * c.im) :122 */     \
+        if (mag_sq == (REAL)0) { *m = (REAL)0; *pr = (REAL)1; *pi = (REAL)0; return; }                                 \
+        const REAL mag = SQRT(mag_sq);                                                                                 \
+        *m = NAME##_pow_mag(mag, mag_sq, power);                                                                       \
+        const REAL inv = (REAL)1 / mag;                                  /* recip :132 */                               \
+        *pr = re * inv; *pi = im * inv;                                                                                \
+    }                                                                                                                  \
+    static REAL NAME##_np_mod(REAL x, REAL m) { return FMOD(FMOD(x, m) + m, m); }                                      \
+    static void NAME(int cue, const REAL *left, const REAL *right, size_t n_frames, size_t start_bin, size_t stop_bin, \
+                     double bin_width, size_t power, int wrapped, REAL *out) {                                         \
+        const REAL pi = PI_T, two_pi = (REAL)2.0 * pi, bw = (REAL)bin_width;                                           \
+        for (size_t b = start_bin; b < stop_bin; ++b)                                                                  \
+            for (size_t f = 0; f < n_frames; ++f) {                                                                    \
+                const REAL *l = left + 2 * (b * n_frames + f), *r = right + 2 * (b * n_frames + f);                    \
+                REAL ml, plr, pli, mr, prr, pri, o;                                                                    \
+                NAME##_magphase(l[0], l[1], cue == ORC_CUE_ITD ? power : 1, &ml, &plr, &pli);                          \
+                NAME##_magphase(r[0], r[1], cue == ORC_CUE_ITD ? power : 1, &mr, &prr, &pri);                          \
+                if (cue == ORC_CUE_ITD) {                                    /* :528-545 */                             \
+                    o = (REAL)0;                                                                                       \
+                    if (ml + mr > (REAL)0) {                                                                           \
+                        const REAL diff = ATAN2(pli, plr) - ATAN2(pri, prr);                                           \
+                        const REAL w = NAME##_np_mod(diff + pi, two_pi) - pi;                                          \
+                        o = w / (two_pi * bw * (REAL)b);                                                               \
+                    }                                                                                                  \
+                } else if (cue == ORC_CUE_IPD) {                             /* :875-889 */                             \
+                    const REAL diff = ATAN2(pli, plr) - ATAN2(pri, prr);                                               \
+                    o = wrapped ? NAME##_np_mod(diff + pi, two_pi) - pi : diff;                                        \
+                } else {                                                                                               \
+                    o = (REAL)NAN;                                           /* from_elem(.., T::nan()) :1212, :1555 */ \
+                    if (ml + mr > (REAL)0 && ml > (REAL)0 && mr > (REAL)0) {                                           \
+                        const REAL ratio = mr / ml;                                                                    \
+                        if (cue == ORC_CUE_ILD) o = (REAL)-20.0 * LOG10(ratio);              /* :1229-1231 */           \
+                        else o = ratio < (REAL)1 ? (REAL)1 - ratio : -((REAL)1 - (REAL)1 / ratio);   /* :1572-1580 */   \
+                    }                                                                                                  \
+                }                                                                                                      \
+                out[(b - start_bin) * n_frames + f] = o;                                                               \
+            }                                                                                                          \
+    }
+ORC_BINAURAL(binaural_f32, float, fmaf, sqrtf, atan2f, fmodf, log10f, (float)M_PI)
+ORC_BINAURAL(binaural_f64, double, fma, sqrt, atan2, fmod, log10, M_PI)
+
+int orc_binaural_from_stft(int dtype, int cue, const void *left, const void *right, size_t n_bins, size_t n_frames,
+                           size_t start_bin, size_t stop_bin, double bin_width, size_t magphase_power, int wrapped, void *out) {
+    g_err[0] = 0;
+    if (start_bin >= stop_bin || stop_bin > n_bins) { snprintf(g_err, sizeof(g_err), "Frequency range should have at least one bin"); return 1; }
+    if (dtype == ORC_F32) binaural_f32(cue, (const float *)left, (const float *)right, n_frames, start_bin, stop_bin, bin_width, magphase_power, wrapped, (float *)out);
+    else binaural_f64(cue, (const double *)left, (const double *)right, n_frames, start_bin, stop_bin, bin_width, magphase_power, wrapped, (double *)out);
     return 0;
 }
 

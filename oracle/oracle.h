@@ -70,6 +70,11 @@ enum { ORC_CHROMANORM_NONE = 0, ORC_CHROMANORM_L1 = 1, ORC_CHROMANORM_L2 = 2, OR
 int orc_chroma_filterbank(double sample_rate, size_t n_fft, double tuning, double f_min, double f_max, double *out);
 int orc_chroma_from_spectrogram(int dtype, const void *spec, size_t n_bins, size_t n_frames, double sample_rate,
                                 size_t n_fft, double tuning, double f_min, double f_max, int norm, void *out);
+enum { ORC_CUE_ITD = 0, ORC_CUE_IPD = 1, ORC_CUE_ILD = 2, ORC_CUE_ILR = 3 };
+/* src/binaural.rs: the element-wise half of compute_{itd,ipd,ild,ilr}_spectrogram (:472-580, :830-917, :1187-1262,
+ * :1530-1620) incl. magphase (:106-180): left/right complex (n_bins, n_frames) -> out (stop_bin-start_bin, n_frames). */
+int orc_binaural_from_stft(int dtype, int cue, const void *left, const void *right, size_t n_bins, size_t n_frames,
+                           size_t start_bin, size_t stop_bin, double bin_width, size_t magphase_power, int wrapped, void *out);
 int orc_rfft(int dtype, const void *x, size_t n_in, size_t n_fft, void *out);
 int orc_compute_batch(const orc_desc *d, const void *samples, size_t n_clips, size_t n_samples, size_t clip_stride,
                       void *out, size_t out_stride, int n_threads,

@@ -40,4 +40,10 @@ cudaError_t launch_mfcc(bool f64, const void *log_mel, void *out, long long n_cl
 cudaError_t launch_chroma(bool f64, const void *spec, void *out, long long n_clips, int n_bins, long long n_frames,
                           const void *w_transposed, int norm, int k0, int k1, cudaStream_t stream);
 
+// interaural cue spectrograms from two complex STFTs [n_pairs][n_bins][n_frames] -> [n_pairs][stop_bin - start_bin][n_frames]
+// (kernel_binaural.cu); cue is an sgx_binaural_cue
+cudaError_t launch_binaural(bool f64, int cue, const void *left, const void *right, void *out, long long n_pairs, int n_bins,
+                            long long n_frames, int start_bin, int stop_bin, double bin_width, unsigned power, int wrapped,
+                            cudaStream_t stream);
+
 }  // namespace sgx

@@ -148,6 +148,8 @@ struct sgx_plan {
     std::vector<int> lane_rows;      // r2c_fused_pow2 rows epilogue: int4 per lane slot
     std::vector<double> lane_w;      // ... and its lane-major weights
     int *d_lane_rows = nullptr;
+    void *d_pair[2] = {nullptr, nullptr};   // binaural: complex STFTs of the two channels of a chunk of pairs
+    size_t pair_cap = 0;
     std::vector<double> dense_t;     // chroma: dense matrix transposed to [out_len][n_bins]
     void *d_dense_t = nullptr;
     int dense_c0 = 0, dense_c1 = 0;  // nonzero column range of the dense matrix
@@ -168,6 +170,7 @@ struct sgx_plan {
         if (d_lane_rows) cudaFree(d_lane_rows);
         if (d_lane_w) cudaFree(d_lane_w);
         if (d_dense_t) cudaFree(d_dense_t);
+        for (void *q : d_pair) if (q) cudaFree(q);
         for (auto &s : slot) {
             if (s.d_in) cudaFree(s.d_in);
             if (s.d_out) cudaFree(s.d_out);
@@ -773,6 +776,127 @@ sgx_status sgx_mfcc_from_log_mel(sgx_dtype dtype, const void *log_mel, size_t n_
             }
         } catch (...) { cleanup(); throw; }
         cleanup();
+    });
+}
+
+sgx_status sgx_plan_compute_binaural(sgx_plan *plan, sgx_binaural_cue cue, const void *left, const void *right,
+                                     size_t n_pairs, size_t n_samples, size_t clip_stride, double start_freq, double end_freq,
+                                     size_t magphase_power, int wrapped, void *out, size_t out_bins, size_t out_frames,
+                                     void *cuda_stream) {
+    return guarded([&] {
+        if (!plan || !left || !right || !out) invalid("null argument");
+        sgx_plan &pl = *plan;
+        if (pl.desc.output != SGX_OUT_COMPLEX_STFT) invalid("binaural cues need a complex STFT plan");
+        if (cue < SGX_CUE_ITD || cue > SGX_CUE_ILR) invalid("unknown binaural cue");
+        if (n_samples == 0) invalid("samples must be non-empty");
+        if (n_pairs == 0) invalid("n_pairs must be non-zero");
+        if (clip_stride < n_samples) invalid("clip_stride must be >= n_samples");
+        if (magphase_power == 0 || magphase_power > 0xffffffffu) invalid("magphase_power must be a non-zero u32");
+        const double bw = pl.desc.sample_rate_hz / static_cast<double>(pl.desc.n_fft);       // :476
+        const double sb = std::round(start_freq / bw), eb = std::round(end_freq / bw);         // f64::round, half away from zero
+        if (!(sb >= 0.0) || !(eb > sb)) invalid("Frequency range should have at least one bin");   // the reference's expect() (:549-550)
+        const size_t start_bin = static_cast<size_t>(sb), stop_bin = static_cast<size_t>(eb);
+        const size_t n_bins = pl.tab.out_len;
+        if (stop_bin > n_bins) invalid("End frequency must be less than Nyquist frequency.");
+        const size_t n_frames = frame_count(n_samples, pl.desc.n_fft, pl.desc.hop_size, pl.desc.centre != 0);
+        if (out_bins != stop_bin - start_bin) mismatch(stop_bin - start_bin, out_bins);
+        if (out_frames != n_frames) mismatch(n_frames, out_frames);
+        ensure_device(pl);
+        DeviceGuard g(pl.device);
+        pl.last_launches = 0;
+        const PtrKind kl = ptr_kind(left), kr = ptr_kind(right), ko = ptr_kind(out);
+        if (kl != kr || kl != ko) invalid("left, right and out must all be host pointers or all be device pointers");
+        const bool host = kl != PtrKind::Device;
+        const size_t es = pl.esize;
+        const size_t stft_bytes = n_bins * n_frames * 2 * es, cue_elems = out_bins * n_frames;
+        // pairs per chunk: both channels' STFTs of a chunk stay under ~512 MB each
+        size_t chunk = std::max<size_t>(1, (size_t(512) << 20) / stft_bytes);
+        chunk = std::min(chunk, n_pairs);
+        if (pl.pair_cap < chunk * stft_bytes) {
+            for (void *&q : pl.d_pair) { if (q) { ck(cudaDeviceSynchronize(), "sync"); cudaFree(q); q = nullptr; } }
+            pl.pair_cap = 0;
+            ck(cudaMalloc(&pl.d_pair[0], chunk * stft_bytes), "cudaMalloc(binaural scratch)");
+            ck(cudaMalloc(&pl.d_pair[1], chunk * stft_bytes), "cudaMalloc(binaural scratch)");
+            pl.pair_cap = chunk * stft_bytes;
+        }
+        sgx_plan::Slot &s = pl.slot[0];
+        cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+        if (host) {
+            ensure_slot(s, 2 * chunk * n_samples * es, chunk * cue_elems * es);
+            st = s.s;
+        }
+        for (size_t p0 = 0; p0 < n_pairs; p0 += chunk) {
+            const size_t np = std::min(chunk, n_pairs - p0);
+            const void *ch[2] = {static_cast<const char *>(left) + p0 * clip_stride * es, static_cast<const char *>(right) + p0 * clip_stride * es};
+            size_t stride = clip_stride;
+            if (host) {
+                char *d_in = static_cast<char *>(s.d_in);
+                for (int c = 0; c < 2; ++c) {
+                    ck(cudaMemcpy2DAsync(d_in + c * np * n_samples * es, n_samples * es, ch[c], clip_stride * es, n_samples * es, np,
+                                         cudaMemcpyHostToDevice, st), "H2D copy");
+                    ch[c] = d_in + c * np * n_samples * es;
+                }
+                stride = n_samples;
+            }
+            for (int c = 0; c < 2; ++c)
+                run_device(pl, ch[c], np, n_samples, stride, pl.d_pair[c], static_cast<long long>(n_frames),
+                           static_cast<long long>(n_bins * n_frames), 0, static_cast<long long>(n_frames), st);
+            void *dst = host ? s.d_out : static_cast<char *>(out) + p0 * cue_elems * es;
+            ck(launch_binaural(pl.f64, cue, pl.d_pair[0], pl.d_pair[1], dst, static_cast<long long>(np), static_cast<int>(n_bins),
+                               static_cast<long long>(n_frames), static_cast<int>(start_bin), static_cast<int>(stop_bin), bw,
+                               static_cast<unsigned>(magphase_power), wrapped, st), "kernel launch (binaural_cues)");
+            pl.last_launches += 1;
+            if (host) ck(cudaMemcpyAsync(static_cast<char *>(out) + p0 * cue_elems * es, s.d_out, np * cue_elems * es, cudaMemcpyDeviceToHost, st), "D2H copy");
+        }
+        if (host) ck(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+    });
+}
+
+sgx_status sgx_binaural_from_stft(sgx_dtype dtype, sgx_binaural_cue cue, const void *left, const void *right, size_t n_pairs,
+                                  size_t n_bins, size_t n_frames, size_t start_bin, size_t stop_bin, double bin_width_hz,
+                                  size_t magphase_power, int wrapped, void *out, int device, void *cuda_stream) {
+    return guarded([&] {
+        if (!left || !right || !out) invalid("null argument");
+        if (dtype != SGX_F32 && dtype != SGX_F64) invalid("dtype must be f32 or f64");
+        if (cue < SGX_CUE_ITD || cue > SGX_CUE_ILR) invalid("unknown binaural cue");
+        if (n_pairs == 0 || n_bins == 0 || n_frames == 0) invalid("empty STFT");
+        if (!(bin_width_hz > 0.0 && std::isfinite(bin_width_hz))) invalid("bin width must be finite and > 0");
+        if (start_bin >= stop_bin) invalid("Frequency range should have at least one bin");    // the reference's expect() (:549-550)
+        if (stop_bin > n_bins) mismatch(stop_bin, n_bins);
+        if (magphase_power == 0 || magphase_power > 0xffffffffu) invalid("magphase_power must be a non-zero u32");
+        const bool f64 = dtype == SGX_F64;
+        const size_t es = f64 ? 8 : 4;
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+            cudaGetLastError();
+            backend("no CUDA device available (this library has no CPU fallback)");
+        }
+        int dev = device;
+        if (dev < 0) ck(cudaGetDevice(&dev), "cudaGetDevice");
+        DeviceGuard g(dev);
+        const PtrKind kl = ptr_kind(left), kr = ptr_kind(right), ko = ptr_kind(out);
+        if (kl != kr || kl != ko) invalid("left, right and out must all be host pointers or all be device pointers");
+        cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+        const long long np = static_cast<long long>(n_pairs), nf = static_cast<long long>(n_frames);
+        if (kl == PtrKind::Device) {
+            ck(launch_binaural(f64, cue, left, right, out, np, static_cast<int>(n_bins), nf, static_cast<int>(start_bin),
+                               static_cast<int>(stop_bin), bin_width_hz, static_cast<unsigned>(magphase_power), wrapped, st),
+               "kernel launch (binaural_cues)");
+            return;
+        }
+        const size_t ib = n_pairs * n_bins * n_frames * 2 * es, ob = n_pairs * (stop_bin - start_bin) * n_frames * es;
+        void *d_l = nullptr, *d_r = nullptr, *d_o = nullptr;
+        cudaError_t e = cudaMalloc(&d_l, ib);
+        if (e == cudaSuccess) e = cudaMalloc(&d_r, ib);
+        if (e == cudaSuccess) e = cudaMalloc(&d_o, ob);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_l, left, ib, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_r, right, ib, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = launch_binaural(f64, cue, d_l, d_r, d_o, np, static_cast<int>(n_bins), nf, static_cast<int>(start_bin),
+                                                  static_cast<int>(stop_bin), bin_width_hz, static_cast<unsigned>(magphase_power), wrapped, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_o, ob, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        cudaFree(d_l); cudaFree(d_r); cudaFree(d_o);
+        ck(e, "binaural_from_stft");
     });
 }
 
