@@ -231,6 +231,23 @@ sgx_status sgx_chroma_filterbank(double sample_rate_hz, size_t n_fft, double tun
 sgx_status sgx_rfft(sgx_dtype dtype, const void *samples, size_t n_in, size_t n_fft, void *out, int device,
                     void *cuda_stream);
 
+/*
+ * istft<T>(stft_matrix, n_fft, hop_size, window, center) (src/spectrogram.rs:4813-4911), batched: the plan supplies n_fft,
+ * hop_size, the window and centre (any output kind; a SGX_OUT_COMPLEX_STFT plan that produced the matrix is the natural
+ * one). stft is (n_clips, n_fft/2 + 1, n_frames) of Complex<T>; out is (n_clips, out_len) of T with
+ * out_len = (n_frames - 1) * hop + n_fft, minus 2 * (n_fft / 2) when centred and that leaves anything (:4836-4841,
+ * :4893-4902) -- query it with out = NULL: *out_len_io is set and nothing runs. Per frame: C2R inverse FFT scaled by 1/n_fft
+ * (src/fft_backend.rs:536-566; like realfft, the imaginary parts of the DC / Nyquist bins are ignored), synthesis window,
+ * overlap-add, division by the accumulated squared window where it exceeds 1e-10. Host or device pointers.
+ */
+sgx_status sgx_plan_istft(sgx_plan *plan, const void *stft, size_t n_clips, size_t n_frames, void *out, size_t *out_len_io,
+                          void *cuda_stream);
+
+/* irfft<T>(spectrum, n_fft) (src/spectrogram.rs:4789-4811): spectrum_len must be n_fft/2 + 1 (SGX_DIMENSION_MISMATCH
+ * otherwise); out receives n_fft samples. Host or device pointers. */
+sgx_status sgx_irfft(sgx_dtype dtype, const void *spectrum, size_t spectrum_len, size_t n_fft, void *out, int device,
+                     void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

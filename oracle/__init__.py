@@ -91,6 +91,10 @@ def lib():
         L.orc_binaural_from_stft.restype = C.c_int
         L.orc_binaural_from_stft.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
                                              C.c_size_t, C.c_double, C.c_size_t, C.c_int, C.c_void_p]
+        L.orc_irfft.restype = C.c_int
+        L.orc_irfft.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.orc_istft.restype = C.c_size_t
+        L.orc_istft.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.orc_rfft.restype = C.c_int
         L.orc_rfft.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]
         L.orc_compute_batch.restype = C.c_int
@@ -305,6 +309,31 @@ def binaural(cue: str, left: np.ndarray, right: np.ndarray, n_fft: int, hop: int
     p = Plan(d)
     b0, b1, bw = binaural_band(start_freq, end_freq, sample_rate, n_fft)
     return binaural_from_stft(cue, p.stft(left), p.stft(right), b0, b1, bw, magphase_power, wrapped)
+
+
+def irfft(spectrum: np.ndarray, n_fft: int) -> np.ndarray:
+    """irfft (src/spectrogram.rs:4789-4811)."""
+    spectrum = np.ascontiguousarray(spectrum)
+    assert spectrum.dtype in (np.complex64, np.complex128)
+    if spectrum.size != n_fft // 2 + 1:
+        raise OracleError(f"Dimension mismatch: expected {n_fft // 2 + 1}, got {spectrum.size}")
+    out = np.empty(n_fft, dtype=np.float32 if spectrum.dtype == np.complex64 else np.float64)
+    lib().orc_irfft(F32 if spectrum.dtype == np.complex64 else F64, spectrum.ctypes.data, n_fft, out.ctypes.data)
+    return out
+
+
+def istft(stft_matrix: np.ndarray, n_fft: int, hop: int, window: str = "hanning", centre: bool = True, window_param: float = 0.0) -> np.ndarray:
+    """istft (src/spectrogram.rs:4813-4911): (n_fft//2 + 1, n_frames) complex -> samples."""
+    stft_matrix = np.ascontiguousarray(stft_matrix)
+    assert stft_matrix.dtype in (np.complex64, np.complex128) and stft_matrix.ndim == 2
+    if stft_matrix.shape[0] != n_fft // 2 + 1:
+        raise OracleError(f"Dimension mismatch: expected {n_fft // 2 + 1}, got {stft_matrix.shape[0]}")
+    rdt = np.float32 if stft_matrix.dtype == np.complex64 else np.float64
+    p = Plan(Desc(dtype="f32" if rdt == np.float32 else "f64", n_fft=n_fft, hop=hop, window=window, window_param=window_param, centre=centre))
+    n = lib().orc_istft(p._h, stft_matrix.ctypes.data, stft_matrix.shape[1], None)
+    out = np.empty(n, dtype=rdt)
+    lib().orc_istft(p._h, stft_matrix.ctypes.data, stft_matrix.shape[1], out.ctypes.data)
+    return out
 
 
 def rfft(x: np.ndarray, n_fft: int) -> np.ndarray:

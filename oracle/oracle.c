@@ -11,7 +11,8 @@
  *       (tests/golden/ + tests/test_oracle_*.py list them with file:line), and
  *   (2) outputs of the reference's own NumPy restatement python/examples/numpy_impls.py (stft, power,
  *       magnitude, dB, hann_window), imported from /root/reference by tests/golden/make_golden.py.
- * The mel/ERB/LogHz/MFCC/chroma/binaural numerics have no reference-side vectors: they are restated line by line and
+ * The mel/ERB/LogHz/MFCC/chroma/binaural numerics have no reference-side vectors (the inverse path is
+ * checked against SciPy's pocketfft and by round trips): they are restated line by line and
  * cross-checked by an independent NumPy restatement (oracle/oracle_np.py); "parity unpinned" for those values.
  *
  * All citations are relative to the reference checkout (src/spectrogram.rs unless a file is named).
@@ -600,6 +601,26 @@ int orc_binaural_from_stft(int dtype, int cue, const void *left, const void *rig
     if (dtype == ORC_F32) binaural_f32(cue, (const float *)left, (const float *)right, n_frames, start_bin, stop_bin, bin_width, magphase_power, wrapped, (float *)out);
     else binaural_f64(cue, (const double *)left, (const double *)right, n_frames, start_bin, stop_bin, bin_width, magphase_power, wrapped, (double *)out);
     return 0;
+}
+
+/* inverse path (src/spectrogram.rs:4789-4911) */
+int orc_irfft(int dtype, const void *spectrum, size_t n_fft, void *out) {
+    g_err[0] = 0;
+    if (dtype == ORC_F32) {
+        fft_plan_f32 *fp = fft_plan_new_f32(n_fft);
+        irfft_f32(fp, (const cpx_f32 *)spectrum, (float *)out);
+        fft_plan_free_f32(fp);
+    } else {
+        fft_plan_f64 *fp = fft_plan_new_f64(n_fft);
+        irfft_f64(fp, (const cpx_f64 *)spectrum, (double *)out);
+        fft_plan_free_f64(fp);
+    }
+    return 0;
+}
+
+size_t orc_istft(orc_plan *p, const void *stft, size_t n_frames, void *out) {
+    if (p->p32) return istft_f32(p->p32->fft, (const cpx_f32 *)stft, n_frames, p->d.hop, p->d.centre, p->p32->window, (float *)out);
+    return istft_f64(p->p64->fft, (const cpx_f64 *)stft, n_frames, p->d.hop, p->d.centre, p->p64->window, (double *)out);
 }
 
 /* single-frame R2C of <= n_fft samples, zero padded: free fn fft() (:4490-4520) */

@@ -75,6 +75,10 @@ enum { ORC_CUE_ITD = 0, ORC_CUE_IPD = 1, ORC_CUE_ILD = 2, ORC_CUE_ILR = 3 };
  * :1530-1620) incl. magphase (:106-180): left/right complex (n_bins, n_frames) -> out (stop_bin-start_bin, n_frames). */
 int orc_binaural_from_stft(int dtype, int cue, const void *left, const void *right, size_t n_bins, size_t n_frames,
                            size_t start_bin, size_t stop_bin, double bin_width, size_t magphase_power, int wrapped, void *out);
+/* irfft (src/spectrogram.rs:4789-4811): spectrum[n_fft/2+1] -> out[n_fft]; istft (:4813-4911) with the plan's n_fft, hop,
+ * window and centre: stft (n_fft/2+1, n_frames) complex -> out; returns the output length (out == NULL: query only). */
+int orc_irfft(int dtype, const void *spectrum, size_t n_fft, void *out);
+size_t orc_istft(orc_plan *p, const void *stft, size_t n_frames, void *out);
 int orc_rfft(int dtype, const void *x, size_t n_in, size_t n_fft, void *out);
 int orc_compute_batch(const orc_desc *d, const void *samples, size_t n_clips, size_t n_samples, size_t clip_stride,
                       void *out, size_t out_stride, int n_threads,

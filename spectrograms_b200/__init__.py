@@ -16,7 +16,7 @@ from .plan import (ChromaPlan, Chromagram, Mfcc, MfccPlan, Spectrogram, Spectrog
                    compute_linear_db_spectrogram, compute_linear_magnitude_spectrogram,
                    compute_linear_power_spectrogram, compute_loghz_db_spectrogram,
                    compute_loghz_magnitude_spectrogram, compute_loghz_power_spectrogram, compute_mel_db_spectrogram,
-                   compute_mel_magnitude_spectrogram, compute_mel_power_spectrogram, compute_mfcc, compute_stft, fft, build_chroma_filterbank, chromagram,
+                   compute_mel_magnitude_spectrogram, compute_mel_power_spectrogram, compute_mfcc, compute_stft, fft, irfft, istft, build_chroma_filterbank, chromagram,
                    chromagram_from_spectrogram, compute_chromagram,
                    magnitude_spectrum, mfcc, mfcc_from_log_mel, power_spectrum, rfft, stft)
 from .binaural import (BinauralSpectrogram, ILDSpectrogramParams, ILRSpectrogramParams, IPDSpectrogramParams,

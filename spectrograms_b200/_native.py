@@ -18,7 +18,7 @@ EXPORTS = [
     "sgx_plan_output_shape", "sgx_plan_axes", "sgx_plan_window", "sgx_plan_filterbank", "sgx_plan_kernel_name",
     "sgx_plan_last_launch_count", "sgx_plan_force_generic", "sgx_plan_compute_batch", "sgx_plan_compute_frame",
     "sgx_mfcc_from_log_mel", "sgx_rfft", "sgx_chroma_from_spectrogram", "sgx_chroma_filterbank",
-    "sgx_binaural_from_stft", "sgx_plan_compute_binaural",
+    "sgx_binaural_from_stft", "sgx_plan_compute_binaural", "sgx_plan_istft", "sgx_irfft",
 ]
 
 
@@ -73,6 +73,8 @@ def lib() -> C.CDLL:
     L.sgx_chroma_from_spectrogram.argtypes = [i, vp, sz, sz, sz, d, sz, d, d, d, i, vp, i, vp]
     L.sgx_chroma_filterbank.argtypes = [d, sz, d, d, d, vp]
     L.sgx_binaural_from_stft.argtypes = [i, i, vp, vp, sz, sz, sz, sz, sz, d, sz, i, vp, i, vp]
+    L.sgx_plan_istft.argtypes = [vp, vp, sz, sz, vp, C.POINTER(sz), vp]
+    L.sgx_irfft.argtypes = [i, vp, sz, sz, vp, i, vp]
     L.sgx_plan_compute_binaural.argtypes = [vp, i, vp, vp, sz, sz, sz, d, d, sz, i, vp, sz, sz, vp]
     for name in EXPORTS:
         getattr(L, name)

@@ -46,4 +46,12 @@ cudaError_t launch_binaural(bool f64, int cue, const void *left, const void *rig
                             long long n_frames, int start_bin, int stop_bin, double bin_width, unsigned power, int wrapped,
                             cudaStream_t stream);
 
+// inverse path (kernel_inverse.cu): Hermitian STFT [n_clips][n_fft/2+1][n_frames] -> (windowed) time frames
+// [n_clips][n_frames][n_fft] with the generic family's geometry (p.FT, p.frame_stride, p.buf_elems, p.tiles_per_clip set by
+// the caller), then the overlap-add gather into out [n_clips][out_len] (trim = samples dropped at the front)
+cudaError_t launch_c2r_frames(const KParams &p, bool f64, size_t smem, const void *stft, void *frames_out, long long n_clips,
+                              long long n_frames, int apply_window, cudaStream_t stream);
+cudaError_t launch_ola_gather(bool f64, const void *frames, const void *window, void *out, long long n_clips, long long n_frames,
+                              int n_fft, int hop, long long out_len, long long trim, cudaStream_t stream);
+
 }  // namespace sgx

@@ -148,6 +148,8 @@ struct sgx_plan {
     std::vector<int> lane_rows;      // r2c_fused_pow2 rows epilogue: int4 per lane slot
     std::vector<double> lane_w;      // ... and its lane-major weights
     int *d_lane_rows = nullptr;
+    void *d_frames = nullptr;               // istft: windowed time frames of a chunk of clips
+    size_t frames_cap = 0;
     void *d_pair[2] = {nullptr, nullptr};   // binaural: complex STFTs of the two channels of a chunk of pairs
     size_t pair_cap = 0;
     std::vector<double> dense_t;     // chroma: dense matrix transposed to [out_len][n_bins]
@@ -171,6 +173,7 @@ struct sgx_plan {
         if (d_lane_w) cudaFree(d_lane_w);
         if (d_dense_t) cudaFree(d_dense_t);
         for (void *q : d_pair) if (q) cudaFree(q);
+        if (d_frames) cudaFree(d_frames);
         for (auto &s : slot) {
             if (s.d_in) cudaFree(s.d_in);
             if (s.d_out) cudaFree(s.d_out);
@@ -961,6 +964,118 @@ sgx_status sgx_chroma_from_spectrogram(sgx_dtype dtype, const void *spec, size_t
         cudaFree(d_in); cudaFree(d_out); cudaFree(d_w);
         ck(e, "chroma_from_spectrogram");
     });
+}
+
+namespace {
+// frames of `nc` clips -> out (device pointers); apply_window = 0 and n_frames = 1 gives a bare irfft
+void run_inverse(sgx_plan &pl, const void *d_stft, size_t nc, size_t n_frames, void *d_frames_out, int apply_window, cudaStream_t st) {
+    KParams p;
+    fill_params(pl, p);
+    p.n_clips = static_cast<int>(nc);
+    p.tiles_per_clip = static_cast<int>((n_frames + p.FT - 1) / p.FT);
+    ck(launch_c2r_frames(p, pl.f64, pl.smem_bytes, d_stft, d_frames_out, static_cast<long long>(nc), static_cast<long long>(n_frames),
+                         apply_window, st), "kernel launch (c2r_frames)");
+    pl.last_launches += 1;
+}
+}  // namespace
+
+sgx_status sgx_plan_istft(sgx_plan *plan, const void *stft, size_t n_clips, size_t n_frames, void *out, size_t *out_len_io,
+                          void *cuda_stream) {
+    return guarded([&] {
+        if (!plan || !out_len_io) invalid("null argument");
+        if (n_frames == 0) invalid("stft_matrix must have at least one frame");
+        sgx_plan &pl = *plan;
+        const size_t n = pl.desc.n_fft, hop = pl.desc.hop_size;
+        const size_t pad = pl.desc.centre ? n / 2 : 0;
+        const size_t full = (n_frames - 1) * hop + n;                               // :4837
+        const size_t unpadded = full > 2 * pad ? full - 2 * pad : 0;                // saturating_sub (:4841)
+        const bool trim = pl.desc.centre && unpadded > 0;                           // :4893
+        const size_t out_len = trim ? unpadded : full;
+        if (!out) { *out_len_io = out_len; return; }
+        if (!stft) invalid("null argument");
+        if (n_clips == 0) invalid("n_clips must be non-zero");
+        if (*out_len_io != out_len) mismatch(out_len, *out_len_io);
+        ensure_device(pl);
+        DeviceGuard g(pl.device);
+        pl.last_launches = 0;
+        const PtrKind ki = ptr_kind(stft), ko = ptr_kind(out);
+        if (ki != ko) invalid("stft and out must both be host pointers or both be device pointers");
+        const bool host = ki != PtrKind::Device;
+        const size_t es = pl.esize, bins = pl.tab.out_len;
+        const size_t frame_bytes = n_frames * n * es, stft_bytes = bins * n_frames * 2 * es;
+        size_t chunk = std::max<size_t>(1, (size_t(512) << 20) / std::max(frame_bytes, stft_bytes));
+        chunk = std::min(chunk, n_clips);
+        if (pl.frames_cap < chunk * frame_bytes) {
+            if (pl.d_frames) { ck(cudaDeviceSynchronize(), "sync"); cudaFree(pl.d_frames); pl.d_frames = nullptr; pl.frames_cap = 0; }
+            ck(cudaMalloc(&pl.d_frames, chunk * frame_bytes), "cudaMalloc(istft scratch)");
+            pl.frames_cap = chunk * frame_bytes;
+        }
+        sgx_plan::Slot &s = pl.slot[0];
+        cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+        if (host) {
+            ensure_slot(s, chunk * stft_bytes, chunk * out_len * es);
+            st = s.s;
+        }
+        for (size_t c0 = 0; c0 < n_clips; c0 += chunk) {
+            const size_t nc = std::min(chunk, n_clips - c0);
+            const void *src = static_cast<const char *>(stft) + c0 * stft_bytes;
+            if (host) {
+                ck(cudaMemcpyAsync(s.d_in, src, nc * stft_bytes, cudaMemcpyHostToDevice, st), "H2D copy");
+                src = s.d_in;
+            }
+            run_inverse(pl, src, nc, n_frames, pl.d_frames, 1, st);
+            void *dst = host ? s.d_out : static_cast<char *>(out) + c0 * out_len * es;
+            ck(launch_ola_gather(pl.f64, pl.d_frames, pl.d_window, dst, static_cast<long long>(nc), static_cast<long long>(n_frames),
+                                 static_cast<int>(n), static_cast<int>(hop), static_cast<long long>(out_len),
+                                 static_cast<long long>(trim ? pad : 0), st), "kernel launch (ola_gather)");
+            pl.last_launches += 1;
+            if (host) ck(cudaMemcpyAsync(static_cast<char *>(out) + c0 * out_len * es, s.d_out, nc * out_len * es, cudaMemcpyDeviceToHost, st), "D2H copy");
+        }
+        if (host) ck(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+    });
+}
+
+sgx_status sgx_irfft(sgx_dtype dtype, const void *spectrum, size_t spectrum_len, size_t n_fft, void *out, int device,
+                     void *cuda_stream) {
+    sgx_plan *pl = nullptr;
+    sgx_status st = guarded([&] {
+        if (!spectrum || !out) invalid("null argument");
+        if (n_fft == 0) invalid("n_fft must be set");
+        if (spectrum_len != n_fft / 2 + 1) mismatch(n_fft / 2 + 1, spectrum_len);   // :4797-4802
+    });
+    if (st != SGX_OK) return st;
+    sgx_plan_desc d;
+    std::memset(&d, 0, sizeof d);
+    d.dtype = dtype; d.n_fft = n_fft; d.hop_size = n_fft; d.centre = 0; d.window = SGX_WIN_RECTANGULAR;
+    d.sample_rate_hz = 1.0; d.mapping = SGX_MAP_LINEAR; d.amp = SGX_AMP_POWER; d.output = SGX_OUT_COMPLEX_STFT; d.device = device;
+    st = sgx_plan_create(&d, &pl);
+    if (st != SGX_OK) return st;
+    st = guarded([&] {
+        ensure_device(*pl);
+        DeviceGuard g(pl->device);
+        const size_t es = pl->esize;
+        const PtrKind ki = ptr_kind(spectrum), ko = ptr_kind(out);
+        if (ki != ko) invalid("spectrum and out must both be host pointers or both be device pointers");
+        cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+        if (ki == PtrKind::Device) {
+            run_inverse(*pl, spectrum, 1, 1, out, 0, s);
+            ck(cudaStreamSynchronize(s), "cudaStreamSynchronize");                  // the plan's tables are freed below
+            return;
+        }
+        void *d_in = nullptr, *d_out = nullptr;
+        cudaError_t e = cudaMalloc(&d_in, spectrum_len * 2 * es);
+        if (e == cudaSuccess) e = cudaMalloc(&d_out, n_fft * es);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_in, spectrum, spectrum_len * 2 * es, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) {
+            try { run_inverse(*pl, d_in, 1, 1, d_out, 0, s); } catch (...) { cudaFree(d_in); cudaFree(d_out); throw; }
+            e = cudaMemcpyAsync(out, d_out, n_fft * es, cudaMemcpyDeviceToHost, s);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        cudaFree(d_in); cudaFree(d_out);
+        ck(e, "irfft");
+    });
+    sgx_plan_destroy(pl);
+    return st;
 }
 
 sgx_status sgx_rfft(sgx_dtype dtype, const void *samples, size_t n_in, size_t n_fft, void *out, int device, void *cuda_stream) {

@@ -15,7 +15,7 @@ from typing import Optional, Tuple
 import numpy as np
 
 from . import _native
-from .errors import InvalidInputError
+from .errors import DimensionMismatchError, InvalidInputError
 from .params import (ChromaParams, ErbParams, LogHzParams, LogParams, MelParams, MfccParams, SpectrogramParams,
                      StftParams, WindowType, normalise_dtype)
 
@@ -283,6 +283,45 @@ class _NativePlan:
                                                out.ctypes.data, orow, ocol, 0, None))
         return out
 
+    def istft(self, stft_matrix):
+        L = _native.lib()
+        bins = self.n_fft // 2 + 1
+        squeeze = False
+        n_out = C.c_size_t(0)
+        if _is_torch(stft_matrix):
+            torch = _torch()
+            x = stft_matrix
+            want = torch.complex64 if self.dtype == "f32" else torch.complex128
+            if not x.is_cuda or x.dtype != want:
+                raise InvalidInputError(f"stft_matrix must be a CUDA tensor of dtype {want}")
+            if x.dim() == 2:
+                x, squeeze = x.unsqueeze(0), True
+            if x.dim() != 3 or x.numel() == 0:
+                raise InvalidInputError("stft_matrix must be (n_bins, n_frames) or (n_clips, n_bins, n_frames)")
+            if x.shape[1] != bins:
+                raise DimensionMismatchError(f"Dimension mismatch: expected {bins}, got {x.shape[1]}", bins, int(x.shape[1]))
+            x = x.contiguous()
+            nc, _, nf = x.shape
+            _native.check(L.sgx_plan_istft(self._h, None, nc, nf, None, C.byref(n_out), None))
+            out = torch.empty((nc, n_out.value), dtype=torch.float32 if self.dtype == "f32" else torch.float64, device=x.device)
+            with torch.cuda.device(x.device):
+                _native.check(L.sgx_plan_istft(self._h, x.data_ptr(), nc, nf, out.data_ptr(), C.byref(n_out),
+                                               torch.cuda.current_stream(x.device).cuda_stream))
+            return out[0] if squeeze else out
+        x = np.asarray(stft_matrix)
+        x = np.ascontiguousarray(x, dtype=np.complex64 if self.dtype == "f32" else np.complex128)
+        if x.ndim == 2:
+            x, squeeze = x[None], True
+        if x.ndim != 3 or x.size == 0:
+            raise InvalidInputError("stft_matrix must be (n_bins, n_frames) or (n_clips, n_bins, n_frames)")
+        if x.shape[1] != bins:                                     # :4825-4828
+            raise DimensionMismatchError(f"Dimension mismatch: expected {bins}, got {x.shape[1]}", bins, int(x.shape[1]))
+        nc, _, nf = x.shape
+        _native.check(L.sgx_plan_istft(self._h, None, nc, nf, None, C.byref(n_out), None))
+        out = np.empty((nc, n_out.value), dtype=self.np_dtype)
+        _native.check(L.sgx_plan_istft(self._h, x.ctypes.data, nc, nf, out.ctypes.data, C.byref(n_out), None))
+        return out[0] if squeeze else out
+
     def compute_one(self, samples, out=None):
         if _is_torch(samples):
             if samples.dim() != 1 or samples.numel() == 0:
@@ -413,6 +452,12 @@ class StftPlan:
 
     def compute_batch(self, clips, out=None):
         return self._n.compute_batch(clips, out)
+
+    def istft(self, stft_matrix):
+        """``istft`` (:4813-4911) with this plan's n_fft, hop, window and centre: (n_bins, n_frames) or
+        (n_clips, n_bins, n_frames) complex -> (out_len,) or (n_clips, out_len) samples. NumPy in -> NumPy out, CUDA
+        ``torch.Tensor`` in -> CUDA tensor out on the current stream."""
+        return self._n.istft(stft_matrix)
 
     def window(self) -> np.ndarray: return self._n.window()
     def kernel_name(self) -> str: return self._n.kernel_name()
@@ -680,6 +725,35 @@ def rfft(samples, n_fft: int, dtype=None):
 
 
 fft = rfft
+
+
+def irfft(spectrum, n_fft: int):
+    """``irfft`` (:4789-4811): n_fft/2 + 1 complex bins -> n_fft samples (true inverse of ``rfft``)."""
+    L = _native.lib()
+    x = np.ascontiguousarray(spectrum)
+    if x.dtype not in (np.complex64, np.complex128):
+        x = x.astype(np.complex128)
+    if x.ndim != 1 or x.size == 0:
+        raise InvalidInputError("spectrum must be a non-empty 1-D complex array")
+    out = np.empty(int(n_fft), dtype=np.float32 if x.dtype == np.complex64 else np.float64)
+    _native.check(L.sgx_irfft(0 if x.dtype == np.complex64 else 1, x.ctypes.data, x.size, int(n_fft), out.ctypes.data, -1, None))
+    return out
+
+
+def istft(stft_matrix, n_fft: int, hop_size: int, window="hanning", center: bool = True):
+    """``istft<T>()`` (:4813-4911): overlap-add reconstruction from a complex (n_fft/2+1, n_frames) matrix (or a batch of
+    them); builds a fresh plan like ``stft()`` does. dtype follows the matrix (complex64 -> float32)."""
+    if _is_torch(stft_matrix):
+        dt = "float32" if str(stft_matrix.dtype).endswith("complex64") else "float64"
+        device = stft_matrix.device.index
+    else:
+        stft_matrix = np.asarray(stft_matrix)
+        dt = "float32" if stft_matrix.dtype == np.complex64 else "float64"
+        device = None
+    if int(hop_size) > int(n_fft):
+        raise InvalidInputError("hop_size must be <= n_fft")                   # :4829-4831
+    params = SpectrogramParams(StftParams(n_fft, hop_size, window, center), 1.0)
+    return StftPlan(params, dt, device).istft(stft_matrix)
 
 
 def power_spectrum(samples, n_fft: int, window: Optional[WindowType] = None, dtype=None):
