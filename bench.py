@@ -39,6 +39,8 @@ WORKLOADS = {
                   label="configs[2] music mel-dB per-GPU shard: 512 clips x 30 s @22.05 kHz, n_fft=2048 hop=512 128 mels dB f32"),
     "mfcc": dict(n_clips=1024, n_samples=160000, sr=16000.0, n_fft=400, hop=160, dtype="float32", kind="mfcc",
                  label="configs[3] MFCC per-GPU shard: 1024 clips x 10 s @16 kHz, n_fft=400 hop=160 128 mels -> 40 MFCC f32"),
+    "asr512": dict(n_clips=1024, n_samples=480000, sr=16000.0, n_fft=512, hop=160, dtype="float32", kind="mel_db80",
+                   label="common ASR front end (not a BASELINE config): 1024 clips x 30 s @16 kHz, n_fft=512 hop=160 80 mels dB f32"),
     "chroma": dict(n_clips=512, n_samples=661500, sr=22050.0, n_fft=2048, hop=512, dtype="float32", kind="chroma",
                    label="SURVEY 8f rank 2, chromagram() on the configs[2] shard: 512 clips x 30 s @22.05 kHz, n_fft=2048 hop=512 -> 12 pitch classes (L2) f32"),
     "multichannel": dict(n_clips=64, n_samples=2880000, sr=48000.0, n_fft=4096, hop=1024, dtype="float64", kind="linear_mag",
@@ -52,7 +54,7 @@ def frames_of(w):
 
 
 def out_rows(w):
-    return {"mel_db": 128, "mfcc": 40, "chroma": 12, "linear_mag": w["n_fft"] // 2 + 1}[w["kind"]]
+    return {"mel_db": 128, "mel_db80": 80, "mfcc": 40, "chroma": 12, "linear_mag": w["n_fft"] // 2 + 1}[w["kind"]]
 
 
 def algorithmic_bytes(w):
@@ -64,8 +66,8 @@ def algorithmic_bytes(w):
 def make_plan(w, device=None):
     import spectrograms_b200 as sg
     params = sg.SpectrogramParams(sg.StftParams(w["n_fft"], w["hop"], sg.WindowType.hanning(), True), w["sr"])
-    if w["kind"] == "mel_db":
-        return sg.SpectrogramPlanner(device).mel_plan(params, sg.MelParams(128, 0.0, w["sr"] / 2), sg.LogParams(-80.0), "db", w["dtype"])
+    if w["kind"] in ("mel_db", "mel_db80"):
+        return sg.SpectrogramPlanner(device).mel_plan(params, sg.MelParams(out_rows(w), 0.0, w["sr"] / 2), sg.LogParams(-80.0), "db", w["dtype"])
     if w["kind"] == "mfcc":
         return sg.MfccPlan(params.stft, w["sr"], 128, sg.MfccParams(40), w["dtype"], device)
     if w["kind"] == "chroma":
@@ -76,8 +78,8 @@ def make_plan(w, device=None):
 def oracle_desc(w):
     import oracle
     kw = dict(dtype="f32" if w["dtype"] == "float32" else "f64", n_fft=w["n_fft"], hop=w["hop"], sample_rate=w["sr"])
-    if w["kind"] in ("mel_db", "mfcc"):
-        kw.update(mapping="mel", n_bands=128, f_min=0.0, f_max=w["sr"] / 2, amp="db", floor_db=-80.0)
+    if w["kind"] in ("mel_db", "mel_db80", "mfcc"):
+        kw.update(mapping="mel", n_bands=80 if w["kind"] == "mel_db80" else 128, f_min=0.0, f_max=w["sr"] / 2, amp="db", floor_db=-80.0)
     else:
         kw.update(amp="magnitude")
     return oracle.Desc(**kw)

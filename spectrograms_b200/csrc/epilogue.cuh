@@ -75,7 +75,16 @@ __device__ __forceinline__ void epilogue_from_power(const KParams &p, T *__restr
             const T *val = static_cast<const T *>(p.val);
             const int e0 = __ldg(p.row_ptr + row), e1 = __ldg(p.row_ptr + row + 1);
             acc = T(0);
-            for (int e = e0; e < e1; ++e) acc = t_add_rn(acc, t_mul_rn(__ldg(val + e), pf[__ldg(p.col + e)]));
+            if (p.rows_contig) {
+                // consecutive columns (every mel / loghz row): one column load per row, unrolled weight / tile loads
+                const T *w = val + e0;
+                const T *px = pf + (e0 < e1 ? __ldg(p.col + e0) : 0);
+                const int cnt = e1 - e0;
+#pragma unroll 4
+                for (int i = 0; i < cnt; ++i) acc = t_add_rn(acc, t_mul_rn(__ldg(w + i), px[i]));
+            } else {
+                for (int e = e0; e < e1; ++e) acc = t_add_rn(acc, t_mul_rn(__ldg(val + e), pf[__ldg(p.col + e)]));
+            }
         }
         acc = amp_scale<T>(acc, p.amp, p.apply_db, eps);
         if (to_mfcc) scratch[f * ts + row] = acc;

@@ -151,14 +151,14 @@ __device__ __forceinline__ void pass_store(Cx<T> *z, int t, Cx<T> *v) {
     }
 }
 
-// Thread -> (frame, thread-in-frame) map. Frames that fit a warp (TPF <= 32) keep their threads together and need only
-// warp-level syncs between passes. Bigger frames (TPF >= 64, FT <= 4) are INTERLEAVED: every warp holds 32 / FT
-// consecutive threads of each of the tile's FT frames, so that the transposed tile writes P[bin][FT] of a warp cover 32
-// consecutive words (they were FT-way bank conflicts with one frame per warp), the window load of a warp is one line
-// shared by its FT frames, and the frame-strided FFT accesses stay conflict free because the frame stride is 8 mod 16
-// complex elements. The price is a CTA-wide barrier between passes instead of a per-frame one.
+// Thread -> (frame, thread-in-frame) map. Small frames (TPF <= 16) keep their threads together inside a warp and need only
+// warp-level syncs between passes. Frames of 32 threads and more (n_fft >= 1024, FT <= 8) are INTERLEAVED: every warp holds
+// LPF = 32 / FT consecutive threads of each of the tile's FT frames, so that the transposed tile writes P[bin][FT] of a
+// warp cover 32 consecutive words (they were FT-way bank conflicts with one frame per warp), the window load of a warp
+// is one line shared by its FT frames, and the frame-strided FFT accesses stay conflict free because the frame stride
+// is LPF mod 16 complex elements (zs_of). The price is a CTA-wide barrier between passes instead of a per-frame one.
 template <int TPF, int FT> struct ThreadMap {
-    static constexpr bool kInterleaved = TPF >= 64 && FT > 1;
+    static constexpr bool kInterleaved = TPF >= 32 && FT > 1;
     static constexpr int LPF = kInterleaved ? 32 / FT : TPF;        // lanes of one frame inside a warp
     static __device__ __forceinline__ void get(int tid, int &fl, int &t) {
         if (kInterleaved) {
@@ -172,11 +172,17 @@ template <int TPF, int FT> struct ThreadMap {
     }
 };
 template <int TPF, int FT> __device__ __forceinline__ void frame_sync(int) {
-    if (TPF <= 32) __syncwarp();
-    else __syncthreads();
+    if (ThreadMap<TPF, FT>::kInterleaved || TPF > 32) __syncthreads();
+    else __syncwarp();
 }
 
-constexpr int zs_of(int M) { return pad16(M) + 8; }   // complex elements per frame buffer: >= M + 1 bins, 8 mod 16 for M >= 256
+// complex elements per frame buffer: >= M + 1 bins; for the interleaved map the stride is LPF mod 16 (M >= 256 makes
+// pad16(M) a multiple of 16), which spreads the FT frame segments a warp touches over all banks
+constexpr int zs_of(int M, int FT) {
+    const int tpf = M / 16;
+    const bool inter = tpf >= 32 && FT > 1;
+    return pad16(M) + (inter ? 32 / FT : 8);
+}
 
 template <int M> struct Radices {          // M = 16^P16 * LAST, LAST in {1, 2, 4, 8}
     static constexpr int P16 = M >= 4096 ? 3 : (M >= 256 ? 2 : 1);
@@ -186,7 +192,7 @@ template <int M> struct Radices {          // M = 16^P16 * LAST, LAST in {1, 2, 
 template <typename T, int M, int FT>
 __global__ void __launch_bounds__(FT *(M / 16), (sizeof(T) == 4 ? 4 : 2) * 256 / (FT * (M / 16) > 256 ? FT * (M / 16) : 256)) k_r2c_fused_pow2(const __grid_constant__ KParams p) {
     constexpr int TPF = M / 16, N = 2 * M;
-    constexpr int ZS = zs_of(M);                     // complex elements per frame buffer (M+1 spectrum bins fit too)
+    constexpr int ZS = zs_of(M, FT);                     // complex elements per frame buffer (M+1 spectrum bins fit too)
     using C = Cx<T>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C *zbuf = reinterpret_cast<C *>(smem_raw);
@@ -445,6 +451,27 @@ __global__ void __launch_bounds__(FT *(M / 16), (sizeof(T) == 4 ? 4 : 2) * 256 /
     }
     if (t == 0) pf[M / 2] = pm;
     __syncthreads();
+    if (FT >= 16 && p.output == SGX_OUT_SPECTROGRAM && p.rows_contig && (p.mapping == SGX_MAP_MEL || p.mapping == SGX_MAP_LOGHZ)) {
+        // Wide tiles (n_fft 256 / 512), sparse rows: lane = frame, FT consecutive lanes share a row, so the row's extent
+        // and every weight are one broadcast load and the store is a run of FT frames; all index math is compile time.
+        // Ascending-column, un-fused accumulation as in SparseMatrix::multiply_vec (src/spectrogram.rs:102-117).
+        constexpr int NT = FT * TPF, GROUPS = NT / FT;
+        const int f = tid % FT, g = tid / FT;
+        const T eps = static_cast<T>(p.eps);
+        const T *val = static_cast<const T *>(p.val);
+        const T *px = P + f * p.tile_stride;
+        T *out = static_cast<T *>(p.out) + static_cast<long long>(clip) * p.out_clip_stride + (f0 - p.out_frame_origin) + f;
+        for (int row = g; row < p.n_bins; row += GROUPS) {
+            const int e0 = __ldg(p.row_ptr + row), cnt = __ldg(p.row_ptr + row + 1) - e0;
+            const T *w = val + e0;
+            const T *pc = px + (cnt > 0 ? __ldg(p.col + e0) : 0);
+            T acc = T(0);
+#pragma unroll 4
+            for (int i = 0; i < cnt; ++i) acc = t_add_rn(acc, t_mul_rn(__ldg(w + i), pc[i]));
+            if (f < nf) out[static_cast<long long>(row) * p.out_row_stride] = amp_scale<T>(acc, p.amp, p.apply_db, eps);
+        }
+        return;
+    }
     // scratch for the fused-MFCC log-mel tile sits behind the power tile (host sizes the buffer for it)
     epilogue_from_power<T>(p, P, P + FT * p.tile_stride, clip, f0, nf);
     (void)N;
@@ -477,7 +504,7 @@ bool pow2_supported(size_t n_fft) {
     return n_fft >= 256 && n_fft <= 8192 && (n_fft & (n_fft - 1)) == 0;
 }
 int pow2_frames_per_tile(size_t n_fft, bool f64) { return ft_of(static_cast<int>(n_fft / 2), f64); }
-int pow2_frame_elems(size_t n_fft) { return zs_of(static_cast<int>(n_fft / 2)); }
+int pow2_frame_elems(size_t n_fft) { return zs_of(static_cast<int>(n_fft / 2), ft_of(static_cast<int>(n_fft / 2), false)); }
 
 cudaError_t launch_pow2(const KParams &p, bool f64, size_t smem, cudaStream_t stream) {
 #define SGX_POW2_CASE(MM)                                                                         \

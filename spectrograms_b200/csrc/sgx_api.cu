@@ -455,6 +455,7 @@ void fill_params(const sgx_plan &pl, KParams &p) {
     p.window = pl.d_window; p.tw = pl.d_tw; p.post = pl.d_post;
     p.mapping = d.mapping;
     p.n_bins = static_cast<int>(pl.tab.n_bins);
+    p.rows_contig = pl.rows_contig ? 1 : 0;
     p.lane_rows = reinterpret_cast<const int4 *>(pl.d_lane_rows);
     p.lane_w = pl.d_lane_w;
     p.n_lane_slots = static_cast<int>(pl.lane_rows.size() / 4);
