@@ -14,6 +14,7 @@
 //
 // Compared with the generic family this cuts the shared-memory round trips from log4(M) to 2-3 and removes every
 // runtime division from the index math (all radices, strides and shifts are template constants).
+#include "binaural.cuh"
 #include "epilogue.cuh"
 #include "launch.hpp"
 
@@ -189,7 +190,7 @@ template <int M> struct Radices {          // M = 16^P16 * LAST, LAST in {1, 2, 
     static constexpr int LAST = M / (P16 == 3 ? 4096 : (P16 == 2 ? 256 : 16));
 };
 
-template <typename T, int M, int FT>
+template <typename T, int M, int FT, bool PAIR>
 __global__ void __launch_bounds__(FT *(M / 16), (sizeof(T) == 4 ? 4 : 2) * 256 / (FT * (M / 16) > 256 ? FT * (M / 16) : 256)) k_r2c_fused_pow2(const __grid_constant__ KParams p) {
     constexpr int TPF = M / 16, N = 2 * M;
     constexpr int ZS = zs_of(M, FT);                     // complex elements per frame buffer (M+1 spectrum bins fit too)
@@ -202,12 +203,20 @@ __global__ void __launch_bounds__(FT *(M / 16), (sizeof(T) == 4 ? 4 : 2) * 256 /
     ThreadMap<TPF, FT>::get(tid, fl, t);
     const int clip = blockIdx.x / p.tiles_per_clip;
     const int tile = blockIdx.x - clip * p.tiles_per_clip;
-    const long long f0 = p.frame_begin + static_cast<long long>(tile) * FT;
+    // Ordinary launch: the tile is FT consecutive frames of one clip. Stereo-pair launch (samples_b != null, FT >= 2): FT/2
+    // frames of the left channel in slots 0 .. FT/2-1 and the SAME frames of the right channel in the upper half, so that
+    // the cue epilogue finds both spectra of a frame in the tile.
+    constexpr int HF = FT >= 2 ? FT / 2 : 1;
+    constexpr bool pair = PAIR && FT >= 2;           // a separate instantiation: the ordinary kernels carry none of this
+    const int tf = pair ? HF : FT;                   // time frames per tile
+    const int ch = pair ? fl / HF : 0;
+    const int fi = fl - ch * HF * (pair ? 1 : 0);    // time-frame slot of this thread's frame
+    const long long f0 = p.frame_begin + static_cast<long long>(tile) * tf;
     const long long rem = p.frame_begin + p.frames_todo - f0;
-    const int nf = rem < FT ? static_cast<int>(rem) : FT;
+    const int nf = rem < tf ? static_cast<int>(rem) : tf;
     C *z = zbuf + fl * ZS;
 
-    const T *x = static_cast<const T *>(p.samples) + static_cast<long long>(clip) * p.clip_stride;
+    const T *x = static_cast<const T *>(ch ? p.samples_b : p.samples) + static_cast<long long>(clip) * p.clip_stride;
     const T *win = static_cast<const T *>(p.window);
     const C *tw = static_cast<const C *>(p.tw);
     C v[16];
@@ -215,7 +224,7 @@ __global__ void __launch_bounds__(FT *(M / 16), (sizeof(T) == 4 ? 4 : 2) * 256 /
     // ---- load + window + first pass (CUR = 1: no twiddles). Element n of the packed frame = samples 2n, 2n+1.
     {
         constexpr int R = 16, B = M / R;
-        const long long base = (f0 + fl) * p.hop - p.pad;
+        const long long base = (f0 + (pair ? fi : fl)) * p.hop - p.pad;
         const bool vec_ok = p.vec_ok != 0;
         if (vec_ok && base >= 0 && base + N <= p.n_samples) {
             // interior frame (all but the first / last few of a clip): no bounds logic
@@ -299,6 +308,21 @@ __global__ void __launch_bounds__(FT *(M / 16), (sizeof(T) == 4 ? 4 : 2) * 256 /
         }
         if (t == 0) S[M / 2] = mk<T>(xm.x, xm.y);
         __syncthreads();
+        if (pair) {
+            // compute_{itd,ipd,ild,ilr}_spectrogram (src/binaural.rs:472, :830, :1187, :1530) on the tile: (bin, frame) with
+            // frames fastest, both channels' spectra read from shared memory, one run of HF frames stored per band row
+            const typename Cplx<T>::type *S0 = reinterpret_cast<const typename Cplx<T>::type *>(zbuf);
+            T *out = static_cast<T *>(p.out) + static_cast<long long>(clip) * p.out_clip_stride + (f0 - p.out_frame_origin);
+            const T bw = static_cast<T>(p.cue_bin_width);
+            for (int idx = tid; idx < p.cue_band * HF; idx += FT * TPF) {
+                const int b = idx / HF, f = idx - b * HF;
+                if (f >= nf) continue;
+                const int k = p.cue_start_bin + b;
+                const typename Cplx<T>::type l = S0[f * p.frame_stride + k], r = S0[(HF + f) * p.frame_stride + k];
+                out[static_cast<long long>(b) * p.out_row_stride + f] = binaural_cue<T>(p.cue, l.x, l.y, r.x, r.y, k, bw, p.cue_power, p.cue_wrapped);
+            }
+            return;
+        }
         epilogue_complex<T>(p, reinterpret_cast<typename Cplx<T>::type *>(zbuf), clip, f0, nf);
         return;
     }
@@ -477,14 +501,14 @@ __global__ void __launch_bounds__(FT *(M / 16), (sizeof(T) == 4 ? 4 : 2) * 256 /
     (void)N;
 }
 
-template <typename T, int M, int FT>
+template <typename T, int M, int FT, bool PAIR>
 cudaError_t launch_one(const KParams &p, size_t smem, cudaStream_t stream) {
     const long long grid = static_cast<long long>(p.n_clips) * p.tiles_per_clip;
     if (grid <= 0) return cudaSuccess;
     if (grid > 2147483647LL) return cudaErrorInvalidConfiguration;
-    cudaError_t e = cudaFuncSetAttribute(k_r2c_fused_pow2<T, M, FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaError_t e = cudaFuncSetAttribute(k_r2c_fused_pow2<T, M, FT, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    k_r2c_fused_pow2<T, M, FT><<<static_cast<unsigned>(grid), FT *(M / 16), smem, stream>>>(p);
+    k_r2c_fused_pow2<T, M, FT, PAIR><<<static_cast<unsigned>(grid), FT *(M / 16), smem, stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -509,7 +533,9 @@ int pow2_frame_elems(size_t n_fft) { return zs_of(static_cast<int>(n_fft / 2), f
 cudaError_t launch_pow2(const KParams &p, bool f64, size_t smem, cudaStream_t stream) {
 #define SGX_POW2_CASE(MM)                                                                         \
     case MM:                                                                                      \
-        return f64 ? launch_one<double, MM, ft_of(MM, true)>(p, smem, stream) : launch_one<float, MM, ft_of(MM, false)>(p, smem, stream);
+        if (p.samples_b != nullptr)                                                                \
+            return f64 ? launch_one<double, MM, ft_of(MM, true), true>(p, smem, stream) : launch_one<float, MM, ft_of(MM, false), true>(p, smem, stream); \
+        return f64 ? launch_one<double, MM, ft_of(MM, true), false>(p, smem, stream) : launch_one<float, MM, ft_of(MM, false), false>(p, smem, stream);
     switch (p.n_fft / 2) {
         SGX_POW2_CASE(128)
         SGX_POW2_CASE(256)

@@ -46,6 +46,13 @@ struct KParams {
     const int4 *lane_rows;    // r2c_fused_pow2 rows epilogue: per lane slot {row or -1, first column, count, weight block offset}
     const void *lane_w;       // T: weights, lane-major per warp block: [block offset + i * 32 + lane]
     int n_lane_slots;         // multiple of 32 (0: table absent)
+    // ---- fused stereo-pair binaural cues (r2c_fused_pow2, complex-STFT plans): a tile holds FT/2 frames of each channel
+    const void *samples_b;    // right channel [n_clips][clip_stride]; null = ordinary launch
+    int cue;                  // sgx_binaural_cue
+    int cue_start_bin, cue_band;
+    unsigned cue_power;
+    int cue_wrapped;
+    double cue_bin_width;
     const void *sched;    // r2c_fused_n400: host-built quad schedule of the sparse mapping (see sgx_api.cu), else null
     const void *dense_t;  // T[out_len][n_bins]  the dense matrix transposed (chroma; null otherwise)
     int dense_c0, dense_c1;   // columns outside [dense_c0, dense_c1) of the dense matrix are exactly zero in every row

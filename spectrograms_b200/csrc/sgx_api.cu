@@ -816,7 +816,7 @@ sgx_status sgx_plan_compute_binaural(sgx_plan *plan, sgx_binaural_cue cue, const
         // pairs per chunk: both channels' STFTs of a chunk stay under ~512 MB each
         size_t chunk = std::max<size_t>(1, (size_t(512) << 20) / stft_bytes);
         chunk = std::min(chunk, n_pairs);
-        if (pl.pair_cap < chunk * stft_bytes) {
+        if (!(pl.pow2 && !pl.force_generic && pl.pow2_ft >= 2) && pl.pair_cap < chunk * stft_bytes) {
             for (void *&q : pl.d_pair) { if (q) { ck(cudaDeviceSynchronize(), "sync"); cudaFree(q); q = nullptr; } }
             pl.pair_cap = 0;
             ck(cudaMalloc(&pl.d_pair[0], chunk * stft_bytes), "cudaMalloc(binaural scratch)");
@@ -825,6 +825,67 @@ sgx_status sgx_plan_compute_binaural(sgx_plan *plan, sgx_binaural_cue cue, const
         }
         sgx_plan::Slot &s = pl.slot[0];
         cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+        // Power-of-two plans with at least two frames per tile transform both channels of a pair in ONE launch and
+        // compute the cue in its epilogue: the complex spectra never leave the SM.
+        const bool fused = pl.pow2 && !pl.force_generic && pl.pow2_ft >= 2;
+        if (fused) {
+            if (host) {
+                size_t hchunk = std::max<size_t>(1, (size_t(256) << 20) / std::max(2 * n_samples * es, cue_elems * es));
+                hchunk = std::min(hchunk, n_pairs);
+                ensure_slot(s, 2 * hchunk * n_samples * es, hchunk * cue_elems * es);
+                st = s.s;
+                chunk = hchunk;
+            } else {
+                chunk = n_pairs;
+            }
+            for (size_t p0 = 0; p0 < n_pairs; p0 += chunk) {
+                const size_t np = std::min(chunk, n_pairs - p0);
+                const void *ch[2] = {static_cast<const char *>(left) + p0 * clip_stride * es, static_cast<const char *>(right) + p0 * clip_stride * es};
+                size_t stride = clip_stride;
+                if (host) {
+                    char *d_in = static_cast<char *>(s.d_in);
+                    for (int c = 0; c < 2; ++c) {
+                        ck(cudaMemcpy2DAsync(d_in + c * np * n_samples * es, n_samples * es, ch[c], clip_stride * es, n_samples * es, np,
+                                             cudaMemcpyHostToDevice, st), "H2D copy");
+                        ch[c] = d_in + c * np * n_samples * es;
+                    }
+                    stride = n_samples;
+                }
+                void *dst = host ? s.d_out : static_cast<char *>(out) + p0 * cue_elems * es;
+                KParams q;
+                fill_params(pl, q);
+                q.samples = ch[0];
+                q.samples_b = ch[1];
+                q.n_samples = static_cast<long long>(n_samples);
+                q.clip_stride = static_cast<long long>(stride);
+                q.n_clips = static_cast<int>(np);
+                q.frame_begin = 0;
+                q.frames_todo = static_cast<long long>(n_frames);
+                q.out = dst;
+                q.out_row_stride = static_cast<long long>(n_frames);
+                q.out_clip_stride = static_cast<long long>(cue_elems);
+                q.out_frame_origin = 0;
+                q.FT = pl.pow2_ft;
+                q.frame_stride = pl.pow2_frame_stride;
+                q.tile_stride = pl.pow2_tile_stride;
+                const int hf = pl.pow2_ft / 2;
+                q.tiles_per_clip = static_cast<int>((n_frames + hf - 1) / hf);
+                q.vec_ok = (reinterpret_cast<uintptr_t>(ch[0]) % (2 * es) == 0 && reinterpret_cast<uintptr_t>(ch[1]) % (2 * es) == 0 &&
+                            stride % 2 == 0 && pl.desc.hop_size % 2 == 0 && q.pad % 2 == 0) ? 1 : 0;
+                q.cue = cue;
+                q.cue_start_bin = static_cast<int>(start_bin);
+                q.cue_band = static_cast<int>(out_bins);
+                q.cue_power = static_cast<unsigned>(magphase_power);
+                q.cue_wrapped = wrapped;
+                q.cue_bin_width = bw;
+                if (static_cast<long long>(np) * q.tiles_per_clip > 2147483647LL) backend("batch too large for one launch");
+                ck(launch_pow2(q, pl.f64, pl.pow2_smem, st), "kernel launch (r2c_fused_pow2, stereo pair)");
+                pl.last_launches += 1;
+                if (host) ck(cudaMemcpyAsync(static_cast<char *>(out) + p0 * cue_elems * es, s.d_out, np * cue_elems * es, cudaMemcpyDeviceToHost, st), "D2H copy");
+            }
+            if (host) ck(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+            return;
+        }
         if (host) {
             ensure_slot(s, 2 * chunk * n_samples * es, chunk * cue_elems * es);
             st = s.s;
