@@ -501,6 +501,112 @@ __global__ void __launch_bounds__(FT *(M / 16), (sizeof(T) == 4 ? 4 : 2) * 256 /
     (void)N;
 }
 
+// Inverse of the above for istft / irfft (src/spectrogram.rs:4789-4911): one CTA = FT frames of one clip. The Hermitian
+// half spectrum X (bins, frames) is staged frame-major through shared memory (global reads run along frames), every
+// thread builds its 16 first-pass inputs conj(Z[n]), Z = E + i O with E = (X[n] + conj X[M-n]) / 2 and
+// O = (X[n] - conj X[M-n]) / 2 * conj(W_N^n), the same register radix-16 Stockham passes run FORWARD on conj(Z), and
+// x[2m] = Re Y[m] / M, x[2m+1] = -Im Y[m] / M go out times the synthesis window as time frames [clip][frame][N]
+// (ola_gather in kernel_inverse.cu adds them up). DC / Nyquist imaginary parts are ignored, as realfft does.
+template <typename T, int M, int FT>
+__global__ void __launch_bounds__(FT *(M / 16), (sizeof(T) == 4 ? 4 : 2) * 256 / (FT * (M / 16) > 256 ? FT * (M / 16) : 256))
+k_c2r_pow2(const __grid_constant__ KParams p, const typename Cplx<T>::type *__restrict__ stft, T *__restrict__ frames_out, long long n_frames,
+           int apply_window) {
+    constexpr int TPF = M / 16, N = 2 * M, B = M / 16, NT = FT * TPF;
+    constexpr int ZS = zs_of(M, FT);
+    using C = Cx<T>;
+    using C2 = typename Cplx<T>::type;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C *zbuf = reinterpret_cast<C *>(smem_raw);
+    const int tid = threadIdx.x;
+    int fl, t;
+    ThreadMap<TPF, FT>::get(tid, fl, t);
+    const int clip = blockIdx.x / p.tiles_per_clip;
+    const int tile = blockIdx.x - clip * p.tiles_per_clip;
+    const long long f0 = static_cast<long long>(tile) * FT;
+    const long long rem = n_frames - f0;
+    const int nf = rem < FT ? static_cast<int>(rem) : FT;
+    C *z = zbuf + fl * ZS;
+    const C *tw = static_cast<const C *>(p.tw);
+    const C *post = static_cast<const C *>(p.post);
+
+    // ---- stage X[k][f0 .. f0 + nf) as S[f][k] (frames fastest across lanes)
+    {
+        const C2 *X = stft + static_cast<long long>(clip) * (M + 1) * n_frames + f0;
+        C2 *S = reinterpret_cast<C2 *>(zbuf);
+        for (int idx = tid; idx < (M + 1) * FT; idx += NT) {
+            const int k = idx / FT, f = idx - k * FT;
+            S[f * ZS + k] = f < nf ? X[static_cast<long long>(k) * n_frames + f] : mk<T>(T(0), T(0));
+        }
+    }
+    __syncthreads();
+    C v[16];
+    {
+        const C *S = z;                                // this frame's spectrum, natural order
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int n = t + j * B;
+            C a = S[n], b = S[M - n];
+            if (n == 0) { a.y = T(0); b.y = T(0); }
+            const C e = {T(0.5) * (a.x + b.x), T(0.5) * (a.y - b.y)};
+            const C d = {T(0.5) * (a.x - b.x), T(0.5) * (a.y + b.y)};
+            const C w = ldg_cx<T>(post + n);
+            const C o = {d.x * w.x + d.y * w.y, d.y * w.x - d.x * w.y};
+            v[j] = {e.x - o.y, -(e.y + o.x)};
+        }
+    }
+    __syncthreads();                                   // every spectrum value is in registers: the buffers may be overwritten
+    pass_store<T, M, 16, 1>(z, t, v);
+    frame_sync<TPF, FT>(fl);
+    if constexpr (Radices<M>::P16 >= 2) {
+        pass_load<T, M, 16, 16>(z, tw, t, v);
+        frame_sync<TPF, FT>(fl);
+        pass_store<T, M, 16, 16>(z, t, v);
+        frame_sync<TPF, FT>(fl);
+    }
+    if constexpr (Radices<M>::P16 >= 3) {
+        pass_load<T, M, 16, 256>(z, tw, t, v);
+        frame_sync<TPF, FT>(fl);
+        pass_store<T, M, 16, 256>(z, t, v);
+        frame_sync<TPF, FT>(fl);
+    }
+    if constexpr (Radices<M>::LAST > 1) {
+        constexpr int CUR = M / Radices<M>::LAST;
+        pass_load<T, M, Radices<M>::LAST, CUR>(z, tw, t, v);
+        frame_sync<TPF, FT>(fl);
+        pass_store<T, M, Radices<M>::LAST, CUR>(z, t, v);
+        frame_sync<TPF, FT>(fl);
+    }
+    if (fl >= nf) return;
+    // ---- conj, scale, window, store: thread t owns packed samples m = t + TPF * u
+    const T scale = T(1) / static_cast<T>(M);
+    const C *win = reinterpret_cast<const C *>(static_cast<const T *>(p.window));
+    C *dst = reinterpret_cast<C *>(frames_out + (static_cast<long long>(clip) * n_frames + f0 + fl) * N);
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+        const int m = t + TPF * u;
+        const C y = z[pad16(m)];
+        C x = {y.x * scale, -y.y * scale};
+        if (apply_window) {
+            const C w = ldg_cx<T>(win + m);
+            x = {x.x * w.x, x.y * w.y};
+        }
+        dst[m] = x;
+    }
+}
+
+template <typename T, int M, int FT>
+cudaError_t launch_c2r_one(const KParams &p, size_t smem, const void *stft, void *frames_out, long long n_clips, long long n_frames,
+                           int apply_window, cudaStream_t stream) {
+    const long long grid = n_clips * p.tiles_per_clip;
+    if (grid <= 0) return cudaSuccess;
+    if (grid > 2147483647LL) return cudaErrorInvalidConfiguration;
+    cudaError_t e = cudaFuncSetAttribute(k_c2r_pow2<T, M, FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    k_c2r_pow2<T, M, FT><<<static_cast<unsigned>(grid), FT *(M / 16), smem, stream>>>(p, static_cast<const typename Cplx<T>::type *>(stft),
+                                                                                      static_cast<T *>(frames_out), n_frames, apply_window);
+    return cudaGetLastError();
+}
+
 template <typename T, int M, int FT, bool PAIR>
 cudaError_t launch_one(const KParams &p, size_t smem, cudaStream_t stream) {
     const long long grid = static_cast<long long>(p.n_clips) * p.tiles_per_clip;
@@ -546,6 +652,24 @@ cudaError_t launch_pow2(const KParams &p, bool f64, size_t smem, cudaStream_t st
         default: return cudaErrorInvalidValue;
     }
 #undef SGX_POW2_CASE
+}
+
+cudaError_t launch_c2r_pow2(const KParams &p, bool f64, size_t smem, const void *stft, void *frames_out, long long n_clips,
+                            long long n_frames, int apply_window, cudaStream_t stream) {
+#define SGX_POW2_C2R(MM)                                                                                                         \
+    case MM:                                                                                                                     \
+        return f64 ? launch_c2r_one<double, MM, ft_of(MM, true)>(p, smem, stft, frames_out, n_clips, n_frames, apply_window, stream) \
+                   : launch_c2r_one<float, MM, ft_of(MM, false)>(p, smem, stft, frames_out, n_clips, n_frames, apply_window, stream);
+    switch (p.n_fft / 2) {
+        SGX_POW2_C2R(128)
+        SGX_POW2_C2R(256)
+        SGX_POW2_C2R(512)
+        SGX_POW2_C2R(1024)
+        SGX_POW2_C2R(2048)
+        SGX_POW2_C2R(4096)
+        default: return cudaErrorInvalidValue;
+    }
+#undef SGX_POW2_C2R
 }
 
 }  // namespace sgx

@@ -51,6 +51,9 @@ cudaError_t launch_binaural(bool f64, int cue, const void *left, const void *rig
 // the caller), then the overlap-add gather into out [n_clips][out_len] (trim = samples dropped at the front)
 cudaError_t launch_c2r_frames(const KParams &p, bool f64, size_t smem, const void *stft, void *frames_out, long long n_clips,
                               long long n_frames, int apply_window, cudaStream_t stream);
+// the same on the register radix-16 passes of r2c_fused_pow2 (kernel_pow2.cu); p.tiles_per_clip = ceil(n_frames / FT)
+cudaError_t launch_c2r_pow2(const KParams &p, bool f64, size_t smem, const void *stft, void *frames_out, long long n_clips,
+                            long long n_frames, int apply_window, cudaStream_t stream);
 cudaError_t launch_ola_gather(bool f64, const void *frames, const void *window, void *out, long long n_clips, long long n_frames,
                               int n_fft, int hop, long long out_len, long long trim, cudaStream_t stream);
 

@@ -1034,6 +1034,17 @@ void run_inverse(sgx_plan &pl, const void *d_stft, size_t nc, size_t n_frames, v
     KParams p;
     fill_params(pl, p);
     p.n_clips = static_cast<int>(nc);
+    // the register-radix inverse stores (x[2m], x[2m+1]) pairs: the destination must be pair aligned
+    if (pl.pow2 && !pl.force_generic && reinterpret_cast<uintptr_t>(d_frames_out) % (2 * pl.esize) == 0) {
+        p.FT = pl.pow2_ft;
+        p.frame_stride = pl.pow2_frame_stride;
+        p.tile_stride = pl.pow2_tile_stride;
+        p.tiles_per_clip = static_cast<int>((n_frames + p.FT - 1) / p.FT);
+        ck(launch_c2r_pow2(p, pl.f64, pl.pow2_smem, d_stft, d_frames_out, static_cast<long long>(nc), static_cast<long long>(n_frames),
+                           apply_window, st), "kernel launch (c2r_pow2)");
+        pl.last_launches += 1;
+        return;
+    }
     p.tiles_per_clip = static_cast<int>((n_frames + p.FT - 1) / p.FT);
     ck(launch_c2r_frames(p, pl.f64, pl.smem_bytes, d_stft, d_frames_out, static_cast<long long>(nc), static_cast<long long>(n_frames),
                          apply_window, st), "kernel launch (c2r_frames)");
