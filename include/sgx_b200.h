@@ -1,7 +1,9 @@
 /*
  * sgx_b200.h -- C ABI of libsgx_b200.so, the B200-native (sm_100a) engine for the hot path of the
  * `spectrograms` crate (jmg049/Spectrograms v2.1.0): stft() / StftPlan / SpectrogramPlanner plans
- * (linear | mel | ERB | LogHz  x  power | magnitude | dB) / mfcc_from_log_mel, in f32 and f64.
+ * (linear | mel | ERB | LogHz  x  power | magnitude | dB) / mfcc_from_log_mel, in f32 and f64, and the adjacent
+ * components built on the same kernels: chromagram, the binaural cue spectrograms, irfft / istft.
+ * (sgx_b200.hpp is the C++ host layer over these entry points.)
  *
  * The reference exposes no C ABI; its seam for this path is the plan API. Every entry point
  * below names the reference item it replaces (paths relative to the reference checkout; a bare :N is
