@@ -416,4 +416,37 @@ template <typename T> Matrix<T> chromagram_from_spectrogram(const Matrix<T> &spe
     return out;
 }
 
+// ---- binaural cues (src/binaural.rs): compute_{itd,ipd,ild,ilr}_spectrogram(audio = [left, right], params, plan)
+struct BandParams {                                                   // ITD/IPD/ILD/ILRSpectrogramParams::new (:410-444, :775-806, ...)
+    SpectrogramParams spectrogram_params;
+    double start_freq, end_freq;
+    size_t magphase_power = 1;                                        // ITD only
+    bool wrapped = true;                                              // IPD only
+    BandParams(SpectrogramParams sp, double start, double stop, size_t power = 1, bool wrap = true)
+        : spectrogram_params(std::move(sp)), start_freq(start), end_freq(stop), magphase_power(power), wrapped(wrap) {
+        if (start <= 0.0 || stop <= 0.0) throw InvalidInputError(SGX_INVALID_INPUT, "Start and end frequencies must be positive.");
+        if (start >= stop) throw InvalidInputError(SGX_INVALID_INPUT, "Start frequency must be less than end frequency.");
+        if (stop > spectrogram_params.sample_rate_hz() / 2.0) throw InvalidInputError(SGX_INVALID_INPUT, "End frequency must be less than Nyquist frequency.");
+        if (power == 0) throw InvalidInputError(SGX_INVALID_INPUT, "magphase_power must be non-zero");
+    }
+    std::pair<size_t, size_t> bins() const {                          // (f / bin_width).round() as usize (:476-481)
+        const double bw = spectrogram_params.sample_rate_hz() / static_cast<double>(spectrogram_params.stft().n_fft());
+        return {static_cast<size_t>(start_freq / bw + 0.5), static_cast<size_t>(end_freq / bw + 0.5)};
+    }
+};
+template <typename T> Matrix<T> compute_binaural(sgx_binaural_cue cue, const std::vector<T> &left, const std::vector<T> &right, const BandParams &bp, StftPlan<T> &plan) {
+    if (left.empty() || left.size() != right.size()) throw InvalidInputError(SGX_INVALID_INPUT, "left and right must be equally long and non-empty");
+    const auto [b0, b1] = bp.bins();
+    if (b1 <= b0) throw InvalidInputError(SGX_INVALID_INPUT, "Frequency range should have at least one bin");
+    const size_t nf = plan.output_shape(left.size()).second;
+    Matrix<T> out(b1 - b0, nf);
+    check(sgx_plan_compute_binaural(plan.native(), cue, left.data(), right.data(), 1, left.size(), left.size(), bp.start_freq, bp.end_freq,
+                                    bp.magphase_power, bp.wrapped ? 1 : 0, out.data.data(), out.rows, out.cols, nullptr));
+    return out;
+}
+template <typename T> Matrix<T> compute_itd_spectrogram(const std::vector<T> &l, const std::vector<T> &r, const BandParams &bp, StftPlan<T> &plan) { return compute_binaural<T>(SGX_CUE_ITD, l, r, bp, plan); }   // :472-580
+template <typename T> Matrix<T> compute_ipd_spectrogram(const std::vector<T> &l, const std::vector<T> &r, const BandParams &bp, StftPlan<T> &plan) { return compute_binaural<T>(SGX_CUE_IPD, l, r, bp, plan); }   // :830-917
+template <typename T> Matrix<T> compute_ild_spectrogram(const std::vector<T> &l, const std::vector<T> &r, const BandParams &bp, StftPlan<T> &plan) { return compute_binaural<T>(SGX_CUE_ILD, l, r, bp, plan); }   // :1187-1262
+template <typename T> Matrix<T> compute_ilr_spectrogram(const std::vector<T> &l, const std::vector<T> &r, const BandParams &bp, StftPlan<T> &plan) { return compute_binaural<T>(SGX_CUE_ILR, l, r, bp, plan); }   // :1530-1620
+
 }  // namespace sgx

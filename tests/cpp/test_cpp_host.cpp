@@ -106,6 +106,16 @@ int main() {
     double n2 = 0.0;
     for (size_t r = 0; r < 12; ++r) { if (ch(r, 10) > ch(pc, 10)) pc = r; n2 += ch(r, 10) * ch(r, 10); }
     EXPECT(pc == 9 && std::fabs(n2 - 1.0) < 1e-12);
+    // binaural: right = left / 2 -> ILD = 20 log10(2) dB and ILR = 0.5 on every bin with energy; identical channels -> IPD 0
+    std::vector<double> xr(x.size());
+    for (size_t i = 0; i < x.size(); ++i) xr[i] = 0.5 * x[i];
+    BandParams bp(p, 300.0, 600.0);
+    EXPECT(contains(throws<InvalidInputError>([&] { BandParams(p, 600.0, 300.0); }), "Start frequency must be less than end frequency."));
+    auto ild = compute_ild_spectrogram<double>(x, xr, bp, sp);
+    auto ilr = compute_ilr_spectrogram<double>(x, xr, bp, sp);
+    auto ipd = compute_ipd_spectrogram<double>(x, x, bp, sp);
+    EXPECT(ild.rows == bp.bins().second - bp.bins().first && ild.cols == 63);
+    EXPECT(std::fabs(ild(4, 30) - 20.0 * std::log10(2.0)) < 1e-9 && std::fabs(ilr(4, 30) - 0.5) < 1e-12 && ipd(4, 30) == 0.0);
     std::puts("CPP_HOST_OK host+gpu");
     return 0;
 }
