@@ -73,16 +73,16 @@ __device__ __forceinline__ void epilogue_from_power(const KParams &p, T *__restr
             for (int k = 0; k < p.out_len; ++k) acc = t_add_rn(acc, t_mul_rn(__ldg(w + k), pf[k]));
         } else {
             const T *val = static_cast<const T *>(p.val);
-            const int e0 = __ldg(p.row_ptr + row), e1 = __ldg(p.row_ptr + row + 1);
             acc = T(0);
             if (p.rows_contig) {
-                // consecutive columns (every mel / loghz row): one column load per row, unrolled weight / tile loads
-                const T *w = val + e0;
-                const T *px = pf + (e0 < e1 ? __ldg(p.col + e0) : 0);
-                const int cnt = e1 - e0;
+                // consecutive columns (every mel / loghz row): one descriptor load per row, unrolled weight / tile loads
+                const int4 d = __ldg(p.row_desc + row);          // {first entry, count, first column}
+                const T *w = val + d.x;
+                const T *px = pf + d.z;
 #pragma unroll 4
-                for (int i = 0; i < cnt; ++i) acc = t_add_rn(acc, t_mul_rn(__ldg(w + i), px[i]));
+                for (int i = 0; i < d.y; ++i) acc = t_add_rn(acc, t_mul_rn(__ldg(w + i), px[i]));
             } else {
+                const int e0 = __ldg(p.row_ptr + row), e1 = __ldg(p.row_ptr + row + 1);
                 for (int e = e0; e < e1; ++e) acc = t_add_rn(acc, t_mul_rn(__ldg(val + e), pf[__ldg(p.col + e)]));
             }
         }

@@ -486,9 +486,10 @@ __global__ void __launch_bounds__(FT *(M / 16), (sizeof(T) == 4 ? 4 : 2) * 256 /
         const T *px = P + f * p.tile_stride;
         T *out = static_cast<T *>(p.out) + static_cast<long long>(clip) * p.out_clip_stride + (f0 - p.out_frame_origin) + f;
         for (int row = g; row < p.n_bins; row += GROUPS) {
-            const int e0 = __ldg(p.row_ptr + row), cnt = __ldg(p.row_ptr + row + 1) - e0;
-            const T *w = val + e0;
-            const T *pc = px + (cnt > 0 ? __ldg(p.col + e0) : 0);
+            const int4 d = __ldg(p.row_desc + row);              // {first entry, count, first column}
+            const int cnt = d.y;
+            const T *w = val + d.x;
+            const T *pc = px + d.z;
             T acc = T(0);
 #pragma unroll 4
             for (int i = 0; i < cnt; ++i) acc = t_add_rn(acc, t_mul_rn(__ldg(w + i), pc[i]));

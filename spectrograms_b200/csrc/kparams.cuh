@@ -43,6 +43,7 @@ struct KParams {
     const void *val;      // T[nnz]              T::from_f64(value) (:113)
     const void *dense;    // T[n_bins][out_len]  (erb)
     int rows_contig;      // every CSR row's columns are consecutive (mel triangles, loghz pairs): col[e] = col[e0] + (e - e0)
+    const int4 *row_desc; // rows_contig only: per row {first entry e0, count, first column, 0} -- one 16-byte load instead of three dependent ones
     const int4 *lane_rows;    // r2c_fused_pow2 rows epilogue: per lane slot {row or -1, first column, count, weight block offset}
     const void *lane_w;       // T: weights, lane-major per warp block: [block offset + i * 32 + lane]
     int n_lane_slots;         // multiple of 32 (0: table absent)

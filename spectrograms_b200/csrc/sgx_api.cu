@@ -145,6 +145,8 @@ struct sgx_plan {
     bool fast400_sparse = false;     // ... with the shared-memory sparse table
     int sparse_quads = 0, sparse_weights = 0;
     bool rows_contig = false;        // CSR rows have consecutive columns
+    std::vector<int> row_desc;       // contiguous CSR rows: int4 {e0, cnt, c0, 0} per row
+    int *d_row_desc = nullptr;
     std::vector<int> lane_rows;      // r2c_fused_pow2 rows epilogue: int4 per lane slot
     std::vector<double> lane_w;      // ... and its lane-major weights
     int *d_lane_rows = nullptr;
@@ -170,6 +172,7 @@ struct sgx_plan {
         if (d_col) cudaFree(d_col);
         if (d_wofs) cudaFree(d_wofs);
         if (d_lane_rows) cudaFree(d_lane_rows);
+        if (d_row_desc) cudaFree(d_row_desc);
         if (d_lane_w) cudaFree(d_lane_w);
         if (d_dense_t) cudaFree(d_dense_t);
         for (void *q : d_pair) if (q) cudaFree(q);
@@ -344,6 +347,12 @@ void select_family(sgx_plan &pl) {
         pl.sparse_weights = padded;
     }
     pl.rows_contig = csr && contiguous;
+    pl.row_desc.clear();
+    if (pl.rows_contig)
+        for (size_t r = 0; r < pl.tab.n_bins; ++r) {
+            const int e0 = pl.tab.row_ptr[r], cnt = pl.tab.row_ptr[r + 1] - e0;
+            pl.row_desc.insert(pl.row_desc.end(), {e0, cnt, cnt ? pl.tab.col[e0] : 0, 0});
+        }
     // dense mappings: the column range outside which every row is exactly zero (chroma: bins outside [f_min, f_max]),
     // and, for chroma, the matrix transposed to [bin][12] for the chunked row sums of r2c_fused_pow2
     pl.dense_c0 = 0;
@@ -428,6 +437,7 @@ void ensure_device(sgx_plan &pl) {
     pl.d_col = upload_int(pl.tab.col);
     pl.d_wofs = upload_int(pl.wofs);
     pl.d_lane_rows = upload_int(pl.lane_rows);
+    pl.d_row_desc = upload_int(pl.row_desc);
     pl.d_lane_w = upload(pl.lane_w, pl.f64);
     pl.d_dense_t = upload(pl.dense_t, pl.f64);
     pl.d_val = upload(pl.tab.val, pl.f64);
@@ -456,6 +466,7 @@ void fill_params(const sgx_plan &pl, KParams &p) {
     p.mapping = d.mapping;
     p.n_bins = static_cast<int>(pl.tab.n_bins);
     p.rows_contig = pl.rows_contig ? 1 : 0;
+    p.row_desc = reinterpret_cast<const int4 *>(pl.d_row_desc);
     p.lane_rows = reinterpret_cast<const int4 *>(pl.d_lane_rows);
     p.lane_w = pl.d_lane_w;
     p.n_lane_slots = static_cast<int>(pl.lane_rows.size() / 4);
