@@ -32,12 +32,12 @@ __device__ __forceinline__ void epilogue_from_power(const KParams &p, T *__restr
         // chromagram() (src/chroma.rs:487-503): magnitude tile -> 12 dense rows in ascending bin order (:384-394) ->
         // per-frame normalisation (:406-453). scratch holds the un-normalised rows [f * ts + c].
         for (int idx = tid; idx < p.out_len * FT; idx += nthr) {
-            const int f = idx / p.out_len, k = idx - f * p.out_len;
+            const int f = fd_div(idx, p.fd_out_len), k = idx - f * p.out_len;
             if (f < nf) P[f * ts + k] = t_sqrt(P[f * ts + k]);
         }
         __syncthreads();
         for (int idx = tid; idx < 12 * FT; idx += nthr) {
-            const int row = idx / FT, f = idx - row * FT;
+            const int row = fd_div(idx, p.fd_FT), f = idx - row * FT;
             if (f >= nf) continue;
             const T *w = static_cast<const T *>(p.dense) + static_cast<long long>(row) * p.out_len;
             const T *pf = P + f * ts;
@@ -60,7 +60,7 @@ __device__ __forceinline__ void epilogue_from_power(const KParams &p, T *__restr
     // rows x frames, frames fastest
     const int total = p.n_bins * FT;
     for (int idx = tid; idx < total; idx += nthr) {
-        const int row = idx / FT;
+        const int row = fd_div(idx, p.fd_FT);
         const int f = idx - row * FT;
         if (f >= nf) continue;
         const T *pf = P + f * ts;
@@ -97,7 +97,7 @@ __device__ __forceinline__ void epilogue_from_power(const KParams &p, T *__restr
     const T *lift = static_cast<const T *>(p.lifter);
     const int rows = p.n_mfcc - p.mfcc_row0;
     for (int idx = tid; idx < rows * FT; idx += nthr) {
-        const int r = idx / FT;
+        const int r = fd_div(idx, p.fd_FT);
         const int f = idx - r * FT;
         if (f >= nf) continue;
         const int c = r + p.mfcc_row0;
@@ -118,7 +118,7 @@ __device__ __forceinline__ void epilogue_complex(const KParams &p, const typenam
     C *out = static_cast<C *>(p.out) + static_cast<long long>(clip) * p.out_clip_stride + (f0 - p.out_frame_origin);
     const int total = p.out_len * FT;
     for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        const int k = idx / FT;
+        const int k = fd_div(idx, p.fd_FT);
         const int f = idx - k * FT;
         if (f >= nf) continue;
         out[static_cast<long long>(k) * p.out_row_stride + f] = S[f * p.frame_stride + k];

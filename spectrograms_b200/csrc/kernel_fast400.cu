@@ -351,6 +351,7 @@ cudaError_t launch_fast400(const KParams &p, const float *window_f32, bool spars
     F400Params P;
     P.k = p;
     P.k.FT = f400::kFT;
+    P.k.fd_FT = make_fastdiv(static_cast<unsigned>(f400::kFT));
     P.k.tiles_per_clip = static_cast<int>((p.frames_todo + f400::kFT - 1) / f400::kFT);
     for (int i = 0; i < f400::kN; ++i) P.c.win[i] = window_f32[i];
     const long double pi = 3.14159265358979323846264338327950288L;

@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(256) k_r2c_fused_generic(const __grid_constant
 
     // ---- 1. gather / pad / window / pack
     for (int idx = tid; idx < nf * L; idx += nthr) {
-        const int f = idx / L;
+        const int f = fd_div(idx, p.fd_L);
         const int n = idx - f * L;
         const long long base = (f0 + f) * p.hop - p.pad;
         C z;
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256) k_r2c_fused_generic(const __grid_constant
         C *S = outb;
         const C *post = static_cast<const C *>(p.post);
         for (int idx = tid; idx < nf * p.out_len; idx += nthr) {
-            const int f = idx / p.out_len;
+            const int f = fd_div(idx, p.fd_out_len);
             const int k = idx - f * p.out_len;
             const C *zf = Z + f * FS;
             C X;
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(256) k_r2c_fused_generic(const __grid_constant
         const C *post = static_cast<const C *>(p.post);
         const int ts = p.tile_stride;
         for (int idx = tid; idx < nf * p.out_len; idx += nthr) {
-            const int f = idx / p.out_len;
+            const int f = fd_div(idx, p.fd_out_len);
             const int k = idx - f * p.out_len;
             const C *zf = Z + f * FS;
             C X;

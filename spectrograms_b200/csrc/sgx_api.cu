@@ -462,6 +462,17 @@ void fill_params(const sgx_plan &pl, KParams &p) {
     p.even = pl.even;
     p.n_stages = static_cast<int>(pl.radix.size());
     for (size_t i = 0; i < pl.radix.size(); ++i) p.radix[i] = pl.radix[i];
+    {
+        unsigned cur = 1;
+        for (size_t i = 0; i < pl.radix.size() && i < static_cast<size_t>(kFdStages); ++i) {
+            p.fd_stage_B[i] = make_fastdiv(static_cast<unsigned>(pl.L / pl.radix[i]));
+            p.fd_stage_cur[i] = make_fastdiv(cur);
+            cur *= static_cast<unsigned>(pl.radix[i]);
+        }
+        p.fd_L = make_fastdiv(static_cast<unsigned>(pl.L));
+        p.fd_out_len = make_fastdiv(static_cast<unsigned>(pl.tab.out_len));
+        p.fd_r0 = make_fastdiv(pl.radix.empty() ? 1u : static_cast<unsigned>(pl.radix[0]));
+    }
     p.window = pl.d_window; p.tw = pl.d_tw; p.post = pl.d_post;
     p.mapping = d.mapping;
     p.n_bins = static_cast<int>(pl.tab.n_bins);
@@ -484,6 +495,7 @@ void fill_params(const sgx_plan &pl, KParams &p) {
     p.dct = pl.d_dct; p.lifter = pl.d_lifter;
     p.dct_folded = pl.d_dct_folded; p.dct_tasks = pl.dct_tasks;
     p.FT = pl.FT; p.buf_elems = pl.buf_elems; p.frame_stride = pl.frame_stride; p.tile_stride = pl.tile_stride;
+    p.fd_FT = make_fastdiv(static_cast<unsigned>(pl.FT));
 }
 
 // run frames [frame_begin, frame_begin+frames_todo) of n_clips device-resident clips
@@ -520,6 +532,7 @@ void run_device(sgx_plan &pl, const void *d_samples, size_t n_clips, size_t n_sa
             ck(launch_fast400(q, pl.window_f32.data(), pl.fast400_sparse, pl.sparse_quads, pl.sparse_weights, pl.sm_count, stream), "kernel launch (r2c_fused_n400)");
         } else if (pl.pow2 && !pl.force_generic) {
             q.FT = pl.pow2_ft;
+            q.fd_FT = make_fastdiv(static_cast<unsigned>(q.FT));
             q.frame_stride = pl.pow2_frame_stride;
             q.tile_stride = pl.pow2_tile_stride;
             // vector loads of (x[2n], x[2n+1]) pairs need pair-aligned addresses: aligned base, even stride, even hop and pad
@@ -877,6 +890,7 @@ sgx_status sgx_plan_compute_binaural(sgx_plan *plan, sgx_binaural_cue cue, const
                 q.out_clip_stride = static_cast<long long>(cue_elems);
                 q.out_frame_origin = 0;
                 q.FT = pl.pow2_ft;
+                q.fd_FT = make_fastdiv(static_cast<unsigned>(q.FT));
                 q.frame_stride = pl.pow2_frame_stride;
                 q.tile_stride = pl.pow2_tile_stride;
                 const int hf = pl.pow2_ft / 2;
@@ -1048,6 +1062,7 @@ void run_inverse(sgx_plan &pl, const void *d_stft, size_t nc, size_t n_frames, v
     // the register-radix inverse stores (x[2m], x[2m+1]) pairs: the destination must be pair aligned
     if (pl.pow2 && !pl.force_generic && reinterpret_cast<uintptr_t>(d_frames_out) % (2 * pl.esize) == 0) {
         p.FT = pl.pow2_ft;
+        p.fd_FT = make_fastdiv(static_cast<unsigned>(p.FT));
         p.frame_stride = pl.pow2_frame_stride;
         p.tile_stride = pl.pow2_tile_stride;
         p.tiles_per_clip = static_cast<int>((n_frames + p.FT - 1) / p.FT);

@@ -23,12 +23,14 @@ __device__ __forceinline__ typename Cplx<T>::type *stockham_stages(const KParams
     for (int s = 0; s < p.n_stages; ++s) {
         const int r = p.radix[s];
         const int B = L / r;           // butterflies per frame
-        const int m = B / cur;
+        const int m = B / cur;                         // uniform: once per stage
+        const bool fast = s < kFdStages;
+        const FastDiv fdB = p.fd_stage_B[fast ? s : 0], fdc = p.fd_stage_cur[fast ? s : 0];
         if (r <= 5) {
             for (int idx = tid; idx < nf * B; idx += nthr) {
-                const int f = idx / B;
+                const int f = fast ? fd_div(idx, fdB) : idx / B;
                 const int b = idx - f * B;
-                const int i = b / cur;
+                const int i = fast ? fd_div(b, fdc) : b / cur;
                 const int q = b - i * cur;
                 const C *src = in + f * FS + b;
                 C *dst = outb + f * FS + i * r * cur + q;
@@ -83,12 +85,12 @@ __device__ __forceinline__ typename Cplx<T>::type *stockham_stages(const KParams
         } else {
             // cofactor stage: out[i][k][q] = sum_j in[j][i][q] * W_L^{ j * (q*m + k*(L/r)) }, one output per thread
             for (int idx = tid; idx < nf * L; idx += nthr) {
-                const int f = idx / L;
+                const int f = fd_div(idx, p.fd_L);
                 const int o = idx - f * L;        // o = (i*r + k)*cur + q
-                const int q = o % cur;
-                const int ik = o / cur;
-                const int k = ik % r;
-                const int i = ik / r;
+                const int ik = fd_div(o, fdc);            // stage 0 always has a precomputed divisor
+                const int q = o - ik * cur;
+                const int i = fd_div(ik, p.fd_r0);       // a cofactor stage is always stage 0
+                const int k = ik - i * r;
                 const int b = i * cur + q;
                 const C *src = in + f * FS + b;
                 const int step = static_cast<int>((static_cast<long long>(q) * m + static_cast<long long>(k) * B) % L);
