@@ -32,3 +32,13 @@ def test_cpp_host_layer_compute_checks(tmp_path):
     r = subprocess.run([_build(tmp_path)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "CPP_HOST_OK host+gpu" in r.stdout
+
+
+def test_fast_divisors_match_integer_division(tmp_path):
+    """fastdiv.hpp make_fastdiv / fd_div (the generic family's index math) against exact division, on the host."""
+    exe = str(tmp_path / "test_fastdiv")
+    src = os.path.join(ROOT, "tests", "cpp", "test_fastdiv.cpp")
+    r = subprocess.run(["g++", "-std=c++17", "-O2", src, "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "FASTDIV_OK" in r.stdout, r.stdout + r.stderr
