@@ -458,11 +458,25 @@ __global__ void __launch_bounds__(FT *(M / 16), (sizeof(T) == 4 ? 4 : 2) * 256 /
         __syncthreads();
         // the scaling sits in the (rolled) store loop: one inlined sqrt / log instead of 17 copies -- the f64 square
         // root is long enough that the unrolled form ran out of instruction cache
-        T *out = static_cast<T *>(p.out) + static_cast<long long>(clip) * p.out_clip_stride + (f0 - p.out_frame_origin);
+        // A thread keeps its frame f = tid % FT and walks bins k = tid / FT, += NT / FT: pointer increments instead of a
+        // 64-bit multiply per element, and the amplitude mode is resolved outside the loop.
+        constexpr int NT = FT * TPF, KSTEP = NT / FT;
+        const int f = tid % FT, k0 = tid / FT;
+        if (f < nf) {
+            T *o = static_cast<T *>(p.out) + static_cast<long long>(clip) * p.out_clip_stride + (f0 - p.out_frame_origin) +
+                   static_cast<long long>(k0) * p.out_row_stride + f;
+            const long long ostep = static_cast<long long>(KSTEP) * p.out_row_stride;
+            const T *src = P + f * PS + k0;
+            if (p.amp == SGX_AMP_MAGNITUDE && !p.apply_db) {
 #pragma unroll 2
-        for (int idx = tid; idx < (M + 1) * FT; idx += FT * TPF) {
-            const int k = idx / FT, f = idx % FT;
-            if (f < nf) out[static_cast<long long>(k) * p.out_row_stride + f] = amp_scale<T>(P[f * PS + k], p.amp, p.apply_db, eps);
+                for (int k = k0; k <= M; k += KSTEP, o += ostep, src += KSTEP) *o = t_sqrt(*src);
+            } else if (p.amp != SGX_AMP_MAGNITUDE && !p.apply_db) {
+#pragma unroll 4
+                for (int k = k0; k <= M; k += KSTEP, o += ostep, src += KSTEP) *o = *src;
+            } else {
+#pragma unroll 2
+                for (int k = k0; k <= M; k += KSTEP, o += ostep, src += KSTEP) *o = amp_scale<T>(*src, p.amp, p.apply_db, eps);
+            }
         }
         return;
     }
