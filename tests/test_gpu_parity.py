@@ -396,3 +396,45 @@ def test_parseval_property_full_size_linear_power():
     rhs = 400.0 * (frames ** 2).sum(dim=2)
     assert tuple(pw.shape) == (64, 201, 3001)
     assert float(((lhs - rhs).abs() / rhs).max()) < 1e-11
+
+
+@pytest.mark.parametrize("name", ["c3_music", "c4_mfcc", "c5_multichannel"])
+def test_full_size_other_configs_batch_properties(name):
+    """configs[2] (per-GPU shard: 512 x 30 s @22.05 kHz, 2048/512, 128 mels dB f32), configs[3] (per-GPU shard: 1024 x 10 s,
+    40 MFCC f32) and configs[4] (64 ch x 60 s @48 kHz, 4096/1024, magnitude f64) at full size: clips are independent (a clip
+    computed alone is bit-identical to its slot in the batch), the run is deterministic, the values are finite, and
+    sampled clips match the oracle at the north_star tolerances."""
+    torch = _torch()
+    g = torch.Generator(device="cuda").manual_seed(2)
+    if name == "c3_music":
+        n_clips, n, sr, dt = 512, 661500, 22050.0, torch.float32
+        plan = sg.SpectrogramPlanner().mel_plan(P(2048, 512, sr=sr), sg.MelParams(128, 0.0, sr / 2), sg.LogParams(-80.0), "db", "float32")
+        ref = oracle.Plan(odesc("float64", 2048, 512, sr=sr, mapping="mel", n_bands=128, f_min=0.0, f_max=sr / 2, amp="db", floor_db=-80.0))
+        shape, check = (512, 128, 1292), lambda a, r: np.abs(a - r).max() <= TOL_DB
+    elif name == "c4_mfcc":
+        n_clips, n, sr, dt = 1024, 160000, 16000.0, torch.float32
+        plan = sg.MfccPlan(sg.StftParams(400, 160, "hanning", True), sr, 128, sg.MfccParams(40), "float32")
+        ref = None
+        shape, check = (1024, 40, 1001), None
+    else:
+        n_clips, n, sr, dt = 64, 2880000, 48000.0, torch.float64
+        plan = sg.SpectrogramPlanner().linear_plan(P(4096, 1024, sr=sr), None, "magnitude", "float64")
+        ref = oracle.Plan(odesc("float64", 4096, 1024, sr=sr, amp="magnitude"))
+        shape, check = (64, 2049, 2813), lambda a, r: rel_l2(a, r) <= TOL_F64
+    clips = torch.randn((n_clips, n), generator=g, device="cuda", dtype=dt)
+    out = plan.compute_batch(clips)
+    assert tuple(out.shape) == shape and bool(torch.isfinite(out).all())
+    assert torch.equal(out, plan.compute_batch(clips))                                 # deterministic
+    for i in (0, n_clips // 2, n_clips - 1):
+        alone = plan.compute(clips[i]).data
+        assert torch.equal(alone, out[i])                                              # clips are independent
+    if ref is not None:
+        i = n_clips - 1
+        r = ref.compute(clips[i].cpu().numpy().astype(np.float64))
+        assert check(out[i].cpu().numpy().astype(np.float64), r)
+    else:
+        x = clips[7].cpu().numpy()
+        want = oracle.compute_batch(oracle.Desc(dtype="f32", n_fft=400, hop=160, sample_rate=sr, mapping="mel", n_bands=128, f_min=0.0,
+                                                f_max=sr / 2, amp="db", floor_db=-80.0), x[None], 1,
+                                    mfcc=dict(n_mfcc=40, include_c0=True, lifter=22, faithful=False))[0]
+        assert rel_l2(out[7].cpu().numpy(), want) <= 2e-5                               # f32 oracle vs f32 kernel on noise
