@@ -248,6 +248,16 @@ class _NativePlan:
             raise InvalidInputError("torch inputs must be CUDA tensors (use NumPy arrays for host data)")
         return torch
 
+    @staticmethod
+    def _check_out_dims(shape, n_clips: int) -> None:
+        """The C ABI sees only the trailing (rows, frames) of ``out``; the clip dimension is checked here so that a
+        short or 2-D buffer can never be overrun: (n_clips, rows, frames), or (rows, frames) for a single clip."""
+        if len(shape) == 3:
+            if shape[0] != n_clips:
+                raise DimensionMismatchError(f"Dimension mismatch: expected {n_clips}, got {shape[0]}", n_clips, int(shape[0]))
+        elif not (len(shape) == 2 and n_clips == 1):
+            raise InvalidInputError("out must be (n_clips, rows, n_frames), or (rows, n_frames) for a single clip")
+
     def compute_batch(self, clips, out=None):
         """clips: (n_clips, n_samples). Returns / fills (n_clips, rows, n_frames)."""
         L = _native.lib()
@@ -261,8 +271,14 @@ class _NativePlan:
             rows, nf = self.output_shape(n_samples)
             if out is None:
                 out = torch.empty((n_clips, rows, nf), dtype=self._out_dtype(torch), device=clips.device)
-            elif not out.is_contiguous():
-                raise InvalidInputError("out must be contiguous")
+            else:
+                if not _is_torch(out) or not out.is_cuda or out.device != clips.device:
+                    raise InvalidInputError("out must be a CUDA tensor on the same device as the input")
+                if out.dtype != self._out_dtype(torch):
+                    raise InvalidInputError(f"out dtype {out.dtype} does not match the plan's output dtype {self._out_dtype(torch)}")
+                if not out.is_contiguous():
+                    raise InvalidInputError("out must be contiguous")
+                self._check_out_dims(tuple(out.shape), n_clips)
             orow, ocol = (out.shape[-2], out.shape[-1]) if out.dim() >= 2 else (0, 0)
             stream = torch.cuda.current_stream(clips.device).cuda_stream
             with torch.cuda.device(clips.device):
@@ -276,8 +292,12 @@ class _NativePlan:
         rows, nf = self.output_shape(n_samples)
         if out is None:
             out = np.empty((n_clips, rows, nf), dtype=self._out_dtype())
-        elif not isinstance(out, np.ndarray) or not out.flags.c_contiguous or out.dtype != self._out_dtype():
-            raise InvalidInputError(f"out must be a C-contiguous NumPy array of dtype {np.dtype(self._out_dtype())}")
+        else:
+            if not isinstance(out, np.ndarray) or not out.flags.c_contiguous or out.dtype != self._out_dtype():
+                raise InvalidInputError(f"out must be a C-contiguous NumPy array of dtype {np.dtype(self._out_dtype())}")
+            if not out.flags.writeable:
+                raise InvalidInputError("out must be writeable")
+            self._check_out_dims(out.shape, n_clips)
         orow, ocol = (out.shape[-2], out.shape[-1]) if out.ndim >= 2 else (0, 0)
         _native.check(L.sgx_plan_compute_batch(self._h, clips.ctypes.data, n_clips, n_samples, n_samples,
                                                out.ctypes.data, orow, ocol, 0, None))

@@ -242,3 +242,23 @@ def test_shard_range_partitions_clips():
             assert max(hi - lo for lo, hi in rs) == -(-n // w)
     with pytest.raises(ValueError):
         sg.shard_range(8, 8, 8)
+
+
+def test_compute_batch_rejects_out_buffers_it_could_overrun():
+    """the C ABI sees only (rows, frames) of ``out``; the clip dimension, rank and dtype are checked before."""
+    plan = sg.SpectrogramPlanner().mel_plan(sg.SpectrogramParams(sg.StftParams(400, 160), 16000.0), sg.MelParams(16, 0.0, 8000.0),
+                                            None, "power", "float32")
+    clips = np.zeros((3, 1600), dtype=np.float32)
+    rows, nf = plan.output_shape(1600)
+    with pytest.raises(sg.DimensionMismatchError):
+        plan.compute_batch(clips, out=np.empty((2, rows, nf), dtype=np.float32))       # fewer clips than the input
+    with pytest.raises(sg.InvalidInputError):
+        plan.compute_batch(clips, out=np.empty((rows, nf), dtype=np.float32))          # 2-D out with n_clips > 1
+    with pytest.raises(sg.InvalidInputError):
+        plan.compute_batch(clips, out=np.empty((3, rows, nf), dtype=np.float64))       # wrong dtype
+    with pytest.raises(sg.InvalidInputError):
+        plan.compute_batch(clips, out=np.empty((3 * rows * nf,), dtype=np.float32))    # 1-D
+    ro = np.empty((3, rows, nf), dtype=np.float32)
+    ro.setflags(write=False)
+    with pytest.raises(sg.InvalidInputError):
+        plan.compute_batch(clips, out=ro)
