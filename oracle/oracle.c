@@ -4,16 +4,27 @@
  * THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE. Only tests/, __graft_entry__.smoke() and bench.py's
  * cpu_baseline / --impl reference legs may load it. The product (spectrograms_b200/) never links or calls it.
  *
- * Parity pinning status: PARTIALLY PINNED. The reference crate cannot be compiled here (no cargo/rustc;
- * realfft 3.5.0 / rustfft 6.4.1 are un-vendored crates.io dependencies, Cargo.lock:920-922,1002-1004), and
- * the reference ships no golden vectors. The oracle is pinned against
+ * Parity pinning status: PINNED for the north_star path -- STFT, window, power / magnitude / dB, the mel, ERB and
+ * LogHz filterbanks and their spectrograms, the DCT-II / lifter and MFCC. The reference crate cannot be compiled here
+ * (no cargo/rustc; realfft 3.5.0 / rustfft 6.4.1 are un-vendored crates.io dependencies, Cargo.lock:920-922,1002-1004)
+ * and ships no golden vectors, so the pins are
  *   (1) every known-answer / shape / property assertion the reference's own tests make for this path
- *       (tests/golden/ + tests/test_oracle_*.py list them with file:line), and
- *   (2) outputs of the reference's own NumPy restatement python/examples/numpy_impls.py (stft, power,
- *       magnitude, dB, hann_window), imported from /root/reference by tests/golden/make_golden.py.
- * The mel/ERB/LogHz/MFCC/chroma/binaural numerics have no reference-side vectors (the inverse path is
- * checked against SciPy's pocketfft and by round trips): they are restated line by line and
- * cross-checked by an independent NumPy restatement (oracle/oracle_np.py); "parity unpinned" for those values.
+ *       (tests/test_oracle_pinning.py lists them with file:line);
+ *   (2) outputs of the reference's own NumPy restatement python/examples/numpy_impls.py, imported unmodified from
+ *       /root/reference by tests/golden/make_golden.py -> tests/golden/ref_numpy_impls.npz: stft, hann_window, power,
+ *       magnitude, dB, erb_centers + gammatone_response + erb_spectrogram (= src/erb.rs:266-402) and
+ *       log_frequency_matrix + logfreq_spectrogram (= src/spectrogram.rs:2438-2508);
+ *   (3) third-party implementations of the algorithms the crate names -> tests/golden/third_party_pins.npz:
+ *       torchaudio.functional.melscale_fbanks(mel_scale="slaney", norm=None|"slaney") for the librosa-style mel
+ *       filterbank (src/spectrogram.rs:2262-2432; exact 394 / 2018 non-zero pattern, weights to torchaudio's own f32
+ *       rounding) and scipy.fft.dct(type=2)/2 for dct_ii (src/mfcc.rs:278-292);
+ *   tests/test_reference_pins.py checks the oracle, the product's host tables AND (under -m gpu) the CUDA output
+ *   directly against (2) and (3).
+ * STILL UNPINNED ("parity unpinned"): the chroma filterbank and the binaural cues -- the reference ships no vectors, its
+ * NumPy chroma is a different (hard-assignment) algorithm and no third-party implementation is installed; they are
+ * restated line by line, cross-checked by oracle/oracle_np.py and by derived known answers. The inverse path is
+ * checked against SciPy's pocketfft irfft and by round trips. L1 / L2 mel norms and the Apple-TR35 ERB spacing are
+ * covered by the two-restatement cross-check only.
  *
  * All citations are relative to the reference checkout (src/spectrogram.rs unless a file is named).
  * Compile with -ffp-contract=off: the reference (rustc) never contracts a*b+c unless mul_add is written.
