@@ -158,6 +158,12 @@ size_t sgx_plan_last_launch_count(const sgx_plan *plan);
 /* Force the generic kernel family (1) or allow specialised kernels (0, default). Test hook. */
 sgx_status sgx_plan_force_generic(sgx_plan *plan, int force);
 
+/* TMEM / tcgen05 kernel variant of a family (r2c_fused_n400_tc: the FFT exchange lives in tensor memory and the filterbank
+ * projection -- FrequencyMapping::apply, src/spectrogram.rs:1822-1881 -- runs as 3xTF32 MMAs): -1 = automatic (default:
+ * used where it is measured faster, i.e. the dense ERB projection), 0 = never, 1 = whenever the plan supports it.
+ * Test / measurement hook. */
+sgx_status sgx_plan_set_tensor_cores(sgx_plan *plan, int enable);
+
 /*
  * The batched entry point: for c in 0..n_clips { plan.compute_into(&samples[c], &mut out[c]) }  (:414-477,
  * :1548-1580; the reference has no batch API -- batching is a user loop, src/lib.rs:228-235).

@@ -15,15 +15,10 @@
 // the window is copied once per CTA into shared memory (warp-uniform broadcast reads); the pass-2 twiddles are read from
 // the constant bank (kernel parameter) with warp-uniform indices.
 #include "epilogue.cuh"
-#include "fft400_core.cuh"
+#include "fast400_common.cuh"
 #include "launch.hpp"
 
 namespace sgx {
-
-struct F400Params {
-    KParams k;
-    f400::Consts c;
-};
 
 namespace {
 
@@ -35,41 +30,6 @@ constexpr int kBufWords = kPWords > kSigWords ? kPWords : kSigWords;
 constexpr size_t kFixedSmemBytes = sizeof(float) * (2 * kBufWords + kYWords);
 constexpr int kPrefetchSplit = 40 * 32;       // float2 units of a tile (2680) prefetched by warp 10
 constexpr size_t kSmemBudget = (233472 - 2 * 1024) / 2;      // two CTAs per SM: 228 KB per SM, 1 KB reserved per CTA
-
-__device__ __forceinline__ void cp_async8(float *dst_smem, const float *src, int src_bytes) {
-    const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(dst_smem));
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit_wait_all() {
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
-}
-
-// stage one tile's samples [s0, s0 + 5360) of a clip into a padded signal buffer
-// float2 units j = first, first + step, ... < last of the tile are handled by the calling thread
-__device__ __forceinline__ void load_tile(float *sig, const float *x, long long s0, long long n, bool vec_ok, int first, int step,
-                                          int last) {
-    if (vec_ok && s0 >= 0 && s0 + kTileSamples <= n) {
-        // interior tile (all but the first / last tile of a clip): no bounds logic at all
-        const float *src = x + s0;
-#pragma unroll 4
-        for (int j = first; j < last; j += step) cp_async8(sig + 2 * j + 2 * (j / (kHop / 2)), src + 2 * j, 8);
-    } else if (vec_ok) {
-        for (int j = first; j < last; j += step) {
-            const long long s = s0 + 2 * j;
-            const long long avail = n - s;                // samples available from s on
-            const int bytes = (s < 0 || avail <= 0) ? 0 : (avail >= 2 ? 8 : 4);
-            cp_async8(sig + 2 * j + 2 * (j / (kHop / 2)), bytes ? x + s : x, bytes);
-        }
-    } else {
-        for (int j = first; j < last; j += step) {
-            const long long s = s0 + 2 * j;
-            float2 v;
-            v.x = (s >= 0 && s < n) ? __ldg(x + s) : 0.f;
-            v.y = (s + 1 >= 0 && s + 1 < n) ? __ldg(x + s + 1) : 0.f;
-            *reinterpret_cast<float2 *>(sig + 2 * j + 2 * (j / (kHop / 2))) = v;
-        }
-    }
-}
 
 // Interior-tile prefetch by ONE warp, hop block by hop block: block b (160 samples = 80 float2 units) goes to word 162 b,
 // so source and destination advance by constants and each block costs three cp.async per lane (the third on 16 lanes).
@@ -84,13 +44,6 @@ __device__ __forceinline__ void prefetch_tile_by_warp(float *sig, const float *s
     }
     cp_async8(d, s, 8);                                                                   // last block: 80 samples
     if (lane < 8) cp_async8(d + 64, s + 64, 8);
-}
-
-// lg2.approx.ftz: the argument is clamped to eps > 0 first, so the denormal fix-up of __log2f is dead weight
-__device__ __forceinline__ float fast_lg2(float v) {
-    float r;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
-    return r;
 }
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
@@ -113,13 +66,6 @@ __device__ __forceinline__ float4 lds_v4(unsigned a) {
 // on the host, so a quad is nearly homogeneous; the per-lane predicate e < cnt keeps the exact reference arithmetic:
 // ascending columns, acc += T(w) * x with separate rounding (SparseMatrix::multiply_vec, src/spectrogram.rs:102-117).
 // AMP: 0 power, 1 magnitude, 2 dB.
-template <int AMP>
-__device__ __forceinline__ float finish_value(float acc, float eps) {
-    if (AMP == 1) acc = sqrtf(acc);
-    if (AMP == 2) acc = 3.01029995663981195f * fast_lg2(fmaxf(acc, eps));
-    return acc;
-}
-
 // TO_SMEM: instead of storing to global memory, leave the scaled rows in a shared tile mtile[row][32] (same permuted
 // frame order as the power tile) for the fused DCT.
 template <int AMP, bool TO_SMEM, bool FULL>
@@ -353,15 +299,7 @@ cudaError_t launch_fast400(const KParams &p, const float *window_f32, bool spars
     P.k.FT = f400::kFT;
     P.k.fd_FT = make_fastdiv(static_cast<unsigned>(f400::kFT));
     P.k.tiles_per_clip = static_cast<int>((p.frames_todo + f400::kFT - 1) / f400::kFT);
-    for (int i = 0; i < f400::kN; ++i) P.c.win[i] = window_f32[i];
-    const long double pi = 3.14159265358979323846264338327950288L;
-    for (int k1 = 0; k1 <= 10; ++k1)
-        for (int n2 = 0; n2 < 20; ++n2) {
-            const long double a = -2.0L * pi * static_cast<long double>((n2 * k1) % 400) / 400.0L;
-            const double s = (k1 == 0 || k1 == 10) ? 1.0 : 0.5;
-            P.c.tw2[k1][n2] = make_float2(static_cast<float>(s * static_cast<double>(cosl(a))),
-                                          static_cast<float>(s * static_cast<double>(sinl(a))));
-        }
+    fast400_fill_consts(P.c, window_f32);
     const long long total = static_cast<long long>(p.n_clips) * P.k.tiles_per_clip;
     if (total <= 0) return cudaSuccess;
     const long long grid = std::min<long long>(total, 2LL * sm_count);     // persistent: 2 CTAs per SM

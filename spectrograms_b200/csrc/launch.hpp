@@ -24,6 +24,16 @@ bool fast400_sparse_fits(int n_quads, int padded_weights);
 int fast400_max_scratch_rows();
 int fast400_warps();
 
+// r2c_fused_n400_tc: the same family with TMEM as the exchange medium and the filterbank on tcgen05 (kernel_n400_tc.cu).
+// p.sched points at the device copy of the step blob built by the host (sgx_api.cu: build_tc_blob):
+//   int n_steps, n_rounds, round_start[n_rounds + 1], pad to 4 ints; int4 {A column, D column, byte offset of the step's B
+//   tiles, accumulate | N << 8}[n_steps]; float B[b_floats] (per step N rows x 8 bins as K-major core matrices: hi tile,
+//   then lo tile; N = 16 or 64).
+cudaError_t launch_fast400_tc(const KParams &p, const float *window_f32, int n_steps, int n_rounds, size_t b_floats, int sm_count,
+                              cudaStream_t stream);
+size_t fast400_tc_smem_bytes(int n_steps, int n_rounds, size_t b_floats);
+bool fast400_tc_fits(int n_steps, int n_rounds, size_t b_floats);
+
 // r2c_fused_pow2: n_fft = 256 .. 8192 (powers of two), f32 / f64 (kernel_pow2.cu). p.FT, p.frame_stride, p.tile_stride and
 // p.tiles_per_clip must be set from the helpers below; p.vec_ok is the "vector loads allowed" flag.
 bool pow2_supported(size_t n_fft);

@@ -143,6 +143,12 @@ struct sgx_plan {
     int pow2_ft = 1, pow2_frame_stride = 0, pow2_tile_stride = 0;
     size_t pow2_smem = 0;
     bool fast400_sparse = false;     // ... with the shared-memory sparse table
+    bool fast400_tc = false;         // ... on the TMEM / tcgen05 kernel (r2c_fused_n400_tc)
+    int tc_mode = -1;                // sgx_plan_set_tensor_cores: -1 auto (dense mappings only), 0 never, 1 whenever available
+    std::vector<int> tc_blob;        // step blob of r2c_fused_n400_tc (launch.hpp)
+    int tc_steps = 0, tc_rounds = 0;
+    size_t tc_b_floats = 0;
+    int *d_tc_blob = nullptr;
     int sparse_quads = 0, sparse_weights = 0;
     bool rows_contig = false;        // CSR rows have consecutive columns
     std::vector<int> row_desc;       // contiguous CSR rows: int4 {e0, cnt, c0, 0} per row
@@ -171,6 +177,7 @@ struct sgx_plan {
         if (d_row_ptr) cudaFree(d_row_ptr);
         if (d_col) cudaFree(d_col);
         if (d_wofs) cudaFree(d_wofs);
+        if (d_tc_blob) cudaFree(d_tc_blob);
         if (d_lane_rows) cudaFree(d_lane_rows);
         if (d_row_desc) cudaFree(d_row_desc);
         if (d_lane_w) cudaFree(d_lane_w);
@@ -258,6 +265,109 @@ void build_lane_rows(sgx_plan &pl) {
                     dense ? pl.tab.dense[static_cast<size_t>(r) * ol + i] : pl.tab.val[pl.tab.row_ptr[r] + i];
         }
     }
+}
+
+// r2c_fused_n400_tc is measured slower than the CUDA-core kernel for the banded mel / loghz filterbanks (2.1 ms against
+// 1.5 ms per configs[1] step: ~80 MMAs of ~125 cycles each per 128 frames) and faster for the dense ERB projection, whose
+// cost on CUDA cores grows with n_filters x 201 while the MMA count does not. Auto therefore picks it for ERB only.
+bool use_tc(const sgx_plan &pl) {
+    if (!pl.fast400 || !pl.fast400_tc || pl.force_generic || pl.tc_mode == 0) return false;
+    return pl.tc_mode == 1 || pl.desc.mapping == SGX_MAP_ERB;
+}
+
+// Step blob of r2c_fused_n400_tc: the filterbank as the B operand of tcgen05.mma. Rows are taken 16 at a time (one MMA
+// block, N = 16) and 64 at a time per round (the D columns); for every block only the 8-bin K steps between its first and
+// last non-zero column are emitted (mel / loghz rows are banded; a dense ERB block spans all 26 steps). Each step carries
+// its weights as two K-major SWIZZLE_NONE tiles of 16 rows x 8 bins -- T::from_f64(w) split into a TF32-exact hi part and
+// the f32 remainder -- laid out as 8 x 16-byte core matrices: float index (n / 8) * 64 + (k / 4) * 32 + (n % 8) * 4 + k % 4.
+void build_tc_blob(sgx_plan &pl) {
+    pl.tc_blob.clear();
+    pl.tc_steps = pl.tc_rounds = 0;
+    const sgx_plan_desc &d = pl.desc;
+    const bool csr = d.mapping == SGX_MAP_MEL || d.mapping == SGX_MAP_LOGHZ;
+    const bool dense = d.mapping == SGX_MAP_ERB;
+    if (!pl.fast400 || !(csr || dense) || d.output != SGX_OUT_SPECTROGRAM) return;
+    const size_t nb = pl.tab.n_bins, ol = pl.tab.out_len;
+    auto weight = [&](size_t r, size_t k) -> double {
+        if (r >= nb || k >= ol) return 0.0;
+        if (dense) return pl.tab.dense[r * ol + k];
+        for (int e = pl.tab.row_ptr[r]; e < pl.tab.row_ptr[r + 1]; ++e)
+            if (static_cast<size_t>(pl.tab.col[e]) == k) return pl.tab.val[e];
+        return 0.0;
+    };
+    const int n_rounds = static_cast<int>((nb + 63) / 64);
+    std::vector<int> round_start(1, 0), steps;
+    std::vector<float> bw;
+    // first / last 8-bin K step holding a non-zero weight (as T) of rows [r0, r1); an all-zero range still clears its D columns
+    auto k_range = [&](size_t r0, size_t r1, long &j0, long &j1) {
+        long cmin = -1, cmax = -1;
+        for (size_t r = r0; r < std::min(nb, r1); ++r)
+            for (size_t k = 0; k < ol; ++k)
+                if (static_cast<float>(weight(r, k)) != 0.0f) {
+                    if (cmin < 0 || static_cast<long>(k) < cmin) cmin = static_cast<long>(k);
+                    cmax = std::max(cmax, static_cast<long>(k));
+                }
+        if (cmin < 0) cmin = cmax = 0;
+        j0 = cmin / 8;
+        j1 = cmax / 8;
+    };
+    auto emit = [&](size_t r0, int N, int dcol, long j0, long j1) {
+        for (long j = j0; j <= j1; ++j) {
+            steps.insert(steps.end(), {static_cast<int>(8 * j), dcol, static_cast<int>(bw.size() * sizeof(float)), (j != j0 ? 1 : 0) | (N << 8)});
+            const size_t base = bw.size(), half = static_cast<size_t>(N) * 8;
+            bw.resize(base + 2 * half, 0.0f);
+            for (int n = 0; n < N; ++n)
+                for (int k = 0; k < 8; ++k) {
+                    const float w = static_cast<float>(weight(r0 + static_cast<size_t>(n), static_cast<size_t>(8 * j + k)));
+                    uint32_t bits;
+                    std::memcpy(&bits, &w, 4);
+                    bits &= 0xffffe000u;
+                    float hi;
+                    std::memcpy(&hi, &bits, 4);
+                    const size_t idx = static_cast<size_t>((n / 8) * 64 + (k / 4) * 32 + (n % 8) * 4 + (k % 4));
+                    bw[base + idx] = hi;
+                    bw[base + half + idx] = w - hi;
+                }
+        }
+    };
+    for (int round = 0; round < n_rounds; ++round) {
+        // an MMA costs ~125 cycles whatever its N (tools/ubench/mma_rate_probe.cu), so a round of 64 rows is issued either as
+        // four banded N = 16 blocks or as one N = 64 block over the union of their K ranges -- whichever needs fewer MMAs
+        const size_t r0 = static_cast<size_t>(round) * 64;
+        long u0, u1, banded = 0;
+        k_range(r0, r0 + 64, u0, u1);
+        for (int b = 0; b < 4 && r0 + 16 * static_cast<size_t>(b) < nb; ++b) {
+            long j0, j1;
+            k_range(r0 + 16 * static_cast<size_t>(b), r0 + 16 * static_cast<size_t>(b) + 16, j0, j1);
+            banded += j1 - j0 + 1;
+        }
+        if (u1 - u0 + 1 <= banded) {
+            emit(r0, 64, 0, u0, u1);
+        } else {
+            for (int b = 0; b < 4 && r0 + 16 * static_cast<size_t>(b) < nb; ++b) {
+                long j0, j1;
+                k_range(r0 + 16 * static_cast<size_t>(b), r0 + 16 * static_cast<size_t>(b) + 16, j0, j1);
+                emit(r0 + 16 * static_cast<size_t>(b), 16, 16 * b, j0, j1);
+            }
+        }
+        round_start.push_back(static_cast<int>(steps.size() / 4));
+    }
+    const size_t b_floats = bw.size();
+    const int n_steps = static_cast<int>(steps.size() / 4);
+    if (!fast400_tc_fits(n_steps, n_rounds, b_floats)) return;
+    std::vector<int> blob;
+    blob.push_back(n_steps);
+    blob.push_back(n_rounds);
+    blob.insert(blob.end(), round_start.begin(), round_start.end());
+    while (blob.size() % 4) blob.push_back(0);
+    blob.insert(blob.end(), steps.begin(), steps.end());
+    const size_t fofs = blob.size();
+    blob.resize(fofs + bw.size());
+    std::memcpy(blob.data() + fofs, bw.data(), bw.size() * sizeof(float));
+    pl.tc_blob = std::move(blob);
+    pl.tc_steps = n_steps;
+    pl.tc_rounds = n_rounds;
+    pl.tc_b_floats = b_floats;
 }
 
 void select_family(sgx_plan &pl) {
@@ -372,6 +482,8 @@ void select_family(sgx_plan &pl) {
     }
     build_lane_rows(pl);
     pl.fast400_sparse = pl.fast400 && csr && contiguous && fast400_sparse_fits(pl.sparse_quads, pl.sparse_weights);
+    build_tc_blob(pl);
+    pl.fast400_tc = pl.tc_steps > 0;
     pl.kernel_name = pl.fast400 ? "r2c_fused_n400" : pl.pow2 ? "r2c_fused_pow2" : "r2c_fused_generic";
     // folded DCT basis for the fused MFCC epilogue: B[c][n-1-i] = (-1)^c B[c][i] -> half basis, tasks of 4 coefficients of
     // one parity: [task][i < n/2][4], even-coefficient tasks first
@@ -436,6 +548,7 @@ void ensure_device(sgx_plan &pl) {
     pl.d_row_ptr = upload_int(pl.tab.row_ptr);
     pl.d_col = upload_int(pl.tab.col);
     pl.d_wofs = upload_int(pl.wofs);
+    pl.d_tc_blob = upload_int(pl.tc_blob);
     pl.d_lane_rows = upload_int(pl.lane_rows);
     pl.d_row_desc = upload_int(pl.row_desc);
     pl.d_lane_w = upload(pl.lane_w, pl.f64);
@@ -528,6 +641,12 @@ void run_device(sgx_plan &pl, const void *d_samples, size_t n_clips, size_t n_sa
         if (pl.fast400 && !pl.force_generic) {
             // 8-byte vector loads need an 8-byte aligned base and an even clip stride
             q.vec_ok = (reinterpret_cast<uintptr_t>(q.samples) % 8 == 0 && clip_stride % 2 == 0) ? 1 : 0;
+            if (use_tc(pl)) {
+                q.sched = pl.d_tc_blob;
+                ck(launch_fast400_tc(q, pl.window_f32.data(), pl.tc_steps, pl.tc_rounds, pl.tc_b_floats, pl.sm_count, stream), "kernel launch (r2c_fused_n400_tc)");
+                pl.last_launches += 1;
+                continue;
+            }
             q.sched = pl.fast400_sparse ? pl.d_wofs : nullptr;
             ck(launch_fast400(q, pl.window_f32.data(), pl.fast400_sparse, pl.sparse_quads, pl.sparse_weights, pl.sm_count, stream), "kernel launch (r2c_fused_n400)");
         } else if (pl.pow2 && !pl.force_generic) {
@@ -657,13 +776,22 @@ sgx_status sgx_plan_filterbank(const sgx_plan *plan, double *dense_out, size_t *
 
 const char *sgx_plan_kernel_name(const sgx_plan *plan) {
     if (!plan) return "";
-    return plan->force_generic ? "r2c_fused_generic" : plan->kernel_name.c_str();
+    if (plan->force_generic) return "r2c_fused_generic";
+    if (use_tc(*plan)) return "r2c_fused_n400_tc";
+    return plan->kernel_name.c_str();
 }
 size_t sgx_plan_last_launch_count(const sgx_plan *plan) { return plan ? plan->last_launches : 0; }
 sgx_status sgx_plan_force_generic(sgx_plan *plan, int force) {
     return guarded([&] {
         if (!plan) invalid("null plan");
         plan->force_generic = force != 0;
+    });
+}
+
+sgx_status sgx_plan_set_tensor_cores(sgx_plan *plan, int enable) {
+    return guarded([&] {
+        if (!plan) invalid("null plan");
+        plan->tc_mode = enable < 0 ? -1 : (enable != 0 ? 1 : 0);
     });
 }
 

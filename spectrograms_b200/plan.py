@@ -228,6 +228,11 @@ class _NativePlan:
     def force_generic(self, force: bool = True) -> None:
         _native.check(_native.lib().sgx_plan_force_generic(self._h, int(force)))
 
+    def set_tensor_cores(self, enable=True) -> None:
+        """TMEM + tcgen05 kernel variant of the plan's family: True = whenever supported, False = never, None = automatic
+        (the default: where it is measured faster). Test and measurement hook."""
+        _native.check(_native.lib().sgx_plan_set_tensor_cores(self._h, -1 if enable is None else int(bool(enable))))
+
     # -- compute
     def _out_dtype(self, torch_mod=None):
         cplx = self.output == _OUT_STFT
@@ -438,6 +443,7 @@ class SpectrogramPlan:
     def kernel_name(self) -> str: return self._n.kernel_name()
     def last_launch_count(self) -> int: return self._n.last_launch_count()
     def force_generic(self, force: bool = True) -> None: self._n.force_generic(force)
+    def set_tensor_cores(self, enable=True) -> None: self._n.set_tensor_cores(enable)
 
 
 class StftPlan:
@@ -483,6 +489,7 @@ class StftPlan:
     def kernel_name(self) -> str: return self._n.kernel_name()
     def last_launch_count(self) -> int: return self._n.last_launch_count()
     def force_generic(self, force: bool = True) -> None: self._n.force_generic(force)
+    def set_tensor_cores(self, enable=True) -> None: self._n.set_tensor_cores(enable)
 
 
 class MfccPlan:
@@ -509,6 +516,7 @@ class MfccPlan:
     def kernel_name(self) -> str: return self._n.kernel_name()
     def last_launch_count(self) -> int: return self._n.last_launch_count()
     def force_generic(self, force: bool = True) -> None: self._n.force_generic(force)
+    def set_tensor_cores(self, enable=True) -> None: self._n.set_tensor_cores(enable)
 
 
 class Chromagram:
@@ -557,6 +565,7 @@ class ChromaPlan:
     def kernel_name(self) -> str: return self._n.kernel_name()
     def last_launch_count(self) -> int: return self._n.last_launch_count()
     def force_generic(self, force: bool = True) -> None: self._n.force_generic(force)
+    def set_tensor_cores(self, enable=True) -> None: self._n.set_tensor_cores(enable)
 
 
 class SpectrogramPlanner:
