@@ -43,9 +43,17 @@ WORKLOADS = {
                    label="common ASR front end (not a BASELINE config): 1024 clips x 30 s @16 kHz, n_fft=512 hop=160 80 mels dB f32"),
     "chroma": dict(n_clips=512, n_samples=661500, sr=22050.0, n_fft=2048, hop=512, dtype="float32", kind="chroma",
                    label="SURVEY 8f rank 2, chromagram() on the configs[2] shard: 512 clips x 30 s @22.05 kHz, n_fft=2048 hop=512 -> 12 pitch classes (L2) f32"),
+    "erb400": dict(n_clips=1024, n_samples=480000, sr=16000.0, n_fft=400, hop=160, dtype="float32", kind="erb_db64",
+                   label="dense ERB projection on the configs[1] batch (not a BASELINE config): 1024 clips x 30 s @16 kHz, n_fft=400 hop=160 64 ERB bands dB f32"),
+    "erb512": dict(n_clips=1024, n_samples=480000, sr=16000.0, n_fft=512, hop=160, dtype="float32", kind="erb_db128",
+                   label="dense ERB-128 projection (not a BASELINE config): 1024 clips x 30 s @16 kHz, n_fft=512 hop=160 128 ERB bands dB f32"),
     "multichannel": dict(n_clips=64, n_samples=2880000, sr=48000.0, n_fft=4096, hop=1024, dtype="float64", kind="linear_mag",
                          label="configs[4] multichannel STFT magnitude: 64 ch x 60 s @48 kHz, n_fft=4096 hop=1024 f64"),
 }
+
+
+# total clips of the workload as BASELINE.json states it (the per-GPU shard above is total / 8): --scaling strong shards these
+BASELINE_TOTAL_CLIPS = {"whisper": 1024, "music": 4096, "mfcc": 8192, "multichannel": 64}
 
 
 def frames_of(w):
@@ -54,7 +62,7 @@ def frames_of(w):
 
 
 def out_rows(w):
-    return {"mel_db": 128, "mel_db80": 80, "mfcc": 40, "chroma": 12, "linear_mag": w["n_fft"] // 2 + 1}[w["kind"]]
+    return {"mel_db": 128, "mel_db80": 80, "mfcc": 40, "chroma": 12, "erb_db64": 64, "erb_db128": 128, "linear_mag": w["n_fft"] // 2 + 1}[w["kind"]]
 
 
 def algorithmic_bytes(w):
@@ -68,6 +76,8 @@ def make_plan(w, device=None):
     params = sg.SpectrogramParams(sg.StftParams(w["n_fft"], w["hop"], sg.WindowType.hanning(), True), w["sr"])
     if w["kind"] in ("mel_db", "mel_db80"):
         return sg.SpectrogramPlanner(device).mel_plan(params, sg.MelParams(out_rows(w), 0.0, w["sr"] / 2), sg.LogParams(-80.0), "db", w["dtype"])
+    if w["kind"] in ("erb_db64", "erb_db128"):
+        return sg.SpectrogramPlanner(device).erb_plan(params, sg.ErbParams(out_rows(w), 50.0, w["sr"] / 2), sg.LogParams(-80.0), "db", w["dtype"])
     if w["kind"] == "mfcc":
         return sg.MfccPlan(params.stft, w["sr"], 128, sg.MfccParams(40), w["dtype"], device)
     if w["kind"] == "chroma":
@@ -80,9 +90,39 @@ def oracle_desc(w):
     kw = dict(dtype="f32" if w["dtype"] == "float32" else "f64", n_fft=w["n_fft"], hop=w["hop"], sample_rate=w["sr"])
     if w["kind"] in ("mel_db", "mel_db80", "mfcc"):
         kw.update(mapping="mel", n_bands=80 if w["kind"] == "mel_db80" else 128, f_min=0.0, f_max=w["sr"] / 2, amp="db", floor_db=-80.0)
+    elif w["kind"] in ("erb_db64", "erb_db128"):
+        kw.update(mapping="erb", n_bands=out_rows(w), f_min=50.0, f_max=w["sr"] / 2, amp="db", floor_db=-80.0)
     else:
         kw.update(amp="magnitude")
     return oracle.Desc(**kw)
+
+
+def kernel_src_sha():
+    """sha1 over the CUDA sources: ties profiles/traffic.json to the code it was captured from."""
+    import glob
+    import hashlib
+    h = hashlib.sha1()
+    for f in sorted(glob.glob(os.path.join(ROOT, "spectrograms_b200", "csrc", "*"))):
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
+def config_of(w, world, scaling="weak", total_clips=None):
+    """The `config` object of the JSON line -- built by this one function for BOTH arms so that the driver's
+    same_config check compares like with like."""
+    es = 4 if w["dtype"] == "float32" else 8
+    c = {"workload": w["label"], "clips_per_gpu": w["n_clips"], "frames_per_clip": frames_of(w),
+         "sharding": f"clips x{world}, no collective",
+         "l2": f"inputs per step {w['n_clips'] * w['n_samples'] * es / 1e9:.2f} GB > 126 MB L2 (no flush needed)"}
+    if scaling == "strong":
+        c["total_clips"] = total_clips
+    return c
+
+
+PORT_NOTE = ("oracle/oracle.c, a scalar C restatement of the reference algorithm compiled -O3 -march=native -ffp-contract=off (auto-vectorised at best), one plan per thread "
+             "(the crate's documented scaling recipe). The Rust crate cannot be built here (no cargo; realfft 3.5.0 / rustfft 6.4.1 "
+             "un-vendored). Unlike rustfft the port has no hand-written SIMD (AVX2/AVX-512) butterflies and no cached-plan radix "
+             "specialisations: expect the real crate to be up to a few times faster per core, so every GPU/CPU ratio here is an upper bound")
 
 
 class ClockSampler:
@@ -172,15 +212,20 @@ def cpu_baseline(w, sample_clips, threads, faithful=True, reps=4):
     return reps * sample_clips * frames_of(w) / total, total
 
 
-def run_reference(args, w, rank, world):
-    """--impl reference: the reference's CPU algorithm (oracle port) with all host threads, bounded sample per step."""
+def run_reference(args, w, rank, world, scaling, total_clips):
+    """--impl reference: the reference's CPU algorithm (oracle port) with all host threads. Each step processes the SAME
+    batch the GPU arm's step does (all of this rank-0 box's clips: n_clips per GPU x N at weak scaling, the fixed total at
+    strong scaling) unless --ref-clips bounds it; frames/s of a CPU pass is size-independent, the config stays identical."""
     if rank != 0:
         return
     import oracle
     cores = os.cpu_count() or 1
-    sample = max(cores, min(w["n_clips"], args.ref_clips))
+    full = total_clips if scaling == "strong" else w["n_clips"]           # one GPU's batch: the CPU box has no N
+    sample = full if args.ref_clips <= 0 else max(cores, min(full, args.ref_clips))
     d = oracle_desc(w)
-    clips = np.random.default_rng(0).standard_normal((sample, w["n_samples"])).astype(np.float32 if w["dtype"] == "float32" else np.float64)
+    clips = np.random.default_rng(0).standard_normal((sample, w["n_samples"]), dtype=np.float32)
+    if w["dtype"] != "float32":
+        clips = clips.astype(np.float64)
     mf = dict(n_mfcc=40, include_c0=True, lifter=22, faithful=True) if w["kind"] == "mfcc" else None
     for _ in range(args.warmup):
         oracle.compute_batch(d, clips, cores, mfcc=mf)
@@ -192,11 +237,10 @@ def run_reference(args, w, rank, world):
     line = {
         "impl": "reference", "metric": "log-mel frames/sec", "value": value, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32" if w["dtype"] == "float32" else "f64", "data": "synthetic (seeded white noise)",
-        "config": {"workload": w["label"], "sample": f"{sample} clips per step"},
+        "scaling": scaling, "vs_baseline": None, "dtype": "f32" if w["dtype"] == "float32" else "f64", "data": "synthetic (seeded white noise)",
+        "config": config_of(w, world, scaling, total_clips),
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample} of {w['n_clips']} clips per step, one plan per thread (oracle/oracle.c restatement of the reference; "
-                                   "the Rust crate cannot be built here: no cargo, un-vendored realfft/rustfft)"},
+                         "sample": f"{sample} clips per step ({'the full per-GPU batch' if sample == full else 'bounded by --ref-clips'}); " + PORT_NOTE},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -213,7 +257,11 @@ def main():
     ap.add_argument("--clips", type=int, default=0, help="override clips per GPU (0 = the workload's size)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer end-to-end leg (0 = min(steps, 10))")
     ap.add_argument("--cpu-clips", type=int, default=256, help="bounded CPU-baseline sample (clips)")
-    ap.add_argument("--ref-clips", type=int, default=64, help="--impl reference: clips per step")
+    ap.add_argument("--ref-clips", type=int, default=0, help="--impl reference: clips per step (0 = the whole per-GPU batch, as the GPU arm)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every rank owns a full batch; strong: the workload's BASELINE total (music 4096, mfcc 8192 clips) is split over the ranks")
+    ap.add_argument("--no-strong-line", action="store_true", help="skip the extra strong-scaling configs[2] measurement under key strong_scaling")
+    ap.add_argument("--tensor-cores", default="auto", choices=["auto", "on", "off"], help="TMEM / tcgen05 kernel variant (sgx_plan_set_tensor_cores)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--generic", action="store_true", help="force the generic kernel family")
@@ -229,6 +277,13 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    total_clips = None
+    if args.scaling == "strong":
+        from spectrograms_b200.sharding import shard_range
+        total_clips = args.clips or BASELINE_TOTAL_CLIPS.get(args.workload, w["n_clips"])
+        lo, hi = shard_range(total_clips, rank if args.impl == "b200" else 0, world if args.impl == "b200" else 1)
+        w["n_clips"] = max(1, hi - lo)
+        w["label"] = w["label"].replace("per-GPU shard", "whole batch") + f" [strong scaling: {total_clips} clips over {world} GPUs]"
 
     if w["kind"] == "chroma":
         args.no_cpu = True          # the oracle has no batched chroma driver (parity: tests/test_chroma.py)
@@ -237,7 +292,7 @@ def main():
                 print(json.dumps({"impl": "reference", "unavailable": "no batched CPU driver for the chroma workload; it is not a BASELINE config"}))
             return
     if args.impl == "reference":
-        run_reference(args, w, rank, world)
+        run_reference(args, w, rank, world, args.scaling, total_clips)
         return
 
     import torch
@@ -256,6 +311,8 @@ def main():
     plan = make_plan(w, local_rank)
     if args.generic:
         plan.force_generic(True)
+    if args.tensor_cores != "auto" and hasattr(plan, "set_tensor_cores"):
+        plan.set_tensor_cores(args.tensor_cores == "on")
     n_frames = frames_of(w)
     rows = out_rows(w)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
@@ -287,7 +344,8 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms_max = float(t.item())
-    value = world * frames_per_step * args.steps / (total_ms_max * 1e-3)
+    job_frames_per_step = (total_clips if args.scaling == "strong" else world * w["n_clips"]) * n_frames
+    value = job_frames_per_step * args.steps / (total_ms_max * 1e-3)
 
     # ---- end to end through the C ABI with pinned host buffers (H2D + kernel + D2H inside the timed region)
     e2e = None
@@ -309,7 +367,7 @@ def main():
         te = torch.tensor([dt], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * frames_per_step * ksteps / float(te.item()), "unit": "frames/s",
+        e2e = {"value": job_frames_per_step * ksteps / float(te.item()), "unit": "frames/s",
                "h2d_bytes_per_step": w["n_clips"] * w["n_samples"] * es, "d2h_bytes_per_step": w["n_clips"] * rows * n_frames * es,
                "steps": ksteps, "ms_per_step": 1e3 * float(te.item()) / ksteps,
                "check": "host result equals device result: %s" % bool(torch.equal(h_out[:4].to(dev), out[:4]))}
@@ -334,6 +392,39 @@ def main():
         gather = {"clips_per_rank": n_g, "ms": float(gms.item()), "bytes_into_rank0": gbytes,
                   "GBps_into_rank0": gbytes / (float(gms.item()) * 1e-3) / 1e9, "rank0_block_intact": ok}
 
+    # ---- strong scaling of configs[2] as BASELINE states it (4096 music clips split over the N ranks), same run, own key
+    strong = None
+    if args.workload == "whisper" and args.scaling == "weak" and not args.no_strong_line and not args.generic and not args.clips:
+        from spectrograms_b200.sharding import shard_range
+        del clips, out
+        torch.cuda.empty_cache()
+        ws = dict(WORKLOADS["music"])
+        tot = BASELINE_TOTAL_CLIPS["music"]
+        lo, hi = shard_range(tot, rank, world)
+        ws["n_clips"] = hi - lo
+        splan = make_plan(ws, local_rank)
+        nfs = frames_of(ws)
+        sclips = torch.randn((ws["n_clips"], ws["n_samples"]), generator=g, device=dev, dtype=torch.float32)
+        sout = torch.empty((ws["n_clips"], out_rows(ws), nfs), device=dev, dtype=torch.float32)
+        ssteps = 5
+        for _ in range(3):
+            splan.compute_batch(sclips, sout)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(ssteps):
+            splan.compute_batch(sclips, sout)
+        s1.record()
+        barrier()
+        sms = torch.tensor([s0.elapsed_time(s1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(sms, op=dist.ReduceOp.MAX)
+        strong = {"workload": f"configs[2] music mel-dB: {tot} clips x 30 s @22.05 kHz, n_fft=2048 hop=512 128 mels dB f32, batch-sharded over {world} GPU(s)",
+                  "scaling": "strong", "total_clips": tot, "clips_this_rank": ws["n_clips"], "metric": "log-mel frames/sec",
+                  "value": tot * nfs * ssteps / (float(sms.item()) * 1e-3), "unit": "frames/s", "ms_per_step": float(sms.item()) / ssteps,
+                  "steps": ssteps, "warmup": 3, "kernel": splan.kernel_name(), "gpu_launches": splan.last_launch_count() * ssteps}
+        del sclips, sout
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -347,11 +438,18 @@ def main():
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     alg_bytes = algorithmic_bytes(w)
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
-    traffic = None
+    # DRAM bytes per launch from the committed `ncu --set full` capture of this kernel -- reported only while the kernel
+    # sources still hash to what was captured (profiles/traffic.json: src_sha), otherwise null (a stale number is worse)
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(args.workload, {}).get(plan.kernel_name())
+            ent = json.load(open(tpath)).get(args.workload, {}).get(plan.kernel_name())
+            if isinstance(ent, dict):
+                if ent.get("src_sha") == kernel_src_sha():
+                    traffic, traffic_src = ent["bytes"], ent.get("source")
+                else:
+                    traffic_src = "stale: kernel sources changed since the capture (%s)" % ent.get("source")
         except Exception:
             traffic = None
     # FP roofline next to the HBM one (the path is FFT arithmetic, not a copy): executed FP lane-operations per frame
@@ -370,7 +468,7 @@ def main():
                       "lane_ops_per_frame": ent["lane_ops_per_frame"], "peak_source": ent["peak_source"]}
         except Exception:
             fp = None
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "kernel": plan.kernel_name(), "kernel_ms": kernel_ms, "kernel_ms_median": float(np.median(per_launch_ms)) / max(1, launches_per_step),
                 "kernel_ms_best": float(np.min(per_launch_ms)) / max(1, launches_per_step),
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
@@ -383,17 +481,18 @@ def main():
         v, secs = cpu_baseline(w, sample, cores)
         cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
                "sample": f"4 passes over {sample} of {w['n_clips']} clips, one plan per thread ({secs:.2f} s wall, "
-                         f"{secs * cores:.0f} core-seconds)"}
+                         f"{secs * cores:.0f} core-seconds); " + PORT_NOTE}
 
     line = {
         "metric": "log-mel frames/sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f32" if w["dtype"] == "float32" else "f64", "data": "synthetic (seeded white noise, generated on device)",
-        "config": {"workload": w["label"], "clips_per_gpu": w["n_clips"], "frames_per_clip": n_frames, "sharding": f"clips x{world}, no collective", "host_numa_bound": bool(numa_bound),
-                   "l2": f"inputs per step {w['n_clips'] * w['n_samples'] * (4 if w['dtype'] == 'float32' else 8) / 1e9:.2f} GB > 126 MB L2 (no flush needed)"},
+        "config": config_of(w, world, args.scaling, total_clips),
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
-        "clocks": clk,
+        "clocks": clk, "host_numa_bound": bool(numa_bound),
     }
+    if strong is not None:
+        line["strong_scaling"] = strong
     if gather is not None:
         line["optional_gather"] = gather
     print(json.dumps(line), flush=True)
