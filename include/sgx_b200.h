@@ -256,6 +256,25 @@ sgx_status sgx_plan_istft(sgx_plan *plan, const void *stft, size_t n_clips, size
 sgx_status sgx_irfft(sgx_dtype dtype, const void *spectrum, size_t spectrum_len, size_t n_fft, void *out, int device,
                      void *cuda_stream);
 
+/* ---- FftPlanner (src/spectrogram.rs:4977-5235): a plan cache for repeated single-frame transforms. The reference object wraps
+ * its FFT backend's planner (plans cached by size); here the cache holds complete plans (device tables included) keyed by
+ * dtype, n_fft, window and output, so the second call of a size pays no table construction or upload. One planner = one
+ * device; like the reference's `&mut self` methods a planner serves one caller at a time. Host or device pointers. */
+typedef struct sgx_fft_planner sgx_fft_planner;
+sgx_status sgx_fft_planner_create(int device /* -1 = current */, sgx_fft_planner **out);      /* FftPlanner::new :4988 */
+sgx_status sgx_fft_planner_destroy(sgx_fft_planner *planner);
+size_t sgx_fft_planner_cached_plans(const sgx_fft_planner *planner);
+/* FftPlanner::fft :5028-5061: unnormalised R2C of n_in <= n_fft samples (zero padded) -> n_fft/2+1 Complex<T> */
+sgx_status sgx_fft_planner_rfft(sgx_fft_planner *planner, sgx_dtype dtype, const void *samples, size_t n_in, size_t n_fft, void *out,
+                                void *cuda_stream);
+/* FftPlanner::irfft :5113-5135: spectrum_len must be n_fft/2+1 (SGX_DIMENSION_MISMATCH otherwise) -> n_fft samples */
+sgx_status sgx_fft_planner_irfft(sgx_fft_planner *planner, sgx_dtype dtype, const void *spectrum, size_t spectrum_len, size_t n_fft,
+                                 void *out, void *cuda_stream);
+/* FftPlanner::power_spectrum :5163-5197 / magnitude_spectrum :5224-5235: zero pad, optional window (SGX_WIN_RECTANGULAR = none),
+ * |X|^2 (magnitude = 0) or |X| (magnitude = 1) -> n_fft/2+1 values of T */
+sgx_status sgx_fft_planner_power_spectrum(sgx_fft_planner *planner, sgx_dtype dtype, const void *samples, size_t n_in, size_t n_fft,
+                                          sgx_window window, double window_param, int magnitude, void *out, void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

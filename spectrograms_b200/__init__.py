@@ -11,7 +11,7 @@ or a GPU is missing, compute calls raise ``FFTBackendError``.
 from .errors import (DimensionMismatchError, FFTBackendError, InternalError, InvalidInputError, SpectrogramError)
 from .params import (ChromaNorm, ChromaParams, ErbParams, GammatoneParams, LogHzParams, LogParams, MelNorm, MelParams, MfccParams,
                      SpectrogramParams, StftParams, WindowType)
-from .plan import (ChromaPlan, Chromagram, Mfcc, MfccPlan, Spectrogram, SpectrogramPlan, SpectrogramPlanner, StftPlan, StftResult,
+from .plan import (ChromaPlan, Chromagram, FftPlanner, Mfcc, MfccPlan, Spectrogram, SpectrogramPlan, SpectrogramPlanner, StftPlan, StftResult,
                    compute_erb_db_spectrogram, compute_erb_magnitude_spectrogram, compute_erb_power_spectrogram,
                    compute_linear_db_spectrogram, compute_linear_magnitude_spectrogram,
                    compute_linear_power_spectrogram, compute_loghz_db_spectrogram,
@@ -23,5 +23,6 @@ from .binaural import (BinauralSpectrogram, ILDSpectrogramParams, ILRSpectrogram
                        ITDSpectrogramParams, binaural_from_stft, compute_ild_spectrogram, compute_ilr_spectrogram,
                        compute_ipd_spectrogram, compute_itd_spectrogram)
 from .sharding import shard_range
+from . import serde
 
 __version__ = "0.1.0"

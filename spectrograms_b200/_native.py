@@ -19,6 +19,8 @@ EXPORTS = [
     "sgx_plan_last_launch_count", "sgx_plan_force_generic", "sgx_plan_set_tensor_cores", "sgx_plan_compute_batch", "sgx_plan_compute_frame",
     "sgx_mfcc_from_log_mel", "sgx_rfft", "sgx_chroma_from_spectrogram", "sgx_chroma_filterbank",
     "sgx_binaural_from_stft", "sgx_plan_compute_binaural", "sgx_plan_istft", "sgx_irfft",
+    "sgx_fft_planner_create", "sgx_fft_planner_destroy", "sgx_fft_planner_cached_plans", "sgx_fft_planner_rfft",
+    "sgx_fft_planner_irfft", "sgx_fft_planner_power_spectrum",
 ]
 
 
@@ -77,6 +79,13 @@ def lib() -> C.CDLL:
     L.sgx_plan_istft.argtypes = [vp, vp, sz, sz, vp, C.POINTER(sz), vp]
     L.sgx_irfft.argtypes = [i, vp, sz, sz, vp, i, vp]
     L.sgx_plan_compute_binaural.argtypes = [vp, i, vp, vp, sz, sz, sz, d, d, sz, i, vp, sz, sz, vp]
+    L.sgx_fft_planner_create.argtypes = [i, C.POINTER(vp)]
+    L.sgx_fft_planner_destroy.argtypes = [vp]
+    L.sgx_fft_planner_cached_plans.argtypes = [vp]
+    L.sgx_fft_planner_cached_plans.restype = sz
+    L.sgx_fft_planner_rfft.argtypes = [vp, i, vp, sz, sz, vp, vp]
+    L.sgx_fft_planner_irfft.argtypes = [vp, i, vp, sz, sz, vp, vp]
+    L.sgx_fft_planner_power_spectrum.argtypes = [vp, i, vp, sz, sz, i, d, i, vp, vp]
     for name in EXPORTS:
         getattr(L, name)
     _lib = L

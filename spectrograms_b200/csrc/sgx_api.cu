@@ -6,7 +6,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/sgx_b200.h"
@@ -1262,6 +1264,41 @@ sgx_status sgx_plan_istft(sgx_plan *plan, const void *stft, size_t n_clips, size
     });
 }
 
+// one C2R transform on an existing complex-STFT plan (rectangular window, hop = n_fft, no centring); host pointers are staged
+static void irfft_with_plan(sgx_plan *pl, const void *spectrum, size_t spectrum_len, size_t n_fft, void *out, void *cuda_stream,
+                            bool sync_device_path) {
+    ensure_device(*pl);
+    DeviceGuard g(pl->device);
+    const size_t es = pl->esize;
+    const PtrKind ki = ptr_kind(spectrum), ko = ptr_kind(out);
+    if (ki != ko) invalid("spectrum and out must both be host pointers or both be device pointers");
+    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+    if (ki == PtrKind::Device) {
+        run_inverse(*pl, spectrum, 1, 1, out, 0, s);
+        if (sync_device_path) ck(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+        return;
+    }
+    void *d_in = nullptr, *d_out = nullptr;
+    cudaError_t e = cudaMalloc(&d_in, spectrum_len * 2 * es);
+    if (e == cudaSuccess) e = cudaMalloc(&d_out, n_fft * es);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_in, spectrum, spectrum_len * 2 * es, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) {
+        try { run_inverse(*pl, d_in, 1, 1, d_out, 0, s); } catch (...) { cudaFree(d_in); cudaFree(d_out); throw; }
+        e = cudaMemcpyAsync(out, d_out, n_fft * es, cudaMemcpyDeviceToHost, s);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(d_in); cudaFree(d_out);
+    ck(e, "irfft");
+}
+
+static sgx_plan_desc one_frame_desc(sgx_dtype dtype, size_t n_fft, int device) {
+    sgx_plan_desc d;
+    std::memset(&d, 0, sizeof d);
+    d.dtype = dtype; d.n_fft = n_fft; d.hop_size = n_fft; d.centre = 0; d.window = SGX_WIN_RECTANGULAR;
+    d.sample_rate_hz = 1.0; d.mapping = SGX_MAP_LINEAR; d.amp = SGX_AMP_POWER; d.output = SGX_OUT_COMPLEX_STFT; d.device = device;
+    return d;
+}
+
 sgx_status sgx_irfft(sgx_dtype dtype, const void *spectrum, size_t spectrum_len, size_t n_fft, void *out, int device,
                      void *cuda_stream) {
     sgx_plan *pl = nullptr;
@@ -1271,36 +1308,10 @@ sgx_status sgx_irfft(sgx_dtype dtype, const void *spectrum, size_t spectrum_len,
         if (spectrum_len != n_fft / 2 + 1) mismatch(n_fft / 2 + 1, spectrum_len);   // :4797-4802
     });
     if (st != SGX_OK) return st;
-    sgx_plan_desc d;
-    std::memset(&d, 0, sizeof d);
-    d.dtype = dtype; d.n_fft = n_fft; d.hop_size = n_fft; d.centre = 0; d.window = SGX_WIN_RECTANGULAR;
-    d.sample_rate_hz = 1.0; d.mapping = SGX_MAP_LINEAR; d.amp = SGX_AMP_POWER; d.output = SGX_OUT_COMPLEX_STFT; d.device = device;
+    const sgx_plan_desc d = one_frame_desc(dtype, n_fft, device);
     st = sgx_plan_create(&d, &pl);
     if (st != SGX_OK) return st;
-    st = guarded([&] {
-        ensure_device(*pl);
-        DeviceGuard g(pl->device);
-        const size_t es = pl->esize;
-        const PtrKind ki = ptr_kind(spectrum), ko = ptr_kind(out);
-        if (ki != ko) invalid("spectrum and out must both be host pointers or both be device pointers");
-        cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
-        if (ki == PtrKind::Device) {
-            run_inverse(*pl, spectrum, 1, 1, out, 0, s);
-            ck(cudaStreamSynchronize(s), "cudaStreamSynchronize");                  // the plan's tables are freed below
-            return;
-        }
-        void *d_in = nullptr, *d_out = nullptr;
-        cudaError_t e = cudaMalloc(&d_in, spectrum_len * 2 * es);
-        if (e == cudaSuccess) e = cudaMalloc(&d_out, n_fft * es);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_in, spectrum, spectrum_len * 2 * es, cudaMemcpyHostToDevice, s);
-        if (e == cudaSuccess) {
-            try { run_inverse(*pl, d_in, 1, 1, d_out, 0, s); } catch (...) { cudaFree(d_in); cudaFree(d_out); throw; }
-            e = cudaMemcpyAsync(out, d_out, n_fft * es, cudaMemcpyDeviceToHost, s);
-        }
-        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-        cudaFree(d_in); cudaFree(d_out);
-        ck(e, "irfft");
-    });
+    st = guarded([&] { irfft_with_plan(pl, spectrum, spectrum_len, n_fft, out, cuda_stream, true); });   // the plan's tables are freed below
     sgx_plan_destroy(pl);
     return st;
 }
@@ -1328,6 +1339,100 @@ sgx_status sgx_rfft(sgx_dtype dtype, const void *samples, size_t n_in, size_t n_
     if (st == SGX_OK && ptr_kind(out) == PtrKind::Device) cudaStreamSynchronize(static_cast<cudaStream_t>(cuda_stream));
     sgx_plan_destroy(pl);
     return st;
+}
+
+// ------------------------------------------------------------------------------------------------ FftPlanner
+// FftPlanner (src/spectrogram.rs:4977-5235): the reference object owns an inner FFT planner that caches plans by size, so
+// repeated single-frame transforms do not rebuild twiddles. Here the cache holds sgx_plan objects (device tables included)
+// keyed by everything that shapes a plan.
+struct sgx_fft_planner {
+    int device = -1;
+    std::map<std::tuple<int, size_t, int, int, uint64_t, int>, sgx_plan *> plans;   // dtype, n_fft, output, window, param bits, amp
+    ~sgx_fft_planner() { for (auto &kv : plans) sgx_plan_destroy(kv.second); }
+};
+
+// cached plan for the key, created on first use; a creation failure leaves sgx_plan_create's status and message in place
+static sgx_status planner_get(sgx_fft_planner *pp, sgx_dtype dtype, size_t n_fft, int output, int window, double wparam, int amp,
+                              sgx_plan **out) {
+    uint64_t bits;
+    std::memcpy(&bits, &wparam, 8);
+    const auto key = std::make_tuple(static_cast<int>(dtype), n_fft, output, window, bits, amp);
+    auto it = pp->plans.find(key);
+    if (it != pp->plans.end()) { *out = it->second; return SGX_OK; }
+    sgx_plan_desc d = one_frame_desc(dtype, n_fft, pp->device);
+    d.output = static_cast<sgx_output>(output);
+    d.window = static_cast<sgx_window>(window);
+    d.window_param = wparam;
+    d.amp = static_cast<sgx_amp>(amp);
+    sgx_plan *pl = nullptr;
+    const sgx_status st = sgx_plan_create(&d, &pl);
+    if (st != SGX_OK) return st;
+    pp->plans.emplace(key, pl);
+    *out = pl;
+    return SGX_OK;
+}
+
+sgx_status sgx_fft_planner_create(int device, sgx_fft_planner **out) {
+    return guarded([&] {
+        if (!out) invalid("null argument");
+        *out = new sgx_fft_planner();
+        (*out)->device = device;
+    });
+}
+sgx_status sgx_fft_planner_destroy(sgx_fft_planner *planner) {
+    return guarded([&] { delete planner; });
+}
+size_t sgx_fft_planner_cached_plans(const sgx_fft_planner *planner) { return planner ? planner->plans.size() : 0; }
+
+sgx_status sgx_fft_planner_rfft(sgx_fft_planner *planner, sgx_dtype dtype, const void *samples, size_t n_in, size_t n_fft, void *out,
+                                void *cuda_stream) {
+    sgx_plan *pl = nullptr;
+    sgx_status st = guarded([&] {
+        if (!planner || !samples || !out) invalid("null argument");
+        if (n_fft == 0) invalid("n_fft must be set");
+        if (n_in == 0) invalid("samples must be non-empty");
+        if (n_in > n_fft) {                                                        // :5034-5040
+            char buf[128];
+            std::snprintf(buf, sizeof buf, "Input length (%zu) exceeds FFT size (%zu)", n_in, n_fft);
+            invalid(buf);
+        }
+    });
+    if (st == SGX_OK) st = planner_get(planner, dtype, n_fft, SGX_OUT_COMPLEX_STFT, SGX_WIN_RECTANGULAR, 0.0, SGX_AMP_POWER, &pl);
+    if (st != SGX_OK) return st;
+    return sgx_plan_compute_frame(pl, samples, n_in, 0, out, cuda_stream);
+}
+
+sgx_status sgx_fft_planner_irfft(sgx_fft_planner *planner, sgx_dtype dtype, const void *spectrum, size_t spectrum_len, size_t n_fft,
+                                 void *out, void *cuda_stream) {
+    sgx_plan *pl = nullptr;
+    sgx_status st = guarded([&] {
+        if (!planner || !spectrum || !out) invalid("null argument");
+        if (n_fft == 0) invalid("n_fft must be set");
+        if (spectrum_len != n_fft / 2 + 1) mismatch(n_fft / 2 + 1, spectrum_len);   // :5120-5126
+    });
+    if (st == SGX_OK) st = planner_get(planner, dtype, n_fft, SGX_OUT_COMPLEX_STFT, SGX_WIN_RECTANGULAR, 0.0, SGX_AMP_POWER, &pl);
+    if (st != SGX_OK) return st;
+    return guarded([&] { irfft_with_plan(pl, spectrum, spectrum_len, n_fft, out, cuda_stream, false); });
+}
+
+sgx_status sgx_fft_planner_power_spectrum(sgx_fft_planner *planner, sgx_dtype dtype, const void *samples, size_t n_in, size_t n_fft,
+                                          sgx_window window, double window_param, int magnitude, void *out, void *cuda_stream) {
+    sgx_plan *pl = nullptr;
+    sgx_status st = guarded([&] {
+        if (!planner || !samples || !out) invalid("null argument");
+        if (n_fft == 0) invalid("n_fft must be set");
+        if (n_in == 0) invalid("samples must be non-empty");
+        if (n_in > n_fft) {                                                        // :5169-5175
+            char buf[128];
+            std::snprintf(buf, sizeof buf, "Input length (%zu) exceeds FFT size (%zu)", n_in, n_fft);
+            invalid(buf);
+        }
+        if (window == SGX_WIN_CUSTOM) invalid("custom windows are not cached by the planner: build a linear plan instead");
+    });
+    if (st == SGX_OK)
+        st = planner_get(planner, dtype, n_fft, SGX_OUT_SPECTROGRAM, window, window_param, magnitude ? SGX_AMP_MAGNITUDE : SGX_AMP_POWER, &pl);
+    if (st != SGX_OK) return st;
+    return sgx_plan_compute_frame(pl, samples, n_in, 0, out, cuda_stream);
 }
 
 }  // extern "C"

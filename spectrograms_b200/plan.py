@@ -16,7 +16,7 @@ import numpy as np
 
 from . import _native
 from .errors import DimensionMismatchError, InvalidInputError
-from .params import (ChromaParams, ErbParams, LogHzParams, LogParams, MelParams, MfccParams, SpectrogramParams,
+from .params import (_as_window, ChromaParams, ErbParams, LogHzParams, LogParams, MelParams, MfccParams, SpectrogramParams,
                      StftParams, WindowType, normalise_dtype)
 
 _WIN = {"rectangular": 0, "hanning": 1, "hamming": 2, "blackman": 3, "kaiser": 4, "gaussian": 5, "custom": 6}
@@ -77,6 +77,16 @@ class Spectrogram:
     # kDLCUDA without a host round trip -- the reference can only offer CPU tensors.
     def to_torch(self):
         return self.data if _is_torch(self.data) else _torch().from_numpy(self.data)
+
+    def to_json(self) -> str:
+        """serde wire format of the crate (``serde_json::to_string(&spec)``, src/spectrogram.rs:2546-2557) -- see serde.py."""
+        from . import serde
+        return serde.to_json(self)
+
+    @staticmethod
+    def from_json(s: str, freq_scale: str = "linear", amp_scale: str = "power", dtype=np.float64) -> "Spectrogram":
+        from . import serde
+        return serde.spectrogram_from_json(s, freq_scale, amp_scale, dtype)
 
     def __dlpack__(self, stream=None):
         t = self.to_torch()
@@ -754,6 +764,95 @@ def rfft(samples, n_fft: int, dtype=None):
 
 
 fft = rfft
+
+
+class FftPlanner:
+    """``FftPlanner`` (src/spectrogram.rs:4977-5235): reuses FFT plans across calls. The reference caches its backend's plans by
+    size; this one caches complete native plans (device tables included) keyed by dtype, n_fft, window and output, so
+    repeated single-frame transforms of a size pay neither table construction nor upload. Methods mirror the reference:
+    ``fft`` (complex spectrum), ``rfft`` (its *magnitude* -- :5072-5079 maps ``Complex::norm``), ``irfft``, ``power_spectrum``,
+    ``magnitude_spectrum``. NumPy in / NumPy out, or CUDA torch tensors in / out."""
+
+    def __init__(self, device: Optional[int] = None):
+        self._h = C.c_void_p()
+        _native.check(_native.lib().sgx_fft_planner_create(-1 if device is None else int(device), C.byref(self._h)))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                _native.lib().sgx_fft_planner_destroy(h)
+            except Exception:
+                pass
+            self._h = C.c_void_p()
+
+    def cached_plans(self) -> int:
+        return int(_native.lib().sgx_fft_planner_cached_plans(self._h))
+
+    @staticmethod
+    def _prep(x, complex_in=False):
+        if _is_torch(x):
+            torch = _torch()
+            ok = (torch.complex64, torch.complex128) if complex_in else (torch.float32, torch.float64)
+            if not x.is_cuda or x.dtype not in ok or x.dim() != 1 or x.numel() == 0:
+                raise InvalidInputError("expected a non-empty 1-D CUDA tensor of a supported dtype (or a NumPy array)")
+            return x.contiguous(), str(x.dtype).endswith(("float32", "complex64"))
+        x = np.ascontiguousarray(x)
+        if complex_in:
+            if x.dtype not in (np.complex64, np.complex128):
+                x = x.astype(np.complex128)
+        elif x.dtype not in (np.float32, np.float64):
+            x = x.astype(np.float64)
+        if x.ndim != 1 or x.size == 0:
+            raise InvalidInputError("expected a non-empty 1-D array")
+        return x, x.dtype in (np.float32, np.complex64)
+
+    @staticmethod
+    def _alloc(like, n, f32, cplx):
+        if _is_torch(like):
+            torch = _torch()
+            dt = (torch.complex64 if f32 else torch.complex128) if cplx else (torch.float32 if f32 else torch.float64)
+            t = torch.empty(n, dtype=dt, device=like.device)
+            return t, t.data_ptr(), torch.cuda.current_stream(like.device).cuda_stream
+        dt = (np.complex64 if f32 else np.complex128) if cplx else (np.float32 if f32 else np.float64)
+        a = np.empty(n, dtype=dt)
+        return a, a.ctypes.data, None
+
+    @staticmethod
+    def _ptr(x):
+        return x.data_ptr() if _is_torch(x) else x.ctypes.data
+
+    def fft(self, samples, n_fft: int):
+        x, f32 = self._prep(samples)
+        out, optr, stream = self._alloc(x, int(n_fft) // 2 + 1, f32, True)
+        _native.check(_native.lib().sgx_fft_planner_rfft(self._h, 0 if f32 else 1, self._ptr(x), x.shape[0], int(n_fft), optr, stream))
+        return out
+
+    def rfft(self, samples, n_fft: int):
+        z = self.fft(samples, n_fft)
+        return z.abs() if _is_torch(z) else np.abs(z)
+
+    def irfft(self, spectrum, n_fft: int):
+        x, f32 = self._prep(spectrum, complex_in=True)
+        out, optr, stream = self._alloc(x, int(n_fft), f32, False)
+        _native.check(_native.lib().sgx_fft_planner_irfft(self._h, 0 if f32 else 1, self._ptr(x), x.shape[0], int(n_fft), optr, stream))
+        return out
+
+    def _spectrum(self, samples, n_fft, window, magnitude):
+        x, f32 = self._prep(samples)
+        w = _as_window(window) if window is not None else WindowType.rectangular()
+        if w.kind == "custom":
+            raise InvalidInputError("custom windows are not cached by the planner: build a linear plan instead")
+        out, optr, stream = self._alloc(x, int(n_fft) // 2 + 1, f32, False)
+        _native.check(_native.lib().sgx_fft_planner_power_spectrum(self._h, 0 if f32 else 1, self._ptr(x), x.shape[0], int(n_fft),
+                                                                   _WIN[w.kind], float(w.param), int(magnitude), optr, stream))
+        return out
+
+    def power_spectrum(self, samples, n_fft: int, window=None):
+        return self._spectrum(samples, n_fft, window, False)
+
+    def magnitude_spectrum(self, samples, n_fft: int, window=None):
+        return self._spectrum(samples, n_fft, window, True)
 
 
 def irfft(spectrum, n_fft: int):
