@@ -371,7 +371,32 @@ def main():
                "h2d_bytes_per_step": w["n_clips"] * w["n_samples"] * es, "d2h_bytes_per_step": w["n_clips"] * rows * n_frames * es,
                "steps": ksteps, "ms_per_step": 1e3 * float(te.item()) / ksteps,
                "check": "host result equals device result: %s" % bool(torch.equal(h_out[:4].to(dev), out[:4]))}
-        del h_in, h_out
+        # the platform ceiling of this leg: the same pinned buffers copied both ways at once with NO kernel, all ranks together
+        # (tools/ubench/host_copy.py is the stand-alone form). e2e.frac_of_copy_ceiling = how much of it the pipeline reaches.
+        sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+        d_in_flat, d_out_flat = clips.view(-1), out.view(-1)
+        hi_flat, ho_flat = h_in.view(-1), h_out.view(-1)
+
+        def copy_step():
+            with torch.cuda.stream(sa):
+                d_in_flat.copy_(hi_flat, non_blocking=True)
+            with torch.cuda.stream(sb):
+                ho_flat.copy_(d_out_flat, non_blocking=True)
+
+        copy_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            copy_step()
+        torch.cuda.synchronize()
+        tc_ = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tc_, op=dist.ReduceOp.MAX)
+        ceil_fps = job_frames_per_step * 3 / float(tc_.item())
+        e2e["copy_ceiling"] = {"value": ceil_fps, "unit": "frames/s", "ms_per_step": 1e3 * float(tc_.item()) / 3,
+                               "what": "concurrent H2D + D2H of the same pinned buffers, no kernel, all ranks at once (max over ranks)"}
+        e2e["frac_of_copy_ceiling"] = e2e["value"] / ceil_fps
+        del h_in, h_out, hi_flat, ho_flat
 
     # ---- optional result gather to rank 0 over NCCL (NVLink / NVSwitch): NOT part of the hot path or of `value`
     gather = None

@@ -85,6 +85,42 @@ template <typename T> struct Dft<T, 16> {
     }
 };
 
+template <typename T> struct Dft<T, 32> {
+    static __device__ __forceinline__ void run(Cx<T> *v) {
+        // n = j + 4 n1: A_j[k1] = DFT8 over n1 of v[j + 4 n1]; X[k1 + 8 k2] = DFT4 over j of W32^(j k1) A_j[k1]
+        Cx<T> a[4][8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int n1 = 0; n1 < 8; ++n1) a[j][n1] = v[j + 4 * n1];
+            Dft<T, 8>::run(a[j]);
+        }
+        // W32^m = (cos(2 pi m / 32), -sin(2 pi m / 32)), m = j k1 <= 21
+        constexpr double kC[8] = {1.0, 0.98078528040323044912618223613424, 0.92387953251128675612818318939679, 0.83146961230254523707878837761791,
+                                  0.70710678118654752440084436210485, 0.55557023301960222474283081394853, 0.38268343236508977172845998403040,
+                                  0.19509032201612826784828486847702};
+#pragma unroll
+        for (int j = 1; j < 4; ++j)
+#pragma unroll
+            for (int k1 = 1; k1 < 8; ++k1) {
+                const int m = j * k1;                        // angle m * pi / 16, quadrant m / 8
+                const int r = m & 7, qd = m >> 3;
+                const T c = static_cast<T>(kC[r]), sn = static_cast<T>(r == 0 ? 0.0 : kC[8 - r]);
+                // (cos, -sin) of the first-quadrant angle, rotated by -i per quadrant
+                Cx<T> w = {c, -sn};
+                if (qd == 1) w = {-sn, -c};
+                else if (qd == 2) w = {-c, sn};
+                if (r == 0 && qd == 1) a[j][k1] = mul_mi(a[j][k1]);
+                else a[j][k1] = a[j][k1] * w;
+            }
+#pragma unroll
+        for (int k1 = 0; k1 < 8; ++k1) {
+            dft4(a[0][k1], a[1][k1], a[2][k1], a[3][k1]);
+            v[k1] = a[0][k1]; v[k1 + 8] = a[1][k1]; v[k1 + 16] = a[2][k1]; v[k1 + 24] = a[3][k1];
+        }
+    }
+};
+
 template <typename T> __device__ __forceinline__ Cx<T> ldg_cx(const Cx<T> *p);
 template <> __device__ __forceinline__ Cx<float> ldg_cx<float>(const Cx<float> *p) {
     const float2 v = __ldg(reinterpret_cast<const float2 *>(p));
@@ -99,22 +135,23 @@ __host__ __device__ constexpr int pad16(int i) { return i + (i >> 4); }
 
 // One Stockham pass of radix R with accumulated length CUR on a frame's M-point buffer; the thread owns butterflies
 // b = t + TPF*u (u < 16/R). v[16] is the thread's register file for the whole pass: load - (CTA barrier) - store.
-template <typename T, int M, int R, int CUR>
+template <typename T, int M, int R, int CUR, int RPT = 16>
 __device__ __forceinline__ void pass_load(const Cx<T> *z, const Cx<T> *__restrict__ tw, int t, Cx<T> *v) {
-    constexpr int TPF = M / 16, B = M / R, MM = M / (CUR * R);
+    constexpr int TPF = M / RPT, B = M / R, MM = M / (CUR * R);
 #pragma unroll
-    for (int u = 0; u < 16 / R; ++u) {
+    for (int u = 0; u < RPT / R; ++u) {
         const int b = t + TPF * u;
         const int q = b & (CUR - 1);
         // twiddles W_{CUR*R}^{j q} = w^j with w = W_M^{q MM}: two table loads (w, w^4); the other powers are products of
         // one of {w, w^2, w^3} and one of {w^4, w^8, w^12}, formed on the fly (at most three chained multiplications) --
         // the memory-instruction queue, not the FP pipe, is what these passes run out of
-        Cx<T> wl[4], wh[4];
+        Cx<T> wl[4], wh[4], w16 = {T(1), T(0)};
         if (CUR > 1) {
             wl[1] = ldg_cx<T>(tw + q * MM);
             if (R > 2) { wl[2] = wl[1] * wl[1]; wl[3] = wl[2] * wl[1]; }
             if (R > 4) wh[1] = ldg_cx<T>(tw + 4 * q * MM);
             if (R > 8) { wh[2] = wh[1] * wh[1]; wh[3] = wh[2] * wh[1]; }
+            if (R > 16) w16 = ldg_cx<T>(tw + 16 * q * MM);        // radix 32: j = 16 + j' costs one more multiplication
         }
         // B is a multiple of 16, so pad16(j*B + b) = j*pad16(B) + pad16(b): one base address, constant strides
         const Cx<T> *zb = z + pad16(b);
@@ -122,19 +159,22 @@ __device__ __forceinline__ void pass_load(const Cx<T> *z, const Cx<T> *__restric
         for (int j = 0; j < R; ++j) {
             Cx<T> x = zb[j * pad16(B)];
             if (CUR > 1 && j > 0) {
-                const int hi = j >> 2, lo = j & 3;
-                const Cx<T> wj = hi == 0 ? wl[lo] : (lo == 0 ? wh[hi] : wh[hi] * wl[lo]);
-                x = x * wj;
+                const int hi = (j >> 2) & 3, lo = j & 3;
+                if ((j & 15) != 0) {
+                    const Cx<T> wj = hi == 0 ? wl[lo] : (lo == 0 ? wh[hi] : wh[hi] * wl[lo]);
+                    x = x * wj;
+                }
+                if (j >= 16) x = x * w16;
             }
             v[u * R + j] = x;
         }
     }
 }
-template <typename T, int M, int R, int CUR>
+template <typename T, int M, int R, int CUR, int RPT = 16>
 __device__ __forceinline__ void pass_store(Cx<T> *z, int t, Cx<T> *v) {
-    constexpr int TPF = M / 16;
+    constexpr int TPF = M / RPT;
 #pragma unroll
-    for (int u = 0; u < 16 / R; ++u) {
+    for (int u = 0; u < RPT / R; ++u) {
         const int b = t + TPF * u;
         const int q = b & (CUR - 1), i = b / CUR;
         Dft<T, R>::run(v + u * R);
@@ -144,7 +184,7 @@ __device__ __forceinline__ void pass_store(Cx<T> *z, int t, Cx<T> *v) {
 #pragma unroll
             for (int k = 0; k < R; ++k) zo[k * pad16(CUR)] = v[u * R + k];
         } else {
-            // first pass (CUR = 1, R = 16): outputs 16 b + k, i.e. 17 b + k after padding
+            // first pass (CUR = 1, R = 16 or 32): outputs R b + k; R b is a multiple of 16, so the pad of k adds on
             Cx<T> *zo = z + pad16(i * R * CUR + q);
 #pragma unroll
             for (int k = 0; k < R; ++k) zo[pad16(k * CUR)] = v[u * R + k];
@@ -158,8 +198,10 @@ __device__ __forceinline__ void pass_store(Cx<T> *z, int t, Cx<T> *v) {
 // warp cover 32 consecutive words (they were FT-way bank conflicts with one frame per warp), the window load of a warp
 // is one line shared by its FT frames, and the frame-strided FFT accesses stay conflict free because the frame stride
 // is LPF mod 16 complex elements (zs_of). The price is a CTA-wide barrier between passes instead of a per-frame one.
-template <int TPF, int FT> struct ThreadMap {
-    static constexpr bool kInterleaved = TPF >= 32 && FT > 1;
+template <int TPF, int FT, int RPT = 16> struct ThreadMap {
+    // the two-pass form (RPT = 32, M = 1024) has exactly one warp per frame: keeping the warp together makes every exchange
+    // of the FFT a warp-level sync, and its epilogue works on a frame-major tile, so it is not interleaved
+    static constexpr bool kInterleaved = RPT == 16 && TPF >= 32 && FT > 1;
     static constexpr int LPF = kInterleaved ? 32 / FT : TPF;        // lanes of one frame inside a warp
     static __device__ __forceinline__ void get(int tid, int &fl, int &t) {
         if (kInterleaved) {
@@ -172,16 +214,16 @@ template <int TPF, int FT> struct ThreadMap {
         }
     }
 };
-template <int TPF, int FT> __device__ __forceinline__ void frame_sync(int) {
-    if (ThreadMap<TPF, FT>::kInterleaved || TPF > 32) __syncthreads();
+template <int TPF, int FT, int RPT = 16> __device__ __forceinline__ void frame_sync(int) {
+    if (ThreadMap<TPF, FT, RPT>::kInterleaved || TPF > 32) __syncthreads();
     else __syncwarp();
 }
 
 // complex elements per frame buffer: >= M + 1 bins; for the interleaved map the stride is LPF mod 16 (M >= 256 makes
 // pad16(M) a multiple of 16), which spreads the FT frame segments a warp touches over all banks
-constexpr int zs_of(int M, int FT) {
-    const int tpf = M / 16;
-    const bool inter = tpf >= 32 && FT > 1;
+constexpr int zs_of(int M, int FT, int RPT = 16) {
+    const int tpf = M / RPT;
+    const bool inter = tpf >= 32 && FT > 1;        // (RPT = 32: the post pass and the epilogue use the interleaved map)
     return pad16(M) + (inter ? 32 / FT : 8);
 }
 
@@ -189,18 +231,24 @@ template <int M> struct Radices {          // M = 16^P16 * LAST, LAST in {1, 2, 
     static constexpr int P16 = M >= 4096 ? 3 : (M >= 256 ? 2 : 1);
     static constexpr int LAST = M / (P16 == 3 ? 4096 : (P16 == 2 ? 256 : 16));
 };
+// Complex values a thread holds. 32 (f32, M = 512 / 1024: n_fft 1024 / 2048) makes the FFT two passes -- radix 32 then radix
+// M / 32 -- with ONE exchange instead of two: the L1 / shared-memory data pipe is what these sizes run out of (94 % busy on
+// BASELINE configs[2] with three passes). f64 and the other sizes keep 16 (64 f64 registers of data per thread are too many).
+template <typename T> constexpr int rpt_of(int M) { return (sizeof(T) == 4 && (M == 512 || M == 1024)) ? 32 : 16; }
 
 template <typename T, int M, int FT, bool PAIR>
-__global__ void __launch_bounds__(FT *(M / 16), (sizeof(T) == 4 ? 4 : 2) * 256 / (FT * (M / 16) > 256 ? FT * (M / 16) : 256)) k_r2c_fused_pow2(const __grid_constant__ KParams p) {
-    constexpr int TPF = M / 16, N = 2 * M;
-    constexpr int ZS = zs_of(M, FT);                     // complex elements per frame buffer (M+1 spectrum bins fit too)
+__global__ void __launch_bounds__(FT *(M / rpt_of<T>(M)), rpt_of<T>(M) == 32 ? 512 / (FT * (M / 32)) : (sizeof(T) == 4 ? 4 : 2) * 256 / (FT * (M / 16) > 256 ? FT * (M / 16) : 256))
+k_r2c_fused_pow2(const __grid_constant__ KParams p) {
+    constexpr int RPT = rpt_of<T>(M);                    // complex values per thread: 16, or 32 for the two-pass sizes
+    constexpr int TPF = M / RPT, N = 2 * M;
+    constexpr int ZS = zs_of(M, FT, RPT);                // complex elements per frame buffer (M+1 spectrum bins fit too)
     using C = Cx<T>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C *zbuf = reinterpret_cast<C *>(smem_raw);
 
     const int tid = threadIdx.x;
     int fl, t;                                       // frame within the tile, thread within the frame
-    ThreadMap<TPF, FT>::get(tid, fl, t);
+    ThreadMap<TPF, FT, RPT>::get(tid, fl, t);
     const int clip = blockIdx.x / p.tiles_per_clip;
     const int tile = blockIdx.x - clip * p.tiles_per_clip;
     // Ordinary launch: the tile is FT consecutive frames of one clip. Stereo-pair launch (samples_b != null, FT >= 2): FT/2
@@ -219,11 +267,11 @@ __global__ void __launch_bounds__(FT *(M / 16), (sizeof(T) == 4 ? 4 : 2) * 256 /
     const T *x = static_cast<const T *>(ch ? p.samples_b : p.samples) + static_cast<long long>(clip) * p.clip_stride;
     const T *win = static_cast<const T *>(p.window);
     const C *tw = static_cast<const C *>(p.tw);
-    C v[16];
+    C v[RPT];
 
     // ---- load + window + first pass (CUR = 1: no twiddles). Element n of the packed frame = samples 2n, 2n+1.
     {
-        constexpr int R = 16, B = M / R;
+        constexpr int R = RPT, B = M / R;
         const long long base = (f0 + (pair ? fi : fl)) * p.hop - p.pad;
         const bool vec_ok = p.vec_ok != 0;
         if (vec_ok && base >= 0 && base + N <= p.n_samples) {
@@ -247,30 +295,51 @@ __global__ void __launch_bounds__(FT *(M / 16), (sizeof(T) == 4 ? 4 : 2) * 256 /
                 v[j] = {a * __ldg(win + 2 * n), b * __ldg(win + 2 * n + 1)};
             }
         }
-        pass_store<T, M, 16, 1>(z, t, v);
+        pass_store<T, M, RPT, 1, RPT>(z, t, v);
     }
-    frame_sync<TPF, FT>(fl);
+    frame_sync<TPF, FT, RPT>(fl);
+    if constexpr (RPT == 32) {
+        // two-pass form: radix 32 done, one pass of radix M / 32 (32 or 16) left -- a single exchange
+        constexpr int R2 = M / 32;
+        pass_load<T, M, R2, 32, RPT>(z, tw, t, v);
+        frame_sync<TPF, FT, RPT>(fl);
+        pass_store<T, M, R2, 32, RPT>(z, t, v);
+        frame_sync<TPF, FT, RPT>(fl);
+    } else {
     if constexpr (Radices<M>::P16 >= 2) {
         pass_load<T, M, 16, 16>(z, tw, t, v);
-        frame_sync<TPF, FT>(fl);
+        frame_sync<TPF, FT, RPT>(fl);
         pass_store<T, M, 16, 16>(z, t, v);
-        frame_sync<TPF, FT>(fl);
+        frame_sync<TPF, FT, RPT>(fl);
     }
     if constexpr (Radices<M>::P16 >= 3) {
         pass_load<T, M, 16, 256>(z, tw, t, v);
-        frame_sync<TPF, FT>(fl);
+        frame_sync<TPF, FT, RPT>(fl);
         pass_store<T, M, 16, 256>(z, t, v);
-        frame_sync<TPF, FT>(fl);
+        frame_sync<TPF, FT, RPT>(fl);
     }
     if constexpr (Radices<M>::LAST > 1) {
         constexpr int CUR = M / Radices<M>::LAST;
         pass_load<T, M, Radices<M>::LAST, CUR>(z, tw, t, v);
-        frame_sync<TPF, FT>(fl);
+        frame_sync<TPF, FT, RPT>(fl);
         pass_store<T, M, Radices<M>::LAST, CUR>(z, t, v);
-        frame_sync<TPF, FT>(fl);
+        frame_sync<TPF, FT, RPT>(fl);
+    }
     }
 
-    // ---- post pass: X[k] = E + W_N^k O, X[M-k] = conj(E - W_N^k O); thread owns k = t + TPF*u (u < 8), plus k = M/2
+    if constexpr (RPT == 32 && TPF >= 32 && FT > 1) {
+        // The FFT passes ran with one warp per frame (warp-level syncs only). The post pass only READS the frame buffers, so it
+        // may use any thread -> (frame, bin) map: switch to the interleaved one (every warp holds 32 / FT consecutive threads
+        // of each frame), which makes the transposed tile writes P[bin][FT] of the epilogue conflict free.
+        __syncthreads();
+        constexpr int LPF = 32 / FT;
+        const int lane = tid & 31, w = tid >> 5;
+        fl = lane / LPF;
+        t = (lane % LPF) + LPF * w;
+        z = zbuf + fl * ZS;
+    }
+
+    // ---- post pass: X[k] = E + W_N^k O, X[M-k] = conj(E - W_N^k O); thread owns k = t + TPF*u (u < RPT/2), plus k = M/2
     //      and k = 0 / M on thread 0. Values are held in registers across the barrier because the tile may alias z.
     const C *post = static_cast<const C *>(p.post);
     auto post_pair = [&](int u, C &xa, C &xb) {
@@ -290,9 +359,9 @@ __global__ void __launch_bounds__(FT *(M / 16), (sizeof(T) == 4 ? 4 : 2) * 256 /
         }
     };
     if (p.output == SGX_OUT_COMPLEX_STFT) {
-        C xa[8], xb[8];
+        C xa[RPT / 2], xb[RPT / 2];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) post_pair(u, xa[u], xb[u]);
+        for (int u = 0; u < RPT / 2; ++u) post_pair(u, xa[u], xb[u]);
         C xm = {T(0), T(0)};
         if (t == 0) {                              // bin M/2: E and O are both Z[M/2]-derived, W_N^(M/2) = -i
             const C a = z[pad16(M / 2)];
@@ -301,7 +370,7 @@ __global__ void __launch_bounds__(FT *(M / 16), (sizeof(T) == 4 ? 4 : 2) * 256 /
         __syncthreads();
         typename Cplx<T>::type *S = reinterpret_cast<typename Cplx<T>::type *>(zbuf) + fl * p.frame_stride;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < RPT / 2; ++u) {
             const int k = t + TPF * u;
             S[k] = mk<T>(xa[u].x, xa[u].y);
             S[M - k] = mk<T>(xb[u].x, xb[u].y);
@@ -328,9 +397,9 @@ __global__ void __launch_bounds__(FT *(M / 16), (sizeof(T) == 4 ? 4 : 2) * 256 /
     }
     // every other output starts from the power spectrum (norm_sqr, src/spectrogram.rs:1332-1334): square before the
     // barrier, so only one value per bin stays live across it
-    T pa[8], pb[8], pm = T(0);
+    T pa[RPT / 2], pb[RPT / 2], pm = T(0);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < RPT / 2; ++u) {
         C xa, xb;
         post_pair(u, xa, xb);
         pa[u] = xa.x * xa.x + xa.y * xa.y;
@@ -352,7 +421,7 @@ __global__ void __launch_bounds__(FT *(M / 16), (sizeof(T) == 4 ? 4 : 2) * 256 /
         // order -- it stays inside the f32 1e-5 / f64 1e-12 budgets (tests/test_chroma.py).
         constexpr int NT = FT * TPF, CH = NT / 12;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < RPT / 2; ++u) {
             const int k = t + TPF * u;
             P[k * FT + fl] = t_sqrt(pa[u]);
             P[(M - k) * FT + fl] = t_sqrt(pb[u]);
@@ -404,7 +473,7 @@ __global__ void __launch_bounds__(FT *(M / 16), (sizeof(T) == 4 ? 4 : 2) * 256 /
         // FT frames of a column with a single vector load, and every weight / column index is loaded once per FT outputs.
         // Same ascending-column, un-fused arithmetic as SparseMatrix::multiply_vec (src/spectrogram.rs:102-117).
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < RPT / 2; ++u) {
             const int k = t + TPF * u;
             P[k * FT + fl] = pa[u];
             P[(M - k) * FT + fl] = pb[u];
@@ -449,7 +518,7 @@ __global__ void __launch_bounds__(FT *(M / 16), (sizeof(T) == 4 ? 4 : 2) * 256 /
         const T eps = static_cast<T>(p.eps);
         T *pfm = P + fl * PS;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < RPT / 2; ++u) {
             const int k = t + TPF * u;
             pfm[k] = pa[u];
             pfm[M - k] = pb[u];
@@ -482,7 +551,7 @@ __global__ void __launch_bounds__(FT *(M / 16), (sizeof(T) == 4 ? 4 : 2) * 256 /
     }
     T *pf = P + fl * p.tile_stride;
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < RPT / 2; ++u) {
         const int k = t + TPF * u;
         pf[k] = pa[u];
         pf[M - k] = pb[u];
@@ -629,16 +698,21 @@ cudaError_t launch_one(const KParams &p, size_t smem, cudaStream_t stream) {
     if (grid > 2147483647LL) return cudaErrorInvalidConfiguration;
     cudaError_t e = cudaFuncSetAttribute(k_r2c_fused_pow2<T, M, FT, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    k_r2c_fused_pow2<T, M, FT, PAIR><<<static_cast<unsigned>(grid), FT *(M / 16), smem, stream>>>(p);
+    k_r2c_fused_pow2<T, M, FT, PAIR><<<static_cast<unsigned>(grid), FT *(M / rpt_of<T>(M)), smem, stream>>>(p);
     return cudaGetLastError();
 }
 
 // frames per tile: 256 threads per CTA. (512-thread f64 tiles for n_fft >= 4096 store wider rows but leave one CTA per
 // SM with nothing to overlap its load and drain phases with: 3.52 ms against 3.20 ms on BASELINE configs[4].)
+constexpr int ft16_of(int M) {          // the inverse kernel keeps 16 values per thread for every size
+    const int ft = 256 / (M / 16);
+    return ft < 1 ? 1 : (ft > 32 ? 32 : ft);
+}
 constexpr int ft_of(int M, bool f64) {
-    const int tpf = M / 16;
-    const int want = 256;
-    (void)f64;
+    const int tpf = M / (f64 ? rpt_of<double>(M) : rpt_of<float>(M));
+    // the one-warp-per-frame two-pass form (f32, M = 1024) runs 128-thread CTAs: 128 registers per thread allow 512 threads per
+    // SM, and four small CTAs overlap their load / FFT / epilogue phases better than two large ones
+    const int want = (!f64 && rpt_of<float>(M) == 32) ? 128 : 256;
     const int ft = want / tpf;
     return ft < 1 ? 1 : (ft > 32 ? 32 : ft);
 }
@@ -649,7 +723,10 @@ bool pow2_supported(size_t n_fft) {
     return n_fft >= 256 && n_fft <= 8192 && (n_fft & (n_fft - 1)) == 0;
 }
 int pow2_frames_per_tile(size_t n_fft, bool f64) { return ft_of(static_cast<int>(n_fft / 2), f64); }
-int pow2_frame_elems(size_t n_fft) { return zs_of(static_cast<int>(n_fft / 2), ft_of(static_cast<int>(n_fft / 2), false)); }
+int pow2_frame_elems(size_t n_fft, bool f64) {
+    const int M = static_cast<int>(n_fft / 2);
+    return zs_of(M, ft_of(M, f64), f64 ? rpt_of<double>(M) : rpt_of<float>(M));
+}
 
 cudaError_t launch_pow2(const KParams &p, bool f64, size_t smem, cudaStream_t stream) {
 #define SGX_POW2_CASE(MM)                                                                         \
@@ -669,12 +746,14 @@ cudaError_t launch_pow2(const KParams &p, bool f64, size_t smem, cudaStream_t st
 #undef SGX_POW2_CASE
 }
 
-cudaError_t launch_c2r_pow2(const KParams &p, bool f64, size_t smem, const void *stft, void *frames_out, long long n_clips,
+int pow2_c2r_frames_per_tile(size_t n_fft) { return ft16_of(static_cast<int>(n_fft / 2)); }
+
+cudaError_t launch_c2r_pow2(const KParams &p, bool f64, const void *stft, void *frames_out, long long n_clips,
                             long long n_frames, int apply_window, cudaStream_t stream) {
 #define SGX_POW2_C2R(MM)                                                                                                         \
     case MM:                                                                                                                     \
-        return f64 ? launch_c2r_one<double, MM, ft_of(MM, true)>(p, smem, stft, frames_out, n_clips, n_frames, apply_window, stream) \
-                   : launch_c2r_one<float, MM, ft_of(MM, false)>(p, smem, stft, frames_out, n_clips, n_frames, apply_window, stream);
+        return f64 ? launch_c2r_one<double, MM, ft16_of(MM)>(p, sizeof(double) * 2 * ft16_of(MM) * zs_of(MM, ft16_of(MM)), stft, frames_out, n_clips, n_frames, apply_window, stream) \
+                   : launch_c2r_one<float, MM, ft16_of(MM)>(p, sizeof(float) * 2 * ft16_of(MM) * zs_of(MM, ft16_of(MM)), stft, frames_out, n_clips, n_frames, apply_window, stream);
     switch (p.n_fft / 2) {
         SGX_POW2_C2R(128)
         SGX_POW2_C2R(256)

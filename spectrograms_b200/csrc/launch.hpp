@@ -38,7 +38,7 @@ bool fast400_tc_fits(int n_steps, int n_rounds, size_t b_floats);
 // p.tiles_per_clip must be set from the helpers below; p.vec_ok is the "vector loads allowed" flag.
 bool pow2_supported(size_t n_fft);
 int pow2_frames_per_tile(size_t n_fft, bool f64);
-int pow2_frame_elems(size_t n_fft);
+int pow2_frame_elems(size_t n_fft, bool f64);
 cudaError_t launch_pow2(const KParams &p, bool f64, size_t smem_bytes, cudaStream_t stream);
 
 // standalone mfcc_from_log_mel (kernel_mfcc.cu): log_mel [n_clips][n_mels][n_frames] -> out [n_clips][rows][n_frames]
@@ -62,8 +62,9 @@ cudaError_t launch_binaural(bool f64, int cue, const void *left, const void *rig
 cudaError_t launch_c2r_frames(const KParams &p, bool f64, size_t smem, const void *stft, void *frames_out, long long n_clips,
                               long long n_frames, int apply_window, cudaStream_t stream);
 // the same on the register radix-16 passes of r2c_fused_pow2 (kernel_pow2.cu); p.tiles_per_clip = ceil(n_frames / FT)
-cudaError_t launch_c2r_pow2(const KParams &p, bool f64, size_t smem, const void *stft, void *frames_out, long long n_clips,
+cudaError_t launch_c2r_pow2(const KParams &p, bool f64, const void *stft, void *frames_out, long long n_clips,
                             long long n_frames, int apply_window, cudaStream_t stream);
+int pow2_c2r_frames_per_tile(size_t n_fft);      // tiles of the inverse kernel: p.tiles_per_clip = ceil(n_frames / this)
 cudaError_t launch_ola_gather(bool f64, const void *frames, const void *window, void *out, long long n_clips, long long n_frames,
                               int n_fft, int hop, long long out_len, long long trim, cudaStream_t stream);
 

@@ -385,7 +385,7 @@ void select_family(sgx_plan &pl) {
     if (!pl.fast400 && pow2_supported(d.n_fft)) {
         const size_t es = pl.esize;
         const int ft = pow2_frames_per_tile(d.n_fft, pl.f64);
-        const size_t zs = static_cast<size_t>(pow2_frame_elems(d.n_fft));
+        const size_t zs = static_cast<size_t>(pow2_frame_elems(d.n_fft, pl.f64));
         size_t ts = std::max(pl.tab.out_len, pl.tab.n_bins);
         if (ts % 2 == 0) ts += 1;
         const size_t smem = std::max(ft * zs * 2 * es, 2 * ft * ts * es);
@@ -1191,12 +1191,12 @@ void run_inverse(sgx_plan &pl, const void *d_stft, size_t nc, size_t n_frames, v
     p.n_clips = static_cast<int>(nc);
     // the register-radix inverse stores (x[2m], x[2m+1]) pairs: the destination must be pair aligned
     if (pl.pow2 && !pl.force_generic && reinterpret_cast<uintptr_t>(d_frames_out) % (2 * pl.esize) == 0) {
-        p.FT = pl.pow2_ft;
+        p.FT = pow2_c2r_frames_per_tile(pl.desc.n_fft);
         p.fd_FT = make_fastdiv(static_cast<unsigned>(p.FT));
         p.frame_stride = pl.pow2_frame_stride;
         p.tile_stride = pl.pow2_tile_stride;
         p.tiles_per_clip = static_cast<int>((n_frames + p.FT - 1) / p.FT);
-        ck(launch_c2r_pow2(p, pl.f64, pl.pow2_smem, d_stft, d_frames_out, static_cast<long long>(nc), static_cast<long long>(n_frames),
+        ck(launch_c2r_pow2(p, pl.f64, d_stft, d_frames_out, static_cast<long long>(nc), static_cast<long long>(n_frames),
                            apply_window, st), "kernel launch (c2r_pow2)");
         pl.last_launches += 1;
         return;
