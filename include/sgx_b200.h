@@ -14,12 +14,16 @@
  *     (src/error.rs:13-28). sgx_last_error_message() returns the thread-local Display string of the last error.
  *   - Ownership: the caller owns every buffer; nothing is retained after a call returns (for device pointers: after
  *     the work queued on `stream` completes). A plan owns its device tables and scratch.
- *   - Threading: a plan is `&mut self` -- one call at a time per plan; distinct plans are independent.
+ *   - Threading: a plan is `&mut self` -- one call at a time per plan; distinct plans are independent. Calls that stage through
+ *     plan-owned device scratch (sgx_plan_istft, the unfused route of sgx_plan_compute_binaural) order themselves after the
+ *     previous use of that scratch with an event, so consecutive asynchronous calls on different streams do not race.
  *   - Layout: outputs are row-major (rows, n_frames) with frames contiguous (:248, :1433), clips outermost.
  *     Complex values are interleaved (re, im) like num_complex::Complex<T>.
  *   - Pointers may be host or device pointers (detected with cudaPointerGetAttributes). Device pointers run
- *     asynchronously on `stream`; host pointers are staged through pinned chunks, computed, copied back, and the
- *     call returns after the results are in host memory.
+ *     asynchronously on `stream`; host pointers are copied in chunks (64 MB) to device staging buffers, computed and copied back
+ *     over three private streams, and the call returns after the results are in host memory. The copies come straight from
+ *     the caller's buffers: they overlap with compute only if the caller's memory is pinned (cudaHostAlloc / cudaHostRegister);
+ *     pageable memory works but serialises.
  *   - There is no CPU fallback: without a CUDA device every compute call fails with SGX_BACKEND_ERROR.
  */
 #ifndef SGX_B200_H

@@ -267,6 +267,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_r2c_fused_n400(const __grid_con
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(static_cast<const float4 *>(p.dct_folded) + i) : "memory");
             }
             if (p.apply_db) sparse_quads_epilogue<2, true>(p, ptile, s_quads, s_qinfo, ocf, scratch, nf, warp, lane);
+            else if (p.amp == SGX_AMP_MAGNITUDE) sparse_quads_epilogue<1, true>(p, ptile, s_quads, s_qinfo, ocf, scratch, nf, warp, lane);
             else sparse_quads_epilogue<0, true>(p, ptile, s_quads, s_qinfo, ocf, scratch, nf, warp, lane);
             cp_async_commit_wait_all();
             __syncthreads();

@@ -161,6 +161,14 @@ struct sgx_plan {
     void *d_frames = nullptr;               // istft: windowed time frames of a chunk of clips
     size_t frames_cap = 0;
     void *d_pair[2] = {nullptr, nullptr};   // binaural: complex STFTs of the two channels of a chunk of pairs
+    // Device-pointer istft / binaural calls return asynchronously but stage through the plan-owned scratch above: the last
+    // use is recorded here and the next call (possibly on another stream) waits for it before touching the scratch again.
+    cudaEvent_t scratch_done = nullptr;
+    void scratch_acquire(cudaStream_t st) {
+        if (!scratch_done) { if (cudaEventCreateWithFlags(&scratch_done, cudaEventDisableTiming) != cudaSuccess) { scratch_done = nullptr; return; } }
+        else cudaStreamWaitEvent(st, scratch_done, 0);
+    }
+    void scratch_release(cudaStream_t st) { if (scratch_done) cudaEventRecord(scratch_done, st); }
     size_t pair_cap = 0;
     std::vector<double> dense_t;     // chroma: dense matrix transposed to [out_len][n_bins]
     void *d_dense_t = nullptr;
@@ -186,6 +194,7 @@ struct sgx_plan {
         if (d_dense_t) cudaFree(d_dense_t);
         for (void *q : d_pair) if (q) cudaFree(q);
         if (d_frames) cudaFree(d_frames);
+        if (scratch_done) cudaEventDestroy(scratch_done);
         for (auto &s : slot) {
             if (s.d_in) cudaFree(s.d_in);
             if (s.d_out) cudaFree(s.d_out);
@@ -374,7 +383,11 @@ void build_tc_blob(sgx_plan &pl) {
 
 void select_family(sgx_plan &pl) {
     const sgx_plan_desc &d = pl.desc;
-    pl.fast400 = !pl.f64 && d.n_fft == 400 && d.hop_size == 160 && d.output != SGX_OUT_COMPLEX_STFT &&
+    // the n400 kernels take lg2.approx.ftz of max(v, eps): an eps that is an f32 denormal (floor_db below about -379 dB) would be
+    // flushed to zero and silent bins would come out as -inf instead of the floor, so such plans stay on the other families
+    const bool eps_denormal = d.amp == SGX_AMP_DECIBELS && d.has_floor_db &&
+                              static_cast<float>(std::pow(10.0, d.floor_db / 10.0)) < 1.17549435e-38f;
+    pl.fast400 = !pl.f64 && !eps_denormal && d.n_fft == 400 && d.hop_size == 160 && d.output != SGX_OUT_COMPLEX_STFT &&
                  (d.output != SGX_OUT_MFCC || static_cast<int>(pl.tab.n_bins) <= fast400_max_scratch_rows());
     if (pl.fast400) {
         pl.window_f32.resize(d.n_fft);
@@ -1045,6 +1058,7 @@ sgx_status sgx_plan_compute_binaural(sgx_plan *plan, sgx_binaural_cue cue, const
             ensure_slot(s, 2 * chunk * n_samples * es, chunk * cue_elems * es);
             st = s.s;
         }
+        pl.scratch_acquire(st);
         for (size_t p0 = 0; p0 < n_pairs; p0 += chunk) {
             const size_t np = std::min(chunk, n_pairs - p0);
             const void *ch[2] = {static_cast<const char *>(left) + p0 * clip_stride * es, static_cast<const char *>(right) + p0 * clip_stride * es};
@@ -1068,6 +1082,7 @@ sgx_status sgx_plan_compute_binaural(sgx_plan *plan, sgx_binaural_cue cue, const
             pl.last_launches += 1;
             if (host) ck(cudaMemcpyAsync(static_cast<char *>(out) + p0 * cue_elems * es, s.d_out, np * cue_elems * es, cudaMemcpyDeviceToHost, st), "D2H copy");
         }
+        pl.scratch_release(st);
         if (host) ck(cudaStreamSynchronize(st), "cudaStreamSynchronize");
     });
 }
@@ -1245,6 +1260,7 @@ sgx_status sgx_plan_istft(sgx_plan *plan, const void *stft, size_t n_clips, size
             ensure_slot(s, chunk * stft_bytes, chunk * out_len * es);
             st = s.s;
         }
+        pl.scratch_acquire(st);
         for (size_t c0 = 0; c0 < n_clips; c0 += chunk) {
             const size_t nc = std::min(chunk, n_clips - c0);
             const void *src = static_cast<const char *>(stft) + c0 * stft_bytes;
@@ -1260,6 +1276,7 @@ sgx_status sgx_plan_istft(sgx_plan *plan, const void *stft, size_t n_clips, size
             pl.last_launches += 1;
             if (host) ck(cudaMemcpyAsync(static_cast<char *>(out) + c0 * out_len * es, s.d_out, nc * out_len * es, cudaMemcpyDeviceToHost, st), "D2H copy");
         }
+        pl.scratch_release(st);
         if (host) ck(cudaStreamSynchronize(st), "cudaStreamSynchronize");
     });
 }

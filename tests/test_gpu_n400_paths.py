@@ -22,8 +22,8 @@ def P(centre=True, sr=16000.0):
     return sg.SpectrogramParams(sg.StftParams(400, 160, sg.WindowType.hanning(), centre), sr)
 
 
-def od(centre=True, **kw):
-    return oracle.Desc(dtype="f64", n_fft=400, hop=160, sample_rate=16000.0, centre=centre, **kw)
+def od(centre=True, dtype_override="f64", **kw):
+    return oracle.Desc(dtype=dtype_override, n_fft=400, hop=160, sample_rate=16000.0, centre=centre, **kw)
 
 
 def check(plan, odesc, x, amp):
@@ -138,3 +138,36 @@ def test_two_plans_on_two_streams():
     torch.cuda.synchronize()
     for oa, ob in outs:
         assert torch.equal(oa, ra) and torch.equal(ob, rb)
+
+
+def test_floor_below_the_f32_normal_range_stays_finite():
+    """LogParams only requires a finite floor. With floor_db = -400 the f32 epsilon 1e-40 is a denormal; silent bins
+    must return the floor (the reference's 10 log10(max(0, eps))), not -inf from a flush-to-zero log."""
+    x = np.zeros(8000, dtype=np.float32)
+    x[4000:4400] = make_signal("noise", 400, 16000.0, np.float32, seed=1)
+    plan = sg.SpectrogramPlanner().mel_plan(P(), sg.MelParams(128, 0.0, 8000.0), sg.LogParams(-400.0), "db", "float32")
+    assert not plan.kernel_name().startswith("r2c_fused_n400")          # routed off the ftz kernels
+    got = plan.compute(_torch().from_numpy(x).cuda()).data.cpu().numpy()
+    ref = oracle.Plan(od(dtype_override="f32", mapping="mel", n_bands=128, f_min=0.0, f_max=8000.0, amp="db", floor_db=-400.0)).compute(x)
+    assert np.all(np.isfinite(got)) and got.min() >= -400.5
+    silent = ref < -399.0
+    assert silent.any() and np.abs(got[silent] - ref[silent]).max() <= 0.5 and np.abs(got[~silent] - ref[~silent]).max() <= 1e-2
+    ok = sg.SpectrogramPlanner().mel_plan(P(), sg.MelParams(128, 0.0, 8000.0), sg.LogParams(-370.0), "db", "float32")
+    assert ok.kernel_name().startswith("r2c_fused_n400")               # normal eps: unchanged
+
+
+def test_fused_mfcc_on_magnitude_mel_matches_the_generic_family():
+    """output = MFCC with amp = magnitude fed power-mel to the DCT on the n400 family only. Both families must agree."""
+    from spectrograms_b200.plan import _NativePlan, _OUT_MFCC
+    x = make_signal("noise", 20000, 16000.0, np.float32, seed=4)
+    t = _torch().from_numpy(x).cuda()
+    outs = {}
+    for amp in ("magnitude", "power"):
+        n = _NativePlan(P(), "float32", "mel", sg.MelParams(128, 0.0, 8000.0), amp, None, _OUT_MFCC, sg.MfccParams(13, True, 0))
+        assert n.kernel_name() == "r2c_fused_n400"
+        a = n.compute_one(t).cpu().numpy()
+        n.force_generic(True)
+        b = n.compute_one(t).cpu().numpy()
+        assert rel_l2(a, b) <= TOL_F32
+        outs[amp] = a
+    assert rel_l2(outs["magnitude"], outs["power"]) > 0.1              # and the two scalings really differ
