@@ -17,6 +17,7 @@
 #include "binaural.cuh"
 #include "epilogue.cuh"
 #include "launch.hpp"
+#include "tcgen05.cuh"
 
 namespace sgx {
 namespace {
@@ -273,8 +274,44 @@ k_r2c_fused_pow2(const __grid_constant__ KParams p) {
     {
         constexpr int R = RPT, B = M / R;
         const long long base = (f0 + (pair ? fi : fl)) * p.hop - p.pad;
-        const bool vec_ok = p.vec_ok != 0;
-        if (vec_ok && base >= 0 && base + N <= p.n_samples) {
+        // Optional bulk-copy staging (p.vec_ok & 2; f32 two-pass form only): the tile's (FT - 1) hop + N contiguous samples are
+        // brought into shared memory by ONE cp.async.bulk (the TMA unit's 1-D form, SASS UBLKCP) tracked by an mbarrier, so each
+        // sample crosses L2 -> SM once per CTA instead of once per overlapping frame. Edge tiles keep the register path.
+        bool staged = false;
+        if constexpr (RPT == 32 && sizeof(T) == 4 && !PAIR) {
+            const long long base0 = f0 * p.hop - p.pad;
+            const long long span = static_cast<long long>(FT - 1) * p.hop + N;
+            T *sx = reinterpret_cast<T *>(zbuf + FT * ZS);
+            uint64_t *bar = reinterpret_cast<uint64_t *>(sx + ((FT - 1) * 1024 + N));      // sized for hop <= 1024 by the host
+            if ((p.vec_ok & 2) && nf == FT && base0 >= 0 && base0 + span <= p.n_samples &&
+                ((reinterpret_cast<uintptr_t>(x + base0)) & 15) == 0) {                  // block-uniform condition
+                staged = true;
+                if (tid == 0) {
+                    tc::mbar_init(bar, 1);
+                    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    const unsigned bytes = static_cast<unsigned>(span * sizeof(T));
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_addr(bar)), "r"(bytes) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tc::smem_addr(sx)),
+                                 "l"(x + base0), "r"(bytes), "r"(tc::smem_addr(bar))
+                                 : "memory");
+                }
+                tc::mbar_wait(bar, 0);
+                const C *xf = reinterpret_cast<const C *>(sx + fl * p.hop) + t;
+                const C *wf = reinterpret_cast<const C *>(win) + t;
+#pragma unroll
+                for (int j = 0; j < R; ++j) v[j] = xf[j * B];
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    const C w = ldg_cx<T>(wf + j * B);
+                    v[j] = {v[j].x * w.x, v[j].y * w.y};
+                }
+            }
+        }
+        if (staged) {
+        } else if ((p.vec_ok & 1) && base >= 0 && base + N <= p.n_samples) {
             // interior frame (all but the first / last few of a clip): no bounds logic
             const C *xf = reinterpret_cast<const C *>(x + base) + t;
             const C *wf = reinterpret_cast<const C *>(win) + t;
@@ -723,6 +760,12 @@ bool pow2_supported(size_t n_fft) {
     return n_fft >= 256 && n_fft <= 8192 && (n_fft & (n_fft - 1)) == 0;
 }
 int pow2_frames_per_tile(size_t n_fft, bool f64) { return ft_of(static_cast<int>(n_fft / 2), f64); }
+// extra dynamic shared memory of the bulk-copy staged variant (0: the size does not have one)
+size_t pow2_bulk_stage_bytes(size_t n_fft, size_t hop, bool f64) {
+    const int M = static_cast<int>(n_fft / 2);
+    if (f64 || rpt_of<float>(M) != 32 || hop > 1024 || hop % 4 != 0) return 0;
+    return sizeof(float) * (static_cast<size_t>(ft_of(M, false) - 1) * 1024 + n_fft) + 16;
+}
 int pow2_frame_elems(size_t n_fft, bool f64) {
     const int M = static_cast<int>(n_fft / 2);
     return zs_of(M, ft_of(M, f64), f64 ? rpt_of<double>(M) : rpt_of<float>(M));

@@ -39,6 +39,7 @@ bool fast400_tc_fits(int n_steps, int n_rounds, size_t b_floats);
 bool pow2_supported(size_t n_fft);
 int pow2_frames_per_tile(size_t n_fft, bool f64);
 int pow2_frame_elems(size_t n_fft, bool f64);
+size_t pow2_bulk_stage_bytes(size_t n_fft, size_t hop, bool f64);   // extra smem of the cp.async.bulk staged variant (0: none)
 cudaError_t launch_pow2(const KParams &p, bool f64, size_t smem_bytes, cudaStream_t stream);
 
 // standalone mfcc_from_log_mel (kernel_mfcc.cu): log_mel [n_clips][n_mels][n_frames] -> out [n_clips][rows][n_frames]

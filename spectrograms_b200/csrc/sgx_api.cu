@@ -672,7 +672,16 @@ void run_device(sgx_plan &pl, const void *d_samples, size_t n_clips, size_t n_sa
             // vector loads of (x[2n], x[2n+1]) pairs need pair-aligned addresses: aligned base, even stride, even hop and pad
             q.vec_ok = (reinterpret_cast<uintptr_t>(q.samples) % (2 * pl.esize) == 0 && clip_stride % 2 == 0 &&
                            pl.desc.hop_size % 2 == 0 && q.pad % 2 == 0) ? 1 : 0;
-            ck(launch_pow2(q, pl.f64, pl.pow2_smem, stream), "kernel launch (r2c_fused_pow2)");
+            // cp.async.bulk staging of the signal tile (measured, profiles/r2_pow2_experiments.md): opt-in through SGX_POW2_BULK=1
+            static const bool bulk_env = std::getenv("SGX_POW2_BULK") && std::atoi(std::getenv("SGX_POW2_BULK")) != 0;
+            size_t smem = pl.pow2_smem;
+            const size_t extra = bulk_env && pl.desc.output != SGX_OUT_COMPLEX_STFT ? pow2_bulk_stage_bytes(pl.desc.n_fft, pl.desc.hop_size, pl.f64) : 0;
+            if (extra && q.vec_ok && reinterpret_cast<uintptr_t>(q.samples) % 16 == 0 && clip_stride % 4 == 0 && q.pad % 4 == 0 &&
+                smem + extra <= 200 * 1024) {
+                q.vec_ok |= 2;
+                smem += extra;
+            }
+            ck(launch_pow2(q, pl.f64, smem, stream), "kernel launch (r2c_fused_pow2)");
         } else {
             ck(launch_generic(q, pl.f64, pl.smem_bytes, stream), "kernel launch (r2c_fused_generic)");
         }
