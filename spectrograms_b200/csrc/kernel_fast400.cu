@@ -63,8 +63,9 @@ __device__ __forceinline__ float4 lds_v4(unsigned a) {
 // j, j+8, j+16, j+24, which the permuted power tile hands over in ONE 16-byte read per column (4 wavefronts per warp
 // instruction = the minimum for 512 bytes). Each lane carries four independent accumulators (ILP 4), the row's weights
 // and bookkeeping are loaded once for four outputs, and every store instruction writes four 32-byte runs. Rows are sorted by column count
-// on the host, so a quad is nearly homogeneous; the per-lane predicate e < cnt keeps the exact reference arithmetic:
-// ascending columns, acc += T(w) * x with separate rounding (SparseMatrix::multiply_vec, src/spectrogram.rs:102-117).
+// on the host, so a quad is nearly homogeneous; the per-lane trip count keeps the reference's order of accumulation:
+// ascending columns, acc += T(w) * x (SparseMatrix::multiply_vec, src/spectrogram.rs:102-117), here with one fused
+// rounding per term (fmaf) -- never further from the exact sum than the reference's two roundings.
 // AMP: 0 power, 1 magnitude, 2 dB.
 // TO_SMEM: instead of storing to global memory, leave the scaled rows in a shared tile mtile[row][32] (same permuted
 // frame order as the power tile) for the fused DCT.
@@ -85,15 +86,30 @@ __device__ __forceinline__ void sparse_quads_epilogue_impl(const KParams &p, con
         const unsigned pe = pbase + __float_as_uint(rf.x);
         const unsigned wa = __float_as_uint(rf.z);
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        // per-lane trip count: the divergent loop branch masks finished rows, no predicate inside the body
-#pragma unroll 4
-        for (int e = 0; e < cnt; ++e) {
+        // per-lane trip count: the divergent loop branch masks finished rows, no predicate inside the body. Four columns per
+        // step: the row's weights are padded to a multiple of 4, so one 16-byte broadcast load serves four columns; the
+        // remainder (< 4 columns) runs column by column so that no tile element beyond the row is ever touched.
+        const int cnt4 = cnt >> 2;
+#pragma unroll 1
+        for (int e4 = 0; e4 < cnt4; ++e4) {
+            const float4 w = lds_v4(wa + 16u * e4);
+            const float4 x0 = lds_v4(pe + (kFT * 4u) * (4 * e4));
+            const float4 x1 = lds_v4(pe + (kFT * 4u) * (4 * e4 + 1));
+            const float4 x2 = lds_v4(pe + (kFT * 4u) * (4 * e4 + 2));
+            const float4 x3 = lds_v4(pe + (kFT * 4u) * (4 * e4 + 3));
+            a0 = fmaf(w.x, x0.x, a0); a1 = fmaf(w.x, x0.y, a1); a2 = fmaf(w.x, x0.z, a2); a3 = fmaf(w.x, x0.w, a3);
+            a0 = fmaf(w.y, x1.x, a0); a1 = fmaf(w.y, x1.y, a1); a2 = fmaf(w.y, x1.z, a2); a3 = fmaf(w.y, x1.w, a3);
+            a0 = fmaf(w.z, x2.x, a0); a1 = fmaf(w.z, x2.y, a1); a2 = fmaf(w.z, x2.z, a2); a3 = fmaf(w.z, x2.w, a3);
+            a0 = fmaf(w.w, x3.x, a0); a1 = fmaf(w.w, x3.y, a1); a2 = fmaf(w.w, x3.z, a2); a3 = fmaf(w.w, x3.w, a3);
+        }
+#pragma unroll 1
+        for (int e = 4 * cnt4; e < cnt; ++e) {
             const float w = lds_f32(wa + 4u * e);
             const float4 x = lds_v4(pe + (kFT * 4u) * e);
-            a0 = __fadd_rn(a0, __fmul_rn(w, x.x));
-            a1 = __fadd_rn(a1, __fmul_rn(w, x.y));
-            a2 = __fadd_rn(a2, __fmul_rn(w, x.z));
-            a3 = __fadd_rn(a3, __fmul_rn(w, x.w));
+            a0 = fmaf(w, x.x, a0);
+            a1 = fmaf(w, x.y, a1);
+            a2 = fmaf(w, x.z, a2);
+            a3 = fmaf(w, x.w, a3);
         }
         const int row = __float_as_int(rf.w);
         if (row >= 0) {
