@@ -79,5 +79,93 @@ __device__ __forceinline__ float finish_value(float acc, float eps) {
     return acc;
 }
 
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ float lds_f32(unsigned a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float4 lds_v4(unsigned a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+
+// Sparse filterbank rows (mel triangles, loghz interpolation pairs: every row's columns are contiguous), "quad"
+// schedule: one warp step = 4 rows x 32 frames. Lane (s, j) = (lane >> 3, lane & 7) owns row s of the quad and frames
+// j, j+8, j+16, j+24, which the permuted power tile hands over in ONE 16-byte read per column (4 wavefronts per warp
+// instruction = the minimum for 512 bytes). Each lane carries four independent accumulators (ILP 4), the row's weights
+// and bookkeeping are loaded once for four outputs, and every store instruction writes four 32-byte runs. Rows are sorted by column count
+// on the host, so a quad is nearly homogeneous; the per-lane trip count keeps the reference's order of accumulation:
+// ascending columns, acc += T(w) * x (SparseMatrix::multiply_vec, src/spectrogram.rs:102-117), here with one fused
+// rounding per term (fmaf) -- never further from the exact sum than the reference's two roundings.
+// AMP: 0 power, 1 magnitude, 2 dB.
+// TO_SMEM: instead of storing to global memory, leave the scaled rows in a shared tile mtile[row][32] (same permuted
+// frame order as the power tile) for the fused DCT.
+template <int AMP, bool TO_SMEM, bool FULL>
+__device__ __forceinline__ void sparse_quads_epilogue_impl(const KParams &p, const float *ptile, const int4 *s_quads, int q0, int q1, int qstep,
+                                                           float *out_clip_frame, float *mtile, int nf, int lane) {
+    const float eps = static_cast<float>(p.eps);
+    const int s = lane >> 3, j = lane & 7;
+    const unsigned pbase = smem_u32(ptile) + 16u * j;             // columns 4j..4j+3 = frames j, j+8, j+16, j+24
+    const unsigned qbase = smem_u32(s_quads);
+    const unsigned ors4 = 4u * static_cast<unsigned>(p.out_row_stride);
+    char *ob = reinterpret_cast<char *>(out_clip_frame) + 4 * j;
+#pragma unroll 1
+    for (int qi = q0; qi < q1; qi += qstep) {
+        const float4 rf = lds_v4(qbase + 16u * (4 * qi + s));      // {byte offset of P[c0], cnt, weights address, row}
+        const int cnt = __float_as_int(rf.y);
+        const unsigned pe = pbase + __float_as_uint(rf.x);
+        const unsigned wa = __float_as_uint(rf.z);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        // per-lane trip count: the divergent loop branch masks finished rows, no predicate inside the body. Four columns per
+        // step: the row's weights are padded to a multiple of 4, so one 16-byte broadcast load serves four columns; the
+        // remainder (< 4 columns) runs column by column so that no tile element beyond the row is ever touched.
+        const int cnt4 = cnt >> 2;
+#pragma unroll 1
+        for (int e4 = 0; e4 < cnt4; ++e4) {
+            const float4 w = lds_v4(wa + 16u * e4);
+            const float4 x0 = lds_v4(pe + (kFT * 4u) * (4 * e4));
+            const float4 x1 = lds_v4(pe + (kFT * 4u) * (4 * e4 + 1));
+            const float4 x2 = lds_v4(pe + (kFT * 4u) * (4 * e4 + 2));
+            const float4 x3 = lds_v4(pe + (kFT * 4u) * (4 * e4 + 3));
+            a0 = fmaf(w.x, x0.x, a0); a1 = fmaf(w.x, x0.y, a1); a2 = fmaf(w.x, x0.z, a2); a3 = fmaf(w.x, x0.w, a3);
+            a0 = fmaf(w.y, x1.x, a0); a1 = fmaf(w.y, x1.y, a1); a2 = fmaf(w.y, x1.z, a2); a3 = fmaf(w.y, x1.w, a3);
+            a0 = fmaf(w.z, x2.x, a0); a1 = fmaf(w.z, x2.y, a1); a2 = fmaf(w.z, x2.z, a2); a3 = fmaf(w.z, x2.w, a3);
+            a0 = fmaf(w.w, x3.x, a0); a1 = fmaf(w.w, x3.y, a1); a2 = fmaf(w.w, x3.z, a2); a3 = fmaf(w.w, x3.w, a3);
+        }
+#pragma unroll 1
+        for (int e = 4 * cnt4; e < cnt; ++e) {
+            const float w = lds_f32(wa + 4u * e);
+            const float4 x = lds_v4(pe + (kFT * 4u) * e);
+            a0 = fmaf(w, x.x, a0);
+            a1 = fmaf(w, x.y, a1);
+            a2 = fmaf(w, x.z, a2);
+            a3 = fmaf(w, x.w, a3);
+        }
+        const int row = __float_as_int(rf.w);
+        if (row >= 0) {
+            const float v0 = finish_value<AMP>(a0, eps), v1 = finish_value<AMP>(a1, eps);
+            const float v2 = finish_value<AMP>(a2, eps), v3 = finish_value<AMP>(a3, eps);
+            if (TO_SMEM) {
+                *reinterpret_cast<float4 *>(mtile + row * kFT + 4 * j) = make_float4(v0, v1, v2, v3);
+                continue;
+            }
+            char *orow = ob + static_cast<size_t>(static_cast<unsigned>(row)) * ors4;
+            if (FULL || j < nf) *reinterpret_cast<float *>(orow) = v0;
+            if (FULL || j + 8 < nf) *reinterpret_cast<float *>(orow + 32) = v1;
+            if (FULL || j + 16 < nf) *reinterpret_cast<float *>(orow + 64) = v2;
+            if (FULL || j + 24 < nf) *reinterpret_cast<float *>(orow + 96) = v3;
+        }
+    }
+}
+
+template <int AMP, bool TO_SMEM>
+__device__ __forceinline__ void sparse_quads_epilogue(const KParams &p, const float *ptile, const int4 *s_quads, int q0, int q1, int qstep,
+                                                      float *out_clip_frame, float *mtile, int nf, int lane) {
+    if (nf == kFT) sparse_quads_epilogue_impl<AMP, TO_SMEM, true>(p, ptile, s_quads, q0, q1, qstep, out_clip_frame, mtile, nf, lane);
+    else sparse_quads_epilogue_impl<AMP, TO_SMEM, false>(p, ptile, s_quads, q0, q1, qstep, out_clip_frame, mtile, nf, lane);
+}
+
 }  // namespace f400
 }  // namespace sgx

@@ -130,8 +130,9 @@ struct sgx_plan {
     void *d_dct = nullptr, *d_lifter = nullptr, *d_dct_folded = nullptr;
     std::vector<double> dct_folded;  // [tasks][n_mels/2][4]
     int dct_tasks = 0;
-    int *d_row_ptr = nullptr, *d_col = nullptr, *d_wofs = nullptr;
+    int *d_row_ptr = nullptr, *d_col = nullptr, *d_wofs = nullptr, *d_wofs_tm = nullptr;
     std::vector<int> wofs;           // quad schedule blob of the sparse mapping (r2c_fused_n400)
+    std::vector<int> wofs_tm;        // the same quads in one descending-cost list (r2c_fused_n400_tm)
     // generic-family geometry
     int FT = 1, buf_elems = 0, frame_stride = 0, tile_stride = 0;
     size_t smem_bytes = 0;
@@ -146,6 +147,8 @@ struct sgx_plan {
     size_t pow2_smem = 0;
     bool fast400_sparse = false;     // ... with the shared-memory sparse table
     bool fast400_tc = false;         // ... on the TMEM / tcgen05 kernel (r2c_fused_n400_tc)
+    bool fast400_tm = false;         // ... on the TMEM-exchange kernel (r2c_fused_n400_tm): sparse mel / loghz spectrogram outputs
+    int tm_mode = -1;                // epilogue warps per group of r2c_fused_n400_tm (0, 1, 2); -1: kernel not used
     int tc_mode = -1;                // sgx_plan_set_tensor_cores: -1 auto (dense mappings only), 0 never, 1 whenever available
     std::vector<int> tc_blob;        // step blob of r2c_fused_n400_tc (launch.hpp)
     int tc_steps = 0, tc_rounds = 0;
@@ -187,6 +190,7 @@ struct sgx_plan {
         if (d_row_ptr) cudaFree(d_row_ptr);
         if (d_col) cudaFree(d_col);
         if (d_wofs) cudaFree(d_wofs);
+        if (d_wofs_tm) cudaFree(d_wofs_tm);
         if (d_tc_blob) cudaFree(d_tc_blob);
         if (d_lane_rows) cudaFree(d_lane_rows);
         if (d_row_desc) cudaFree(d_row_desc);
@@ -281,6 +285,11 @@ void build_lane_rows(sgx_plan &pl) {
 // r2c_fused_n400_tc is measured slower than the CUDA-core kernel for the banded mel / loghz filterbanks (2.1 ms against
 // 1.5 ms per configs[1] step: ~80 MMAs of ~125 cycles each per 128 frames) and faster for the dense ERB projection, whose
 // cost on CUDA cores grows with n_filters x 201 while the MMA count does not. Auto therefore picks it for ERB only.
+// r2c_fused_n400_tm: TMEM as the exchange medium of the two FFT passes (kernel_n400_tm.cu)
+bool use_tm(const sgx_plan &pl) {
+    return pl.fast400 && pl.fast400_tm && !pl.force_generic && pl.tm_mode >= 0 && pl.tc_mode != 1;
+}
+
 bool use_tc(const sgx_plan &pl) {
     if (!pl.fast400 || !pl.fast400_tc || pl.force_generic || pl.tc_mode == 0) return false;
     return pl.tc_mode == 1 || pl.desc.mapping == SGX_MAP_ERB;
@@ -418,6 +427,7 @@ void select_family(sgx_plan &pl) {
     bool contiguous = csr;
     int padded = 0;
     pl.wofs.clear();
+    pl.wofs_tm.clear();
     if (csr) {
         const int W = fast400_warps();
         const size_t nb = pl.tab.n_bins;
@@ -438,34 +448,39 @@ void select_family(sgx_plan &pl) {
         for (int q = 0; q < nq; ++q)
             for (int k = 0; k < 4; ++k)
                 if (order[4 * q + k] >= 0) qmax[q] = std::max(qmax[q], cnt[order[4 * q + k]]);
-        std::vector<std::vector<int>> per_warp(W);
-        std::vector<long> load(W, 0);
-        for (int q = 0; q < nq; ++q) {          // quads are already in descending cost order
-            int best = 0;
-            for (int w = 1; w < W; ++w) if (load[w] < load[best]) best = w;
-            per_warp[best].push_back(q);
-            load[best] += 26 + 16 * qmax[q];
-        }
-        const int hdr = (1 + W + 1 + nq + 3) & ~3;
-        std::vector<int> blob(static_cast<size_t>(hdr) + 16 * static_cast<size_t>(nq), 0);
-        blob[0] = nq;
-        int idx = 0;
-        for (int w = 0; w < W; ++w) {
-            blob[1 + w] = idx;
-            for (int q : per_warp[w]) {
-                blob[1 + W + 1 + idx] = qmax[q];
-                for (int k = 0; k < 4; ++k) {
-                    const int r = order[4 * q + k];
-                    int *e = &blob[static_cast<size_t>(hdr) + 4 * (4 * static_cast<size_t>(idx) + k)];
-                    e[0] = (r >= 0 && cnt[r]) ? pl.tab.col[pl.tab.row_ptr[r]] : 0;
-                    e[1] = r >= 0 ? cnt[r] : 0;
-                    e[2] = r >= 0 ? wo[r] : 0;
-                    e[3] = r;
-                }
-                ++idx;
+        auto make_blob = [&](int W) {
+            std::vector<std::vector<int>> per_warp(W);
+            std::vector<long> load(W, 0);
+            for (int q = 0; q < nq; ++q) {          // quads are already in descending cost order
+                int best = 0;
+                for (int w = 1; w < W; ++w) if (load[w] < load[best]) best = w;
+                per_warp[best].push_back(q);
+                load[best] += 26 + 16 * qmax[q];
             }
-        }
-        blob[1 + W] = idx;
+            const int hdr = (1 + W + 1 + nq + 3) & ~3;
+            std::vector<int> blob(static_cast<size_t>(hdr) + 16 * static_cast<size_t>(nq), 0);
+            blob[0] = nq;
+            int idx = 0;
+            for (int w = 0; w < W; ++w) {
+                blob[1 + w] = idx;
+                for (int q : per_warp[w]) {
+                    blob[1 + W + 1 + idx] = qmax[q];
+                    for (int k = 0; k < 4; ++k) {
+                        const int r = order[4 * q + k];
+                        int *e = &blob[static_cast<size_t>(hdr) + 4 * (4 * static_cast<size_t>(idx) + k)];
+                        e[0] = (r >= 0 && cnt[r]) ? pl.tab.col[pl.tab.row_ptr[r]] : 0;
+                        e[1] = r >= 0 ? cnt[r] : 0;
+                        e[2] = r >= 0 ? wo[r] : 0;
+                        e[3] = r;
+                    }
+                    ++idx;
+                }
+            }
+            blob[1 + W] = idx;
+            return blob;
+        };
+        std::vector<int> blob = make_blob(W);
+        pl.wofs_tm = make_blob(1);      // r2c_fused_n400_tm: all quads in descending cost order, dealt round-robin by the kernel
         pl.wofs = blob;
         padded = std::max(padded, 4);
         pl.sparse_quads = nq;
@@ -499,6 +514,11 @@ void select_family(sgx_plan &pl) {
     pl.fast400_sparse = pl.fast400 && csr && contiguous && fast400_sparse_fits(pl.sparse_quads, pl.sparse_weights);
     build_tc_blob(pl);
     pl.fast400_tc = pl.tc_steps > 0;
+    pl.fast400_tm = pl.fast400 && csr && contiguous && d.output == SGX_OUT_SPECTROGRAM && fast400_tm_fits(pl.sparse_quads, pl.sparse_weights);
+    {
+        const char *e = std::getenv("SGX_N400_TM");
+        pl.tm_mode = e ? std::atoi(e) : -1;
+    }
     pl.kernel_name = pl.fast400 ? "r2c_fused_n400" : pl.pow2 ? "r2c_fused_pow2" : "r2c_fused_generic";
     // folded DCT basis for the fused MFCC epilogue: B[c][n-1-i] = (-1)^c B[c][i] -> half basis, tasks of 4 coefficients of
     // one parity: [task][i < n/2][4], even-coefficient tasks first
@@ -563,6 +583,7 @@ void ensure_device(sgx_plan &pl) {
     pl.d_row_ptr = upload_int(pl.tab.row_ptr);
     pl.d_col = upload_int(pl.tab.col);
     pl.d_wofs = upload_int(pl.wofs);
+    pl.d_wofs_tm = upload_int(pl.wofs_tm);
     pl.d_tc_blob = upload_int(pl.tc_blob);
     pl.d_lane_rows = upload_int(pl.lane_rows);
     pl.d_row_desc = upload_int(pl.row_desc);
@@ -656,6 +677,12 @@ void run_device(sgx_plan &pl, const void *d_samples, size_t n_clips, size_t n_sa
         if (pl.fast400 && !pl.force_generic) {
             // 8-byte vector loads need an 8-byte aligned base and an even clip stride
             q.vec_ok = (reinterpret_cast<uintptr_t>(q.samples) % 8 == 0 && clip_stride % 2 == 0) ? 1 : 0;
+            if (use_tm(pl)) {
+                q.sched = pl.d_wofs_tm;
+                ck(launch_fast400_tm(q, pl.window_f32.data(), pl.sparse_quads, pl.sparse_weights, pl.tm_mode, pl.sm_count, stream), "kernel launch (r2c_fused_n400_tm)");
+                pl.last_launches += 1;
+                continue;
+            }
             if (use_tc(pl)) {
                 q.sched = pl.d_tc_blob;
                 ck(launch_fast400_tc(q, pl.window_f32.data(), pl.tc_steps, pl.tc_rounds, pl.tc_b_floats, pl.sm_count, stream), "kernel launch (r2c_fused_n400_tc)");
@@ -801,6 +828,7 @@ sgx_status sgx_plan_filterbank(const sgx_plan *plan, double *dense_out, size_t *
 const char *sgx_plan_kernel_name(const sgx_plan *plan) {
     if (!plan) return "";
     if (plan->force_generic) return "r2c_fused_generic";
+    if (use_tm(*plan)) return "r2c_fused_n400_tm";
     if (use_tc(*plan)) return "r2c_fused_n400_tc";
     return plan->kernel_name.c_str();
 }
