@@ -168,6 +168,13 @@ sgx_status sgx_plan_force_generic(sgx_plan *plan, int force);
  * Test / measurement hook. */
 sgx_status sgx_plan_set_tensor_cores(sgx_plan *plan, int enable);
 
+/* Tensor memory as the exchange medium between the two FFT passes of the n_fft = 400 / hop = 160 f32 family
+ * (r2c_fused_n400_tm; the per-frame FFT of SpectrogramPlan::compute, src/spectrogram.rs:240-294, src/fft_backend.rs:423-431):
+ * -1 = automatic (default: used wherever the plan supports it -- sparse mel / loghz spectrogram outputs), 0 = never (the
+ * shared-memory exchange of r2c_fused_n400), 1 = whenever the plan supports it. Results are bit-identical either way.
+ * Test / measurement hook. */
+sgx_status sgx_plan_set_tmem_exchange(sgx_plan *plan, int enable);
+
 /*
  * The batched entry point: for c in 0..n_clips { plan.compute_into(&samples[c], &mut out[c]) }  (:414-477,
  * :1548-1580; the reference has no batch API -- batching is a user loop, src/lib.rs:228-235).

@@ -16,7 +16,7 @@ SGX_OK, SGX_INVALID_INPUT, SGX_DIMENSION_MISMATCH, SGX_BACKEND_ERROR, SGX_INTERN
 EXPORTS = [
     "sgx_last_error_message", "sgx_last_dimension_mismatch", "sgx_version", "sgx_plan_create", "sgx_plan_destroy",
     "sgx_plan_output_shape", "sgx_plan_axes", "sgx_plan_window", "sgx_plan_filterbank", "sgx_plan_kernel_name",
-    "sgx_plan_last_launch_count", "sgx_plan_force_generic", "sgx_plan_set_tensor_cores", "sgx_plan_compute_batch", "sgx_plan_compute_frame",
+    "sgx_plan_last_launch_count", "sgx_plan_force_generic", "sgx_plan_set_tensor_cores", "sgx_plan_set_tmem_exchange", "sgx_plan_compute_batch", "sgx_plan_compute_frame",
     "sgx_mfcc_from_log_mel", "sgx_rfft", "sgx_chroma_from_spectrogram", "sgx_chroma_filterbank",
     "sgx_binaural_from_stft", "sgx_plan_compute_binaural", "sgx_plan_istft", "sgx_irfft",
     "sgx_fft_planner_create", "sgx_fft_planner_destroy", "sgx_fft_planner_cached_plans", "sgx_fft_planner_rfft",
@@ -69,6 +69,7 @@ def lib() -> C.CDLL:
     L.sgx_plan_last_launch_count.restype = sz
     L.sgx_plan_force_generic.argtypes = [vp, i]
     L.sgx_plan_set_tensor_cores.argtypes = [vp, i]
+    L.sgx_plan_set_tmem_exchange.argtypes = [vp, i]
     L.sgx_plan_compute_batch.argtypes = [vp, vp, sz, sz, sz, vp, sz, sz, sz, vp]
     L.sgx_plan_compute_frame.argtypes = [vp, vp, sz, sz, vp, vp]
     L.sgx_mfcc_from_log_mel.argtypes = [i, vp, sz, sz, sz, sz, i, sz, vp, i, vp]

@@ -160,6 +160,73 @@ __device__ __forceinline__ void sparse_quads_epilogue_impl(const KParams &p, con
     }
 }
 
+// The same rows, software-pipelined for the kernels whose power tile is followed by zero rows (r2c_fused_n400_tm): every
+// row of a quad carries the quad's longest count rounded up to 4 columns (zero weights behind the row's own), all column
+// steps are 4 wide, and the first step of quad i+1 -- its descriptor, four power-tile reads and four weights -- is loaded
+// while quad i is multiplied, scaled and stored. The shared-memory latency leaves the per-quad dependency chain.
+template <int AMP, bool FULL>
+__device__ __forceinline__ void sparse_quads_pipelined_impl(const KParams &p, const float *ptile, const int4 *s_quads, int q0, int q1,
+                                                            float *out_clip_frame, int nf, int lane) {
+    if (q0 >= q1) return;
+    const float eps = static_cast<float>(p.eps);
+    const int s = lane >> 3, j = lane & 7;
+    const unsigned pbase = smem_u32(ptile) + 16u * j;             // columns 4j..4j+3 = frames j, j+8, j+16, j+24
+    const unsigned qbase = smem_u32(s_quads) + 16u * s;
+    const unsigned ors4 = 4u * static_cast<unsigned>(p.out_row_stride);
+    char *ob = reinterpret_cast<char *>(out_clip_frame) + 4 * j;
+    constexpr unsigned kRow = kFT * 4u;
+    float4 rf = lds_v4(qbase + 64u * q0);                          // {byte offset of P[c0], cnt (multiple of 4), weights address, row}
+    float4 rf2 = lds_v4(qbase + 64u * (q0 + 1 < q1 ? q0 + 1 : q0));
+    unsigned pe = pbase + __float_as_uint(rf.x);
+    float4 w = lds_v4(__float_as_uint(rf.z));
+    float4 x0 = lds_v4(pe), x1 = lds_v4(pe + kRow), x2 = lds_v4(pe + 2 * kRow), x3 = lds_v4(pe + 3 * kRow);
+#pragma unroll 1
+    for (int qi = q0; qi < q1; ++qi) {
+        const float4 cur = rf;
+        const unsigned pcur = pe;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        a0 = fmaf(w.x, x0.x, a0); a1 = fmaf(w.x, x0.y, a1); a2 = fmaf(w.x, x0.z, a2); a3 = fmaf(w.x, x0.w, a3);
+        a0 = fmaf(w.y, x1.x, a0); a1 = fmaf(w.y, x1.y, a1); a2 = fmaf(w.y, x1.z, a2); a3 = fmaf(w.y, x1.w, a3);
+        a0 = fmaf(w.z, x2.x, a0); a1 = fmaf(w.z, x2.y, a1); a2 = fmaf(w.z, x2.z, a2); a3 = fmaf(w.z, x2.w, a3);
+        a0 = fmaf(w.w, x3.x, a0); a1 = fmaf(w.w, x3.y, a1); a2 = fmaf(w.w, x3.z, a2); a3 = fmaf(w.w, x3.w, a3);
+        // next quad: first step in flight while this one finishes (the last iteration re-reads its own, harmlessly)
+        rf = rf2;
+        rf2 = lds_v4(qbase + 64u * (qi + 2 < q1 ? qi + 2 : q1 - 1));
+        pe = pbase + __float_as_uint(rf.x);
+        const float4 wn = lds_v4(__float_as_uint(rf.z));
+        const float4 y0 = lds_v4(pe), y1 = lds_v4(pe + kRow), y2 = lds_v4(pe + 2 * kRow), y3 = lds_v4(pe + 3 * kRow);
+        const int steps = __float_as_int(cur.y) >> 2;
+#pragma unroll 1
+        for (int e4 = 1; e4 < steps; ++e4) {                       // rows longer than four columns (warp-uniform count)
+            const float4 we = lds_v4(__float_as_uint(cur.z) + 16u * e4);
+            const float4 z0 = lds_v4(pcur + kRow * (4 * e4)), z1 = lds_v4(pcur + kRow * (4 * e4 + 1));
+            const float4 z2 = lds_v4(pcur + kRow * (4 * e4 + 2)), z3 = lds_v4(pcur + kRow * (4 * e4 + 3));
+            a0 = fmaf(we.x, z0.x, a0); a1 = fmaf(we.x, z0.y, a1); a2 = fmaf(we.x, z0.z, a2); a3 = fmaf(we.x, z0.w, a3);
+            a0 = fmaf(we.y, z1.x, a0); a1 = fmaf(we.y, z1.y, a1); a2 = fmaf(we.y, z1.z, a2); a3 = fmaf(we.y, z1.w, a3);
+            a0 = fmaf(we.z, z2.x, a0); a1 = fmaf(we.z, z2.y, a1); a2 = fmaf(we.z, z2.z, a2); a3 = fmaf(we.z, z2.w, a3);
+            a0 = fmaf(we.w, z3.x, a0); a1 = fmaf(we.w, z3.y, a1); a2 = fmaf(we.w, z3.z, a2); a3 = fmaf(we.w, z3.w, a3);
+        }
+        const int row = __float_as_int(cur.w);
+        if (row >= 0) {
+            const float v0 = finish_value<AMP>(a0, eps), v1 = finish_value<AMP>(a1, eps);
+            const float v2 = finish_value<AMP>(a2, eps), v3 = finish_value<AMP>(a3, eps);
+            char *orow = ob + static_cast<size_t>(static_cast<unsigned>(row)) * ors4;
+            if (FULL || j < nf) *reinterpret_cast<float *>(orow) = v0;
+            if (FULL || j + 8 < nf) *reinterpret_cast<float *>(orow + 32) = v1;
+            if (FULL || j + 16 < nf) *reinterpret_cast<float *>(orow + 64) = v2;
+            if (FULL || j + 24 < nf) *reinterpret_cast<float *>(orow + 96) = v3;
+        }
+        w = wn; x0 = y0; x1 = y1; x2 = y2; x3 = y3;
+    }
+}
+
+template <int AMP>
+__device__ __forceinline__ void sparse_quads_pipelined(const KParams &p, const float *ptile, const int4 *s_quads, int q0, int q1,
+                                                       float *out_clip_frame, int nf, int lane) {
+    if (nf == kFT) sparse_quads_pipelined_impl<AMP, true>(p, ptile, s_quads, q0, q1, out_clip_frame, nf, lane);
+    else sparse_quads_pipelined_impl<AMP, false>(p, ptile, s_quads, q0, q1, out_clip_frame, nf, lane);
+}
+
 template <int AMP, bool TO_SMEM>
 __device__ __forceinline__ void sparse_quads_epilogue(const KParams &p, const float *ptile, const int4 *s_quads, int q0, int q1, int qstep,
                                                       float *out_clip_frame, float *mtile, int nf, int lane) {

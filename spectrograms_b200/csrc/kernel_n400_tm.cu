@@ -6,22 +6,22 @@
 // path (tcgen05.st 794 B/clk, tcgen05.ld 57 B/clk per SM, tools/ubench/tmem_probe.cu), so the exchange leaves the L1 pipe,
 // the 52 KB exchange buffer leaves shared memory, and four tiles instead of two are in flight per SM.
 //
-//   one persistent CTA per SM = 4 groups; group q = the warps with warp_id % 4 == q (SM sub-partition q, TMEM lanes
-//   32q .. 32q+31). A group walks its own tiles of 32 consecutive frames (lane = frame = TMEM lane) and never synchronises
-//   with the other groups: the four sub-partitions run their FFT-bound and load/store-bound phases out of step.
+//   one persistent CTA per SM = 4 groups x 4 warps; group q = the warps with warp_id % 4 == q (SM sub-partition q, TMEM
+//   lanes 32q .. 32q+31). A group walks its own tiles of 32 consecutive frames (lane = frame = TMEM lane) and never
+//   synchronises with the other groups: the four sub-partitions run their FFT-bound and load/store-bound phases out of step.
+//   Two group barriers per tile:
 //
-//   FFT warps (4 per group)
-//     pass 1   window + 20-point real-pair DFT in registers (fft400_core.cuh) -> Y[k1][n2] into TMEM columns 0..399 of the
-//              thread's own lane (tcgen05.st, SASS STTM)
-//     pass 2   tcgen05.ld (LDTM) of one Y row -> twiddle + 20-point DFT -> |X|^2 into the group's power tile P[bin][frame]
-//              in shared memory
-//   filterbank warps (EW per group; EW = 0: the FFT warps do this themselves after a group barrier)
-//     sparse mel / loghz rows from the power tile (the quad schedule of kernel_fast400.cu) -> sqrt / dB -> row stores.
-//     They hand the tile back through a pair of named barriers (full / free), so the FFT warps start pass 1 of the next
-//     tile while the rows of the previous one are still being written: the FP32 pipe of the sub-partition does not idle
-//     during the load/store-bound epilogue.
+//   phase B   prefetch (cp.async) of the next tile's samples, then pass 2 of tile t: tcgen05.ld (LDTM) of one Y row ->
+//             twiddle + 20-point DFT -> |X|^2 into the group's power tile P[bin][frame] in shared memory
+//   phase A   the filterbank rows of tile t (sparse mel / loghz rows from the power tile, the quad schedule of
+//             kernel_fast400.cu -> sqrt / dB -> row stores) AND pass 1 of tile t+1 (window + 20-point real-pair DFT in
+//             registers -> Y[k1][n2] into TMEM columns 0..399 of the thread's own lane, tcgen05.st / STTM) share one
+//             phase: half the warps start with their rows, the other half with their FFT tasks, so the load/store-bound
+//             rows of one warp fill the issue slots the FP32-bound butterflies of another leave free.
 //
 // Arithmetic is the arithmetic of kernel_fast400.cu (same task functions, same epilogue); only where Y travels differs.
+// Measured steps of this design (dedicated filterbank warps behind full / free barriers lost: one or two such warps per
+// group are latency bound) are in profiles/r2_n400_tm_experiments.md.
 #include "fast400_common.cuh"
 #include "launch.hpp"
 #include "tcgen05.cuh"
@@ -32,38 +32,38 @@ namespace {
 using namespace f400;
 
 constexpr int kGroups = 4;
-constexpr int kFftWarpsPerGroup = 4;
-constexpr int kFftWarps = kGroups * kFftWarpsPerGroup;      // 16
-constexpr int kFftGroupThreads = kFftWarpsPerGroup * 32;    // 128
+constexpr int kMaxGroupWarps = 8;
 constexpr uint32_t kTmemCols = 512;                         // Y needs 400 columns; allocations are powers of two
+constexpr int kPadRows = 8;                                 // zero rows behind the power tile (padded quad rows read them)
+constexpr int kPWordsTm = (kBins + kPadRows) * kFT;
 
 struct TmSmem {
     float *sig;        // [4][kSigWords]   one signal tile per group
-    float *ptile;      // [4][kPWords]     one power tile per group
+    float *ptile;      // [4][kPWordsTm]   one power tile per group (+ zero rows)
     float *win;        // [400]
-    int4 *quads;       // [4 * n_quads]    {byte offset of P[c0], cnt, weights address, row}
+    int4 *quads;       // [4 * n_quads]    {byte offset of P[c0], padded cnt, weights address, row}
+    int *qrange;       // [group warps + 1] quad range of every warp of a group
     float *w;          // padded weights
     uint32_t *tmem_ptr;
 };
 
 __host__ __device__ inline size_t tm_smem_bytes(int n_quads, int padded_weights) {
-    return sizeof(float) * (kGroups * (kSigWords + kPWords) + kN) + sizeof(int4) * 4 * static_cast<size_t>(n_quads) +
-           sizeof(float) * static_cast<size_t>(padded_weights + 8) + 16;
+    return sizeof(float) * (kGroups * (kSigWords + kPWordsTm) + kN) + sizeof(int4) * 4 * static_cast<size_t>(n_quads) +
+           sizeof(int) * 12 + sizeof(float) * static_cast<size_t>(padded_weights + 8) + 16;
 }
 
 __device__ __forceinline__ TmSmem carve(unsigned char *base, int n_quads, int padded_weights) {
     TmSmem s;
     size_t o = 0;
     s.sig = reinterpret_cast<float *>(base + o);        o += sizeof(float) * kGroups * kSigWords;
-    s.ptile = reinterpret_cast<float *>(base + o);      o += sizeof(float) * kGroups * kPWords;
+    s.ptile = reinterpret_cast<float *>(base + o);      o += sizeof(float) * kGroups * kPWordsTm;
     s.quads = reinterpret_cast<int4 *>(base + o);       o += sizeof(int4) * 4 * static_cast<size_t>(n_quads);
     s.win = reinterpret_cast<float *>(base + o);        o += sizeof(float) * kN;
+    s.qrange = reinterpret_cast<int *>(base + o);       o += sizeof(int) * 12;
     s.w = reinterpret_cast<float *>(base + o);          o += sizeof(float) * static_cast<size_t>(padded_weights + 8);
     s.tmem_ptr = reinterpret_cast<uint32_t *>(base + o);
     return s;
 }
-
-__device__ __forceinline__ void bar_arrive(int id, int threads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
 // ---- pass 1, one task = (frame = lane, column pair t): f400::pass1_task with Y going to the thread's TMEM lane.
 // Y layout (columns): row 0 = (Y[0][n2], Y[10][n2]) pairs, rows 1..9 = Y[k1][n2] complex; column 40 * row + 2 * n2 (+1).
@@ -91,14 +91,30 @@ __device__ __forceinline__ void pass1_tm(const float *__restrict__ sig, const fl
     }
 }
 
-// ---- pass 2, one task = (frame = lane, k1): Y row from TMEM -> twiddle -> DFT20 -> |X|^2 into P[bin][frame]
-__device__ __forceinline__ void pass2_tm(uint32_t ybase, const float2 *__restrict__ tw2, float *__restrict__ ptile, int f, int k1) {
-    uint32_t q[40];
+// ---- pass 2, one task = (frame = lane, k1): Y row from TMEM -> twiddle -> DFT20 -> |X|^2 into P[bin][frame].
+// The TMEM read port of a sub-partition delivers 14 B/clk (a 40-column row of 32 lanes takes ~360 cycles); the other warps of
+// the group cover it. (Requesting the warp's next row while the butterfly runs was measured slower: 1.37 against 1.32 ms.)
+__device__ __forceinline__ void y_row_request(uint32_t ybase, int k1, uint32_t (&q)[40]) {
     const uint32_t row = ybase + ((k1 == 0 || k1 == 10) ? 0 : 40 * k1);
     tc::ld32(row, q);
     tc::ld8(row + 32, q + 32);
-    tc::wait_ld();
-    float2 v[20];
+}
+// tcgen05.wait::ld, with the row registers as read-write operands so that no use of them can be scheduled above the wait
+__device__ __forceinline__ void y_row_wait(uint32_t (&q)[40]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(q[0]), "+r"(q[1]), "+r"(q[2]), "+r"(q[3]), "+r"(q[4]), "+r"(q[5]), "+r"(q[6]), "+r"(q[7]), "+r"(q[8]), "+r"(q[9]),
+                   "+r"(q[10]), "+r"(q[11]), "+r"(q[12]), "+r"(q[13]), "+r"(q[14]), "+r"(q[15]), "+r"(q[16]), "+r"(q[17]), "+r"(q[18]),
+                   "+r"(q[19])
+                 :
+                 : "memory");
+    asm volatile(""
+                 : "+r"(q[20]), "+r"(q[21]), "+r"(q[22]), "+r"(q[23]), "+r"(q[24]), "+r"(q[25]), "+r"(q[26]), "+r"(q[27]), "+r"(q[28]),
+                   "+r"(q[29]), "+r"(q[30]), "+r"(q[31]), "+r"(q[32]), "+r"(q[33]), "+r"(q[34]), "+r"(q[35]), "+r"(q[36]), "+r"(q[37]),
+                   "+r"(q[38]), "+r"(q[39])
+                 :
+                 : "memory");
+}
+__device__ __forceinline__ void pass2_twiddle(const uint32_t (&q)[40], const float2 *__restrict__ tw2, int k1, float2 (&v)[20]) {
     if (k1 == 0) {
 #pragma unroll
         for (int j = 0; j < 10; ++j) {
@@ -119,42 +135,63 @@ __device__ __forceinline__ void pass2_tm(uint32_t ybase, const float2 *__restric
             v[2 * j + 1] = cfma2(bc2(__uint_as_float(q[4 * j + 3])), make_float2(-w1.y, w1.x), cmul2(bc2(__uint_as_float(q[4 * j + 2])), w1));
         }
     }
-    pass2_finish(v, ptile, f, k1);
 }
 
-__device__ __forceinline__ void rows_epilogue(const KParams &p, const float *ptile, const int4 *quads, int q0, int nq, int qstep, float *ocf,
-                                              int nf, int lane) {
-    if (p.apply_db) sparse_quads_epilogue<2, false>(p, ptile, quads, q0, nq, qstep, ocf, nullptr, nf, lane);
-    else if (p.amp == SGX_AMP_MAGNITUDE) sparse_quads_epilogue<1, false>(p, ptile, quads, q0, nq, qstep, ocf, nullptr, nf, lane);
-    else sparse_quads_epilogue<0, false>(p, ptile, quads, q0, nq, qstep, ocf, nullptr, nf, lane);
+// Interior-tile prefetch by the four warps of a group, hop block by hop block: block b (160 samples = 80 float2 units)
+// goes to word 162 b, so source and destination advance by constants and a block costs three cp.async per lane.
+template <int GW>
+__device__ __forceinline__ void prefetch_tile_by_group(float *sig, const float *src, int wl, int lane) {
+#pragma unroll 1
+    for (int b = wl; b < kSigBlocks; b += GW) {
+        const float *s = src + b * kHop + 2 * lane;
+        float *d = sig + b * kSigBlockStride + 2 * lane;
+        if (b < kSigBlocks - 1) {                      // 33 full blocks
+            cp_async8(d, s, 8);
+            cp_async8(d + 64, s + 64, 8);
+            if (lane < 16) cp_async8(d + 128, s + 128, 8);
+        } else {                                       // last block: 80 samples
+            cp_async8(d, s, 8);
+            if (lane < 8) cp_async8(d + 64, s + 64, 8);
+        }
+    }
 }
 
-template <int EW>
-__global__ void __launch_bounds__(32 * (kFftWarps + kGroups * EW), 1) k_r2c_fused_n400_tm(const __grid_constant__ F400Params P) {
+__device__ __forceinline__ void rows_epilogue(const KParams &p, const float *ptile, const int4 *quads, int q0, int q1, float *ocf, int nf,
+                                              int lane) {
+    if (p.apply_db) sparse_quads_pipelined<2>(p, ptile, quads, q0, q1, ocf, nf, lane);
+    else if (p.amp == SGX_AMP_MAGNITUDE) sparse_quads_pipelined<1>(p, ptile, quads, q0, q1, ocf, nf, lane);
+    else sparse_quads_pipelined<0>(p, ptile, quads, q0, q1, ocf, nf, lane);
+}
+
+// GW: warps per group (4 or 6)
+template <int GW>
+__global__ void __launch_bounds__(kGroups * GW * 32, 1) k_r2c_fused_n400_tm(const __grid_constant__ F400Params P) {
+    constexpr int kGroupWarps = GW, kTmThreads = kGroups * GW * 32, kGroupThreads = GW * 32;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    constexpr int kThreadsAll = 32 * (kFftWarps + kGroups * EW);
-    constexpr int kHandshake = kFftGroupThreads + 32 * EW;      // threads on the full / free barriers of a group
     const KParams &p = P.k;
-    const int *blob = reinterpret_cast<const int *>(p.sched);   // int n_quads; int qrange[2]; int maxcnt[n_quads]; pad; int4 quads[4 n]
+    // p.sched: int n_quads; int qrange[kGroupWarps + 1]; int maxcnt[n_quads]; pad to 16 bytes; int4 {c0, padded cnt, weight offset, row}[4 n]
+    const int *blob = reinterpret_cast<const int *>(p.sched);
     const int nq = __ldg(blob);
     const int padded_weights = p.buf_elems;
     const TmSmem S = carve(smem_raw, nq, padded_weights);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    // ---- one-time setup: tables -> shared memory, TMEM allocation
+    // ---- one-time setup: tables -> shared memory, zero rows behind the power tiles, TMEM allocation
     {
-        const int hdr = (1 + 2 + nq + 3) & ~3;
+        const int hdr = (1 + kGroupWarps + 1 + nq + 3) & ~3;
         const int4 *gq = reinterpret_cast<const int4 *>(blob + hdr);
         const float *val = static_cast<const float *>(p.val);
         const unsigned wbase = smem_u32(S.w);
-        for (int i = tid; i < kN; i += kThreadsAll) S.win[i] = P.c.win[i];
-        for (int i = tid; i < 4 * nq; i += kThreadsAll) {
+        for (int i = tid; i < kN; i += kTmThreads) S.win[i] = P.c.win[i];
+        if (tid <= kGroupWarps) S.qrange[tid] = __ldg(blob + 1 + tid);
+        for (int i = tid; i < kGroups * kPadRows * kFT; i += kTmThreads)
+            S.ptile[(i / (kPadRows * kFT)) * kPWordsTm + kBins * kFT + i % (kPadRows * kFT)] = 0.f;
+        for (int i = tid; i < 4 * nq; i += kTmThreads) {
             const int4 e = __ldg(gq + i);
             S.quads[i] = make_int4(e.x * (kFT * 4), e.y, static_cast<int>(wbase + 4u * e.z), e.w);
-            if (e.w >= 0) {
-                const int e0 = __ldg(p.row_ptr + e.w);
-                for (int k = 0; k < ((e.y + 3) & ~3); ++k) S.w[e.z + k] = k < e.y ? __ldg(val + e0 + k) : 0.f;
-            }
+            const int e0 = e.w >= 0 ? __ldg(p.row_ptr + e.w) : 0;
+            const int cnt = e.w >= 0 ? __ldg(p.row_ptr + e.w + 1) - e0 : 0;
+            for (int k = 0; k < ((e.y + 3) & ~3); ++k) S.w[e.z + k] = k < cnt ? __ldg(val + e0 + k) : 0.f;
         }
         if (warp == 0) tc::alloc(S.tmem_ptr, kTmemCols);
         tc::fence_before_sync();
@@ -166,84 +203,74 @@ __global__ void __launch_bounds__(32 * (kFftWarps + kGroups * EW), 1) k_r2c_fuse
     const int tpc = p.tiles_per_clip;
     const long long total_tiles = static_cast<long long>(p.n_clips) * tpc;
     const long long gstep = 4LL * gridDim.x;
-    const int q = warp & 3;                                  // group = SM sub-partition = TMEM lane quarter
-    float *ptile = S.ptile + q * kPWords;
+    const int q = warp & 3, wl = warp >> 2;                  // group = SM sub-partition = TMEM lane quarter; warp within the group
+    const int gt = wl * 32 + lane;                           // thread within the group
+    const uint32_t lane_base = tm + (static_cast<uint32_t>(32 * q) << 16);
+    float *sig = S.sig + q * kSigWords;
+    float *ptile = S.ptile + q * kPWordsTm;
+    const float *xbase = static_cast<const float *>(p.samples);
+    const bool vec_ok = p.vec_ok != 0;
+    const int q0 = S.qrange[wl], q1 = S.qrange[wl + 1];
+    const int bar = 1 + q;
 
-    if (warp < kFftWarps) {
-        // ================================================================= FFT warps
-        const int wl = warp >> 2;                            // warp within the group
-        const int gt = wl * 32 + lane;                       // thread within the group
-        const uint32_t lane_base = tm + (static_cast<uint32_t>(32 * q) << 16);
-        float *sig = S.sig + q * kSigWords;
-        const float *xbase = static_cast<const float *>(p.samples);
-        const bool vec_ok = p.vec_ok != 0;
-
-        long long g = 4LL * blockIdx.x + q;                  // this group's global tile index
-        if (g < total_tiles) {
-            const long long clip = g / tpc, tile = g - clip * tpc;
-            load_tile(sig, xbase + clip * p.clip_stride, (p.frame_begin + tile * kFT) * kHop - p.pad, p.n_samples, vec_ok, gt,
-                      kFftGroupThreads, kTileSamples / 2);
-        }
-        for (int it = 0; g < total_tiles; g += gstep, ++it) {
-            cp_async_commit_wait_all();
-            tc::fence_before_sync();
-            tc::bar_sync(1 + q, kFftGroupThreads);           // the tile's samples have landed; every Y row of the previous tile has been read
-            tc::fence_after_sync();
+    long long g = 4LL * blockIdx.x + q;                      // this group's global tile index
+    if (g < total_tiles) {                                   // prologue: pass 1 of the group's first tile
+        const long long clip = g / tpc, tile = g - clip * tpc;
+        load_tile(sig, xbase + clip * p.clip_stride, (p.frame_begin + tile * kFT) * kHop - p.pad, p.n_samples, vec_ok, gt, kGroupThreads,
+                  kTileSamples / 2);
+        cp_async_commit_wait_all();
+        tc::bar_sync(bar, kGroupThreads);
 #pragma unroll 1
-            for (int t = wl; t < 10; t += kFftWarpsPerGroup) pass1_tm(sig, S.win, lane, t, lane_base);
-            tc::wait_st();
-            tc::fence_before_sync();
-            tc::bar_sync(1 + q, kFftGroupThreads);           // every Y column of the group is in TMEM; the samples are dead
-            tc::fence_after_sync();
-            {
-                const long long gn = g + gstep;              // prefetch the group's next tile into its (only) signal buffer
-                if (gn < total_tiles) {
-                    const long long cn = gn / tpc, tn = gn - cn * tpc;
-                    load_tile(sig, xbase + cn * p.clip_stride, (p.frame_begin + tn * kFT) * kHop - p.pad, p.n_samples, vec_ok, gt,
-                              kFftGroupThreads, kTileSamples / 2);
-                }
-            }
-            if (EW > 0 && it > 0) tc::bar_sync(9 + q, kHandshake);      // the filterbank warps are done with the previous power tile
+        for (int t = wl; t < 10; t += kGroupWarps) pass1_tm(sig, S.win, lane, t, lane_base);
+        tc::wait_st();
+        tc::fence_before_sync();
+        tc::bar_sync(bar, kGroupThreads);
+        tc::fence_after_sync();
+    }
+    for (; g < total_tiles; g += gstep) {
+        // ---- phase B: Y(g) is complete in TMEM, the samples are dead, the power tile is free
+        const long long gn = g + gstep;
+        const bool has_next = gn < total_tiles;
+        if (has_next) {
+            const long long cn = gn / tpc, tn = gn - cn * tpc;
+            const long long sn = (p.frame_begin + tn * kFT) * kHop - p.pad;
+            const float *xn = xbase + cn * p.clip_stride;
+            if (vec_ok && sn >= 0 && sn + kTileSamples <= p.n_samples) prefetch_tile_by_group<GW>(sig, xn + sn, wl, lane);
+            else load_tile(sig, xn, sn, p.n_samples, vec_ok, gt, kGroupThreads, kTileSamples / 2);
+        }
 #pragma unroll 1
-            for (int k1 = wl; k1 <= 10; k1 += kFftWarpsPerGroup) pass2_tm(lane_base, P.c.tw2[k1], ptile, lane, k1);
-            if (EW > 0) {
-                __threadfence_block();
-                bar_arrive(5 + q, kHandshake);               // power tile full
-            } else {
-                tc::bar_sync(1 + q, kFftGroupThreads);
-                const long long clip = g / tpc, tile = g - clip * tpc;
-                const long long f0 = p.frame_begin + tile * kFT;
-                const long long rem = p.frame_begin + p.frames_todo - f0;
-                const int nf = rem < kFT ? static_cast<int>(rem) : kFT;
-                float *ocf = static_cast<float *>(p.out) + clip * p.out_clip_stride + (f0 - p.out_frame_origin);
-                rows_epilogue(p, ptile, S.quads, wl, nq, kFftWarpsPerGroup, ocf, nf, lane);
-            }
+        for (int k1 = wl; k1 <= 10; k1 += kGroupWarps) {
+            uint32_t yq[40];
+            float2 v[20];
+            y_row_request(lane_base, k1, yq);
+            y_row_wait(yq);
+            pass2_twiddle(yq, P.c.tw2[k1], k1, v);
+            pass2_finish(v, ptile, lane, k1);
         }
-    } else if (EW > 0) {
-        // ================================================================= filterbank warps
-        const int el = (warp - kFftWarps) >> 2;              // filterbank warp within the group
-        for (long long g = 4LL * blockIdx.x + q; g < total_tiles; g += gstep) {
-            const long long clip = g / tpc, tile = g - clip * tpc;
-            const long long f0 = p.frame_begin + tile * kFT;
-            const long long rem = p.frame_begin + p.frames_todo - f0;
-            const int nf = rem < kFT ? static_cast<int>(rem) : kFT;
-            float *ocf = static_cast<float *>(p.out) + clip * p.out_clip_stride + (f0 - p.out_frame_origin);
-            tc::bar_sync(5 + q, kHandshake);                 // power tile full
-            rows_epilogue(p, ptile, S.quads, el, nq, EW > 0 ? EW : 1, ocf, nf, lane);
-            if (g + gstep < total_tiles) bar_arrive(9 + q, kHandshake);   // power tile free again
+        cp_async_commit_wait_all();
+        tc::fence_before_sync();
+        tc::bar_sync(bar, kGroupThreads);                    // P(g) complete, every Y row read, the next tile's samples have landed
+        tc::fence_after_sync();
+        // ---- phase A: the filterbank rows of tile g and pass 1 of the next tile, in opposite orders on alternate warps
+        const long long clip = g / tpc, tile = g - clip * tpc;
+        const long long f0 = p.frame_begin + tile * kFT;
+        const long long rem = p.frame_begin + p.frames_todo - f0;
+        const int nf = rem < kFT ? static_cast<int>(rem) : kFT;
+        float *ocf = static_cast<float *>(p.out) + clip * p.out_clip_stride + (f0 - p.out_frame_origin);
+        if (wl & 1) rows_epilogue(p, ptile, S.quads, q0, q1, ocf, nf, lane);
+        if (has_next) {
+#pragma unroll 1
+            for (int t = wl; t < 10; t += kGroupWarps) pass1_tm(sig, S.win, lane, t, lane_base);
         }
+        if (!(wl & 1)) rows_epilogue(p, ptile, S.quads, q0, q1, ocf, nf, lane);
+        tc::wait_st();
+        tc::fence_before_sync();
+        tc::bar_sync(bar, kGroupThreads);                    // Y(next) complete; the power tile and the samples are free again
+        tc::fence_after_sync();
     }
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::dealloc(tm, kTmemCols);
-}
-
-template <int EW>
-cudaError_t launch_tm(const F400Params &P, long long grid, size_t smem, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(k_r2c_fused_n400_tm<EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess) return e;
-    k_r2c_fused_n400_tm<EW><<<static_cast<unsigned>(grid), 32 * (kFftWarps + kGroups * EW), smem, stream>>>(P);
-    return cudaGetLastError();
 }
 
 }  // namespace
@@ -251,9 +278,21 @@ cudaError_t launch_tm(const F400Params &P, long long grid, size_t smem, cudaStre
 // at least half an SM's worth of shared memory so that one CTA (which owns all 512 TMEM columns) is resident per SM
 size_t fast400_tm_smem_bytes(int n_quads, int padded_weights) { return std::max<size_t>(tm_smem_bytes(n_quads, padded_weights), 120 * 1024); }
 bool fast400_tm_fits(int n_quads, int padded_weights) { return n_quads > 0 && fast400_tm_smem_bytes(n_quads, padded_weights) <= 227 * 1024; }
+int fast400_tm_max_group_warps() { return kMaxGroupWarps; }
+int fast400_tm_pad_rows() { return kPadRows; }
 
-cudaError_t launch_fast400_tm(const KParams &p, const float *window_f32, int n_quads, int padded_weights, int epilogue_warps,
-                              int sm_count, cudaStream_t stream) {
+namespace {
+template <int GW>
+cudaError_t launch_tm(const F400Params &P, long long grid, size_t smem, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(k_r2c_fused_n400_tm<GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    k_r2c_fused_n400_tm<GW><<<static_cast<unsigned>(grid), kGroups * GW * 32, smem, stream>>>(P);
+    return cudaGetLastError();
+}
+}  // namespace
+
+cudaError_t launch_fast400_tm(const KParams &p, const float *window_f32, int n_quads, int padded_weights, int group_warps, int sm_count,
+                              cudaStream_t stream) {
     F400Params P;
     P.k = p;
     P.k.FT = f400::kFT;
@@ -265,10 +304,11 @@ cudaError_t launch_fast400_tm(const KParams &p, const float *window_f32, int n_q
     if (total <= 0) return cudaSuccess;
     const long long grid = std::min<long long>((total + 3) / 4, sm_count);        // persistent: one CTA per SM
     const size_t smem = fast400_tm_smem_bytes(n_quads, padded_weights);
-    switch (epilogue_warps) {
-        case 0: return launch_tm<0>(P, grid, smem, stream);
-        case 1: return launch_tm<1>(P, grid, smem, stream);
-        default: return launch_tm<2>(P, grid, smem, stream);
+    switch (group_warps) {
+        case 4: return launch_tm<4>(P, grid, smem, stream);
+        case 5: return launch_tm<5>(P, grid, smem, stream);
+        case 6: return launch_tm<6>(P, grid, smem, stream);
+        default: return cudaErrorInvalidValue;
     }
 }
 

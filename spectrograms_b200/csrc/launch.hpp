@@ -34,13 +34,16 @@ cudaError_t launch_fast400_tc(const KParams &p, const float *window_f32, int n_s
 size_t fast400_tc_smem_bytes(int n_steps, int n_rounds, size_t b_floats);
 bool fast400_tc_fits(int n_steps, int n_rounds, size_t b_floats);
 
-// r2c_fused_n400_tm: the same family with TMEM as the exchange medium of the two FFT passes, four independent 32-frame
-// groups per SM and epilogue_warps (0, 1, 2) dedicated filterbank warps per group (kernel_n400_tm.cu). Sparse mel / loghz
-// spectrogram outputs; p.sched points at the quad blob built for ONE warp (all quads in descending cost order).
-cudaError_t launch_fast400_tm(const KParams &p, const float *window_f32, int n_quads, int padded_weights, int epilogue_warps,
-                              int sm_count, cudaStream_t stream);
+// r2c_fused_n400_tm: the same family with TMEM as the exchange medium of the two FFT passes and four independent
+// 32-frame groups per SM (kernel_n400_tm.cu). Sparse mel / loghz spectrogram outputs. p.sched points at the quad blob
+// built for group_warps (4, 5 or 6) warps per group with every row of a quad zero-padded to the quad's longest row
+// (rows may read up to fast400_tm_pad_rows() zero rows behind bin 200).
+cudaError_t launch_fast400_tm(const KParams &p, const float *window_f32, int n_quads, int padded_weights, int group_warps, int sm_count,
+                              cudaStream_t stream);
 size_t fast400_tm_smem_bytes(int n_quads, int padded_weights);
 bool fast400_tm_fits(int n_quads, int padded_weights);
+int fast400_tm_max_group_warps();
+int fast400_tm_pad_rows();
 
 // r2c_fused_pow2: n_fft = 256 .. 8192 (powers of two), f32 / f64 (kernel_pow2.cu). p.FT, p.frame_stride, p.tile_stride and
 // p.tiles_per_clip must be set from the helpers below; p.vec_ok is the "vector loads allowed" flag.

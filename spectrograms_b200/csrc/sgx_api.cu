@@ -148,13 +148,14 @@ struct sgx_plan {
     bool fast400_sparse = false;     // ... with the shared-memory sparse table
     bool fast400_tc = false;         // ... on the TMEM / tcgen05 kernel (r2c_fused_n400_tc)
     bool fast400_tm = false;         // ... on the TMEM-exchange kernel (r2c_fused_n400_tm): sparse mel / loghz spectrogram outputs
-    int tm_mode = -1;                // epilogue warps per group of r2c_fused_n400_tm (0, 1, 2); -1: kernel not used
+    int tm_mode = -1;                // sgx_plan_set_tmem_exchange: -1 auto (used wherever it applies), 0 never, 1 whenever available
+    int tm_warps = 4;                // warps per 32-frame group of r2c_fused_n400_tm (4, 5 or 6; SGX_N400_TM_WARPS)
     int tc_mode = -1;                // sgx_plan_set_tensor_cores: -1 auto (dense mappings only), 0 never, 1 whenever available
     std::vector<int> tc_blob;        // step blob of r2c_fused_n400_tc (launch.hpp)
     int tc_steps = 0, tc_rounds = 0;
     size_t tc_b_floats = 0;
     int *d_tc_blob = nullptr;
-    int sparse_quads = 0, sparse_weights = 0;
+    int sparse_quads = 0, sparse_weights = 0, tm_weights = 0;
     bool rows_contig = false;        // CSR rows have consecutive columns
     std::vector<int> row_desc;       // contiguous CSR rows: int4 {e0, cnt, c0, 0} per row
     int *d_row_desc = nullptr;
@@ -287,7 +288,7 @@ void build_lane_rows(sgx_plan &pl) {
 // cost on CUDA cores grows with n_filters x 201 while the MMA count does not. Auto therefore picks it for ERB only.
 // r2c_fused_n400_tm: TMEM as the exchange medium of the two FFT passes (kernel_n400_tm.cu)
 bool use_tm(const sgx_plan &pl) {
-    return pl.fast400 && pl.fast400_tm && !pl.force_generic && pl.tm_mode >= 0 && pl.tc_mode != 1;
+    return pl.fast400 && pl.fast400_tm && !pl.force_generic && pl.tm_mode != 0 && pl.tc_mode != 1;
 }
 
 bool use_tc(const sgx_plan &pl) {
@@ -426,6 +427,11 @@ void select_family(sgx_plan &pl) {
     // pad to 16 bytes; int4 {c0, cnt, padded weight offset, row}[4 * n_quads] in warp order.
     bool contiguous = csr;
     int padded = 0;
+    {
+        const char *e = std::getenv("SGX_N400_TM_WARPS");      // experiments only: 4 (default), 5 or 6 warps per group
+        const int w = e ? std::atoi(e) : 4;
+        pl.tm_warps = w >= 4 && w <= 6 ? w : 4;
+    }
     pl.wofs.clear();
     pl.wofs_tm.clear();
     if (csr) {
@@ -480,7 +486,59 @@ void select_family(sgx_plan &pl) {
             return blob;
         };
         std::vector<int> blob = make_blob(W);
-        pl.wofs_tm = make_blob(1);      // r2c_fused_n400_tm: all quads in descending cost order, dealt round-robin by the kernel
+        // r2c_fused_n400_tm: the quads dealt to the 4 warps of a group; every row of a quad is padded (zero weights) to the
+        // quad's longest row (weight slots rounded up to 4 floats), so the kernel's trip count is warp-uniform. Warps 0 and 1 of a group
+        // also run one more pass-1 task than warps 2 and 3 in the same phase: they start with that much load.
+        {
+            const int Wt = pl.tm_warps;
+            static const long bias = std::getenv("SGX_N400_TM_BIAS") ? std::atol(std::getenv("SGX_N400_TM_BIAS")) : 150;
+            std::vector<int> cntU(nq), woq(4 * static_cast<size_t>(nq));
+            int padded_tm = 0;
+            bool ok = nq > 0;
+            for (int q = 0; q < nq; ++q) {
+                cntU[q] = std::max(4, (qmax[q] + 3) & ~3);
+                for (int k = 0; k < 4; ++k) {
+                    const int r = order[4 * q + k];
+                    woq[4 * static_cast<size_t>(q) + k] = padded_tm;
+                    padded_tm += (cntU[q] + 3) & ~3;
+                    const int c0 = (r >= 0 && cnt[r]) ? pl.tab.col[pl.tab.row_ptr[r]] : 0;
+                    if (c0 + cntU[q] > static_cast<int>(pl.tab.out_len) + fast400_tm_pad_rows()) ok = false;
+                }
+            }
+            std::vector<std::vector<int>> per_warp(Wt);
+            std::vector<long> load(Wt, 0);
+            for (int w = 0; w < Wt; ++w) load[w] = bias * ((10 - w + Wt - 1) / Wt);      // pass-1 tasks w, w + Wt, ... < 10
+            for (int q = 0; q < nq; ++q) {
+                int best = 0;
+                for (int w = 1; w < Wt; ++w) if (load[w] < load[best]) best = w;
+                per_warp[best].push_back(q);
+                load[best] += 26 + 4 * cntU[q];
+            }
+            const int hdr = (1 + Wt + 1 + nq + 3) & ~3;
+            std::vector<int> tb(static_cast<size_t>(hdr) + 16 * static_cast<size_t>(nq), 0);
+            tb[0] = nq;
+            int idx = 0;
+            for (int w = 0; w < Wt; ++w) {
+                tb[1 + w] = idx;
+                for (int q : per_warp[w]) {
+                    tb[1 + Wt + 1 + idx] = cntU[q];
+                    for (int k = 0; k < 4; ++k) {
+                        const int r = order[4 * q + k];
+                        int *e = &tb[static_cast<size_t>(hdr) + 4 * (4 * static_cast<size_t>(idx) + k)];
+                        e[0] = (r >= 0 && cnt[r]) ? pl.tab.col[pl.tab.row_ptr[r]] : 0;
+                        e[1] = cntU[q];
+                        e[2] = woq[4 * static_cast<size_t>(q) + k];
+                        e[3] = r;
+                    }
+                    ++idx;
+                }
+            }
+            tb[1 + Wt] = idx;
+            if (ok) {
+                pl.wofs_tm = tb;
+                pl.tm_weights = std::max(padded_tm, 4);
+            }
+        }
         pl.wofs = blob;
         padded = std::max(padded, 4);
         pl.sparse_quads = nq;
@@ -514,11 +572,8 @@ void select_family(sgx_plan &pl) {
     pl.fast400_sparse = pl.fast400 && csr && contiguous && fast400_sparse_fits(pl.sparse_quads, pl.sparse_weights);
     build_tc_blob(pl);
     pl.fast400_tc = pl.tc_steps > 0;
-    pl.fast400_tm = pl.fast400 && csr && contiguous && d.output == SGX_OUT_SPECTROGRAM && fast400_tm_fits(pl.sparse_quads, pl.sparse_weights);
-    {
-        const char *e = std::getenv("SGX_N400_TM");
-        pl.tm_mode = e ? std::atoi(e) : -1;
-    }
+    pl.fast400_tm = pl.fast400 && csr && contiguous && d.output == SGX_OUT_SPECTROGRAM && !pl.wofs_tm.empty() &&
+                    fast400_tm_fits(pl.sparse_quads, pl.tm_weights);
     pl.kernel_name = pl.fast400 ? "r2c_fused_n400" : pl.pow2 ? "r2c_fused_pow2" : "r2c_fused_generic";
     // folded DCT basis for the fused MFCC epilogue: B[c][n-1-i] = (-1)^c B[c][i] -> half basis, tasks of 4 coefficients of
     // one parity: [task][i < n/2][4], even-coefficient tasks first
@@ -679,7 +734,7 @@ void run_device(sgx_plan &pl, const void *d_samples, size_t n_clips, size_t n_sa
             q.vec_ok = (reinterpret_cast<uintptr_t>(q.samples) % 8 == 0 && clip_stride % 2 == 0) ? 1 : 0;
             if (use_tm(pl)) {
                 q.sched = pl.d_wofs_tm;
-                ck(launch_fast400_tm(q, pl.window_f32.data(), pl.sparse_quads, pl.sparse_weights, pl.tm_mode, pl.sm_count, stream), "kernel launch (r2c_fused_n400_tm)");
+                ck(launch_fast400_tm(q, pl.window_f32.data(), pl.sparse_quads, pl.tm_weights, pl.tm_warps, pl.sm_count, stream), "kernel launch (r2c_fused_n400_tm)");
                 pl.last_launches += 1;
                 continue;
             }
@@ -837,6 +892,13 @@ sgx_status sgx_plan_force_generic(sgx_plan *plan, int force) {
     return guarded([&] {
         if (!plan) invalid("null plan");
         plan->force_generic = force != 0;
+    });
+}
+
+sgx_status sgx_plan_set_tmem_exchange(sgx_plan *plan, int enable) {
+    return guarded([&] {
+        if (!plan) invalid("null plan");
+        plan->tm_mode = enable < 0 ? -1 : (enable != 0 ? 1 : 0);
     });
 }
 

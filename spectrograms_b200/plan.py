@@ -243,6 +243,12 @@ class _NativePlan:
         (the default: where it is measured faster). Test and measurement hook."""
         _native.check(_native.lib().sgx_plan_set_tensor_cores(self._h, -1 if enable is None else int(bool(enable))))
 
+    def set_tmem_exchange(self, enable=True) -> None:
+        """Tensor memory as the exchange medium of the n_fft = 400 family's two FFT passes (r2c_fused_n400_tm): True = whenever
+        supported, False = never (shared-memory exchange), None = automatic (the default: wherever supported). Bit-identical
+        results either way. Test and measurement hook."""
+        _native.check(_native.lib().sgx_plan_set_tmem_exchange(self._h, -1 if enable is None else int(bool(enable))))
+
     # -- compute
     def _out_dtype(self, torch_mod=None):
         cplx = self.output == _OUT_STFT
@@ -454,6 +460,7 @@ class SpectrogramPlan:
     def last_launch_count(self) -> int: return self._n.last_launch_count()
     def force_generic(self, force: bool = True) -> None: self._n.force_generic(force)
     def set_tensor_cores(self, enable=True) -> None: self._n.set_tensor_cores(enable)
+    def set_tmem_exchange(self, enable=True) -> None: self._n.set_tmem_exchange(enable)
 
 
 class StftPlan:
@@ -500,6 +507,7 @@ class StftPlan:
     def last_launch_count(self) -> int: return self._n.last_launch_count()
     def force_generic(self, force: bool = True) -> None: self._n.force_generic(force)
     def set_tensor_cores(self, enable=True) -> None: self._n.set_tensor_cores(enable)
+    def set_tmem_exchange(self, enable=True) -> None: self._n.set_tmem_exchange(enable)
 
 
 class MfccPlan:
@@ -527,6 +535,7 @@ class MfccPlan:
     def last_launch_count(self) -> int: return self._n.last_launch_count()
     def force_generic(self, force: bool = True) -> None: self._n.force_generic(force)
     def set_tensor_cores(self, enable=True) -> None: self._n.set_tensor_cores(enable)
+    def set_tmem_exchange(self, enable=True) -> None: self._n.set_tmem_exchange(enable)
 
 
 class Chromagram:
@@ -576,6 +585,7 @@ class ChromaPlan:
     def last_launch_count(self) -> int: return self._n.last_launch_count()
     def force_generic(self, force: bool = True) -> None: self._n.force_generic(force)
     def set_tensor_cores(self, enable=True) -> None: self._n.set_tensor_cores(enable)
+    def set_tmem_exchange(self, enable=True) -> None: self._n.set_tmem_exchange(enable)
 
 
 class SpectrogramPlanner:

@@ -49,7 +49,7 @@ int main() {
     EXPECT(contains(throws<InvalidInputError>([&] { planner.mel_plan<float>(p, MelParams(40, 0.0, 9000.0)); }), "Nyquist"));   // tests/spectrogram_tests.rs:147-158
     auto mel = planner.mel_plan<float>(SpectrogramParams(StftParams(400, 160), 16000.0), MelParams(128, 0.0, 8000.0), LogParams(-80.0), Amp::Decibels);
     EXPECT(mel.output_shape(480000) == std::make_pair(size_t(128), size_t(3001)));                                    // BASELINE configs[1]
-    EXPECT(mel.kernel_name() == "r2c_fused_n400");
+    EXPECT(mel.kernel_name() == "r2c_fused_n400_tm");
     EXPECT(SpectrogramParams::speech_default(16000.0).stft().hop_size() == 160 && SpectrogramParams::music_default(44100.0).stft().n_fft() == 2048);
     EXPECT(contains(throws<InvalidInputError>([] { WindowType::custom({}); }), "cannot be empty"));
     EXPECT(contains(throws<InvalidInputError>([] { StftParams(8, 4, WindowType::custom({1, 2, 3}), true); }), "must match n_fft"));

@@ -18,11 +18,9 @@ def rel(a, b):
 
 
 def plan_for(amp, tm, mapping="mel", nb=128):
-    """tm: None = shared-memory kernel, 0 / 1 / 2 = TMEM kernel with that many filterbank warps per group"""
-    if tm is None:
-        os.environ.pop("SGX_N400_TM", None)
-    else:
-        os.environ["SGX_N400_TM"] = str(tm)
+    """tm: None = shared-memory kernel, 4 / 5 / 6 = TMEM kernel with that many warps per 32-frame group"""
+    if tm is not None:
+        os.environ["SGX_N400_TM_WARPS"] = str(tm)
     params = sg.SpectrogramParams(sg.StftParams(400, 160, "hanning", True), 16000.0)
     pl = sg.SpectrogramPlanner()
     db = sg.LogParams(-80.0) if amp == "db" else None
@@ -30,13 +28,14 @@ def plan_for(amp, tm, mapping="mel", nb=128):
         p = pl.mel_plan(params, sg.MelParams(nb, 0.0, 8000.0), db, amp, "float32")
     else:
         p = pl.log_hz_plan(params, sg.LogHzParams(nb, 60.0, 7000.0), db, amp, "float32")
-    os.environ.pop("SGX_N400_TM", None)
+    os.environ.pop("SGX_N400_TM_WARPS", None)
+    p.set_tmem_exchange(tm is not None)
     return p
 
 
 def main():
     quick = "--quick" in sys.argv
-    modes = [0, 1, 2]
+    modes = [4]
     if "--modes" in sys.argv:
         modes = [int(v) for v in sys.argv[sys.argv.index("--modes") + 1].split(",")]
     rng = np.random.default_rng(0)
@@ -62,7 +61,7 @@ def main():
                                 e_tm, e_cc = float(np.abs(ya[-1] - ref).max()), float(np.abs(yb[-1] - ref).max())
                             else:
                                 e_tm, e_cc = rel(ya[-1], ref), rel(yb[-1], ref)
-                            print(f"{mapping:5s} nb={nb:3d} n={n:6d} clips={n_clips:2d} {amp:9s} ew={tm}: tm {e_tm:.3e}  smem {e_cc:.3e}  "
+                            print(f"{mapping:5s} nb={nb:3d} n={n:6d} clips={n_clips:2d} {amp:9s} warps={tm}: tm {e_tm:.3e}  smem {e_cc:.3e}  "
                                   f"bit-identical={same}", flush=True)
                             tol = 1e-3 if amp == "db" else 1e-5
                             assert e_tm <= tol, "TMEM kernel out of tolerance"
@@ -81,7 +80,7 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
-        key = f"{p.kernel_name()}" + ("" if tm is None else f"/ew{tm}")
+        key = f"{p.kernel_name()}" + ("" if tm is None else f"/warps{tm}")
         res[key] = {"ms_median": float(np.median(ts)), "ms_best": float(np.min(ts))}
         print(key, res[key], flush=True)
     print(json.dumps(res))
