@@ -163,7 +163,59 @@ __device__ __forceinline__ void sparse_quads_epilogue_impl(const KParams &p, con
 // The same rows, software-pipelined for the kernels whose power tile is followed by zero rows (r2c_fused_n400_tm): every
 // row of a quad carries the quad's longest count rounded up to 4 columns (zero weights behind the row's own), all column
 // steps are 4 wide, and the first step of quad i+1 -- its descriptor, four power-tile reads and four weights -- is loaded
-// while quad i is multiplied, scaled and stored. The shared-memory latency leaves the per-quad dependency chain.
+// while quad i is multiplied, scaled and stored, so the shared-memory latency leaves the per-quad dependency chain. The
+// loop handles two quads per trip with two register sets (no rotation moves); the multiply-adds are packed (two frames per
+// FFMA2, weight as the broadcast operand). Every quad slot holds a real row (the host pads the last quad with copies of one
+// of its rows, which store the same values twice), so there is no per-row branch.
+struct QuadRegs {
+    float4 d;                      // {byte offset of P[c0], cnt (multiple of 4), weights address, row}
+    float4 w, x0, x1, x2, x3;      // first 4-column step
+    unsigned pe;
+};
+__device__ __forceinline__ void quad_fetch(QuadRegs &r, float4 d, unsigned pbase) {
+    constexpr unsigned kRow = kFT * 4u;
+    r.d = d;
+    r.pe = pbase + __float_as_uint(d.x);
+    r.w = lds_v4(__float_as_uint(d.z));
+    r.x0 = lds_v4(r.pe);
+    r.x1 = lds_v4(r.pe + kRow);
+    r.x2 = lds_v4(r.pe + 2 * kRow);
+    r.x3 = lds_v4(r.pe + 3 * kRow);
+}
+template <int AMP, bool FULL>
+__device__ __forceinline__ void quad_finish(const QuadRegs &r, float eps, char *ob, unsigned ors4, int j, int nf) {
+    constexpr unsigned kRow = kFT * 4u;
+    float2 lo = make_float2(0.f, 0.f), hi = lo;        // frames (j, j+8) and (j+16, j+24)
+    lo = cfma2(bc2(r.w.x), make_float2(r.x0.x, r.x0.y), lo); hi = cfma2(bc2(r.w.x), make_float2(r.x0.z, r.x0.w), hi);
+    lo = cfma2(bc2(r.w.y), make_float2(r.x1.x, r.x1.y), lo); hi = cfma2(bc2(r.w.y), make_float2(r.x1.z, r.x1.w), hi);
+    lo = cfma2(bc2(r.w.z), make_float2(r.x2.x, r.x2.y), lo); hi = cfma2(bc2(r.w.z), make_float2(r.x2.z, r.x2.w), hi);
+    lo = cfma2(bc2(r.w.w), make_float2(r.x3.x, r.x3.y), lo); hi = cfma2(bc2(r.w.w), make_float2(r.x3.z, r.x3.w), hi);
+    const int steps = __float_as_int(r.d.y) >> 2;
+#pragma unroll 1
+    for (int e4 = 1; e4 < steps; ++e4) {               // rows longer than four columns (warp-uniform count)
+        const float4 we = lds_v4(__float_as_uint(r.d.z) + 16u * e4);
+        const float4 z0 = lds_v4(r.pe + kRow * (4 * e4)), z1 = lds_v4(r.pe + kRow * (4 * e4 + 1));
+        const float4 z2 = lds_v4(r.pe + kRow * (4 * e4 + 2)), z3 = lds_v4(r.pe + kRow * (4 * e4 + 3));
+        lo = cfma2(bc2(we.x), make_float2(z0.x, z0.y), lo); hi = cfma2(bc2(we.x), make_float2(z0.z, z0.w), hi);
+        lo = cfma2(bc2(we.y), make_float2(z1.x, z1.y), lo); hi = cfma2(bc2(we.y), make_float2(z1.z, z1.w), hi);
+        lo = cfma2(bc2(we.z), make_float2(z2.x, z2.y), lo); hi = cfma2(bc2(we.z), make_float2(z2.z, z2.w), hi);
+        lo = cfma2(bc2(we.w), make_float2(z3.x, z3.y), lo); hi = cfma2(bc2(we.w), make_float2(z3.z, z3.w), hi);
+    }
+    float v0, v1, v2, v3;
+    if (AMP == 2) {
+        const float2 l = cmul2(bc2(3.01029995663981195f), make_float2(fast_lg2(fmaxf(lo.x, eps)), fast_lg2(fmaxf(lo.y, eps))));
+        const float2 h = cmul2(bc2(3.01029995663981195f), make_float2(fast_lg2(fmaxf(hi.x, eps)), fast_lg2(fmaxf(hi.y, eps))));
+        v0 = l.x; v1 = l.y; v2 = h.x; v3 = h.y;
+    } else {
+        v0 = finish_value<AMP>(lo.x, eps); v1 = finish_value<AMP>(lo.y, eps);
+        v2 = finish_value<AMP>(hi.x, eps); v3 = finish_value<AMP>(hi.y, eps);
+    }
+    char *orow = ob + static_cast<size_t>(__float_as_uint(r.d.w)) * ors4;
+    if (FULL || j < nf) *reinterpret_cast<float *>(orow) = v0;
+    if (FULL || j + 8 < nf) *reinterpret_cast<float *>(orow + 32) = v1;
+    if (FULL || j + 16 < nf) *reinterpret_cast<float *>(orow + 64) = v2;
+    if (FULL || j + 24 < nf) *reinterpret_cast<float *>(orow + 96) = v3;
+}
 template <int AMP, bool FULL>
 __device__ __forceinline__ void sparse_quads_pipelined_impl(const KParams &p, const float *ptile, const int4 *s_quads, int q0, int q1,
                                                             float *out_clip_frame, int nf, int lane) {
@@ -174,49 +226,18 @@ __device__ __forceinline__ void sparse_quads_pipelined_impl(const KParams &p, co
     const unsigned qbase = smem_u32(s_quads) + 16u * s;
     const unsigned ors4 = 4u * static_cast<unsigned>(p.out_row_stride);
     char *ob = reinterpret_cast<char *>(out_clip_frame) + 4 * j;
-    constexpr unsigned kRow = kFT * 4u;
-    float4 rf = lds_v4(qbase + 64u * q0);                          // {byte offset of P[c0], cnt (multiple of 4), weights address, row}
-    float4 rf2 = lds_v4(qbase + 64u * (q0 + 1 < q1 ? q0 + 1 : q0));
-    unsigned pe = pbase + __float_as_uint(rf.x);
-    float4 w = lds_v4(__float_as_uint(rf.z));
-    float4 x0 = lds_v4(pe), x1 = lds_v4(pe + kRow), x2 = lds_v4(pe + 2 * kRow), x3 = lds_v4(pe + 3 * kRow);
+    const int last = q1 - 1;
+    QuadRegs A, B;
+    quad_fetch(A, lds_v4(qbase + 64u * q0), pbase);
+    float4 dn = lds_v4(qbase + 64u * (q0 + 1 < q1 ? q0 + 1 : last));      // descriptor one quad ahead of the fetches
 #pragma unroll 1
-    for (int qi = q0; qi < q1; ++qi) {
-        const float4 cur = rf;
-        const unsigned pcur = pe;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        a0 = fmaf(w.x, x0.x, a0); a1 = fmaf(w.x, x0.y, a1); a2 = fmaf(w.x, x0.z, a2); a3 = fmaf(w.x, x0.w, a3);
-        a0 = fmaf(w.y, x1.x, a0); a1 = fmaf(w.y, x1.y, a1); a2 = fmaf(w.y, x1.z, a2); a3 = fmaf(w.y, x1.w, a3);
-        a0 = fmaf(w.z, x2.x, a0); a1 = fmaf(w.z, x2.y, a1); a2 = fmaf(w.z, x2.z, a2); a3 = fmaf(w.z, x2.w, a3);
-        a0 = fmaf(w.w, x3.x, a0); a1 = fmaf(w.w, x3.y, a1); a2 = fmaf(w.w, x3.z, a2); a3 = fmaf(w.w, x3.w, a3);
-        // next quad: first step in flight while this one finishes (the last iteration re-reads its own, harmlessly)
-        rf = rf2;
-        rf2 = lds_v4(qbase + 64u * (qi + 2 < q1 ? qi + 2 : q1 - 1));
-        pe = pbase + __float_as_uint(rf.x);
-        const float4 wn = lds_v4(__float_as_uint(rf.z));
-        const float4 y0 = lds_v4(pe), y1 = lds_v4(pe + kRow), y2 = lds_v4(pe + 2 * kRow), y3 = lds_v4(pe + 3 * kRow);
-        const int steps = __float_as_int(cur.y) >> 2;
-#pragma unroll 1
-        for (int e4 = 1; e4 < steps; ++e4) {                       // rows longer than four columns (warp-uniform count)
-            const float4 we = lds_v4(__float_as_uint(cur.z) + 16u * e4);
-            const float4 z0 = lds_v4(pcur + kRow * (4 * e4)), z1 = lds_v4(pcur + kRow * (4 * e4 + 1));
-            const float4 z2 = lds_v4(pcur + kRow * (4 * e4 + 2)), z3 = lds_v4(pcur + kRow * (4 * e4 + 3));
-            a0 = fmaf(we.x, z0.x, a0); a1 = fmaf(we.x, z0.y, a1); a2 = fmaf(we.x, z0.z, a2); a3 = fmaf(we.x, z0.w, a3);
-            a0 = fmaf(we.y, z1.x, a0); a1 = fmaf(we.y, z1.y, a1); a2 = fmaf(we.y, z1.z, a2); a3 = fmaf(we.y, z1.w, a3);
-            a0 = fmaf(we.z, z2.x, a0); a1 = fmaf(we.z, z2.y, a1); a2 = fmaf(we.z, z2.z, a2); a3 = fmaf(we.z, z2.w, a3);
-            a0 = fmaf(we.w, z3.x, a0); a1 = fmaf(we.w, z3.y, a1); a2 = fmaf(we.w, z3.z, a2); a3 = fmaf(we.w, z3.w, a3);
-        }
-        const int row = __float_as_int(cur.w);
-        if (row >= 0) {
-            const float v0 = finish_value<AMP>(a0, eps), v1 = finish_value<AMP>(a1, eps);
-            const float v2 = finish_value<AMP>(a2, eps), v3 = finish_value<AMP>(a3, eps);
-            char *orow = ob + static_cast<size_t>(static_cast<unsigned>(row)) * ors4;
-            if (FULL || j < nf) *reinterpret_cast<float *>(orow) = v0;
-            if (FULL || j + 8 < nf) *reinterpret_cast<float *>(orow + 32) = v1;
-            if (FULL || j + 16 < nf) *reinterpret_cast<float *>(orow + 64) = v2;
-            if (FULL || j + 24 < nf) *reinterpret_cast<float *>(orow + 96) = v3;
-        }
-        w = wn; x0 = y0; x1 = y1; x2 = y2; x3 = y3;
+    for (int qi = q0; qi < q1; qi += 2) {
+        quad_fetch(B, dn, pbase);                                  // quad qi + 1 (or a harmless re-read of the last one)
+        dn = lds_v4(qbase + 64u * (qi + 2 < q1 ? qi + 2 : last));
+        quad_finish<AMP, FULL>(A, eps, ob, ors4, j, nf);
+        quad_fetch(A, dn, pbase);                                  // quad qi + 2
+        dn = lds_v4(qbase + 64u * (qi + 3 < q1 ? qi + 3 : last));
+        if (qi + 1 < q1) quad_finish<AMP, FULL>(B, eps, ob, ors4, j, nf);
     }
 }
 

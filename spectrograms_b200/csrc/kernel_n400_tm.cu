@@ -137,6 +137,29 @@ __device__ __forceinline__ void pass2_twiddle(const uint32_t (&q)[40], const flo
     }
 }
 
+// |X[bin]|^2 of the bins a pass-2 butterfly owns into P[bin][f] (f400::pass2_finish with the address arithmetic hoisted): bins
+// k1 + 20 k2 (k2 < 10) going up from k1, bin 200 - k1 (k2 = 10) and the mirrored bins (200 - k1) - 20 (k2 - 10) going down from
+// it; k1 = 0 / 10 own no mirrored bins (conjugate duplicates) and k1 = 10 would repeat bin 190.
+__device__ __forceinline__ void pass2_finish_tm(float2 (&v)[20], float *__restrict__ ptile, int f, int k1) {
+    dft20(v);
+    float pw[20];
+#pragma unroll
+    for (int k2 = 0; k2 < 20; ++k2) {
+        const float2 X = v[reg_of_bin(k2)];
+        const float2 sq = cmul2(X, X);
+        pw[k2] = sq.x + sq.y;                         // norm_sqr = re*re + im*im (src/spectrogram.rs:1332-1334)
+    }
+    float *up = ptile + frame_col(f) + kFT * k1;
+    float *down = ptile + frame_col(f) + kFT * (200 - k1);
+#pragma unroll
+    for (int k2 = 0; k2 < 10; ++k2) up[kFT * 20 * k2] = pw[k2];
+    if (k1 != 10) down[0] = pw[10];
+    if (k1 != 0 && k1 != 10) {
+#pragma unroll
+        for (int k2 = 11; k2 < 20; ++k2) down[-kFT * 20 * (k2 - 10)] = pw[k2];
+    }
+}
+
 // Interior-tile prefetch by the four warps of a group, hop block by hop block: block b (160 samples = 80 float2 units)
 // goes to word 162 b, so source and destination advance by constants and a block costs three cp.async per lane.
 template <int GW>
@@ -201,8 +224,9 @@ __global__ void __launch_bounds__(kGroups * GW * 32, 1) k_r2c_fused_n400_tm(cons
     const uint32_t tm = *S.tmem_ptr;
 
     const int tpc = p.tiles_per_clip;
-    const long long total_tiles = static_cast<long long>(p.n_clips) * tpc;
-    const long long gstep = 4LL * gridDim.x;
+    const int total_tiles = p.n_clips * tpc;                 // the host splits batches so that this fits an int
+    const int gstep = 4 * static_cast<int>(gridDim.x);
+    const int step_clip = gstep / tpc, step_tile = gstep % tpc;
     const int q = warp & 3, wl = warp >> 2;                  // group = SM sub-partition = TMEM lane quarter; warp within the group
     const int gt = wl * 32 + lane;                           // thread within the group
     const uint32_t lane_base = tm + (static_cast<uint32_t>(32 * q) << 16);
@@ -213,10 +237,10 @@ __global__ void __launch_bounds__(kGroups * GW * 32, 1) k_r2c_fused_n400_tm(cons
     const int q0 = S.qrange[wl], q1 = S.qrange[wl + 1];
     const int bar = 1 + q;
 
-    long long g = 4LL * blockIdx.x + q;                      // this group's global tile index
+    int g = 4 * static_cast<int>(blockIdx.x) + q;            // this group's global tile index
+    int clip = g / tpc, tile = g % tpc;                      // ... and its (clip, tile); both advance by carry
     if (g < total_tiles) {                                   // prologue: pass 1 of the group's first tile
-        const long long clip = g / tpc, tile = g - clip * tpc;
-        load_tile(sig, xbase + clip * p.clip_stride, (p.frame_begin + tile * kFT) * kHop - p.pad, p.n_samples, vec_ok, gt, kGroupThreads,
+        load_tile(sig, xbase + static_cast<long long>(clip) * p.clip_stride, (p.frame_begin + static_cast<long long>(tile) * kFT) * kHop - p.pad, p.n_samples, vec_ok, gt, kGroupThreads,
                   kTileSamples / 2);
         cp_async_commit_wait_all();
         tc::bar_sync(bar, kGroupThreads);
@@ -229,12 +253,12 @@ __global__ void __launch_bounds__(kGroups * GW * 32, 1) k_r2c_fused_n400_tm(cons
     }
     for (; g < total_tiles; g += gstep) {
         // ---- phase B: Y(g) is complete in TMEM, the samples are dead, the power tile is free
-        const long long gn = g + gstep;
-        const bool has_next = gn < total_tiles;
+        const bool has_next = g + gstep < total_tiles;
+        int cn = clip + step_clip, tn = tile + step_tile;
+        if (tn >= tpc) { tn -= tpc; ++cn; }
         if (has_next) {
-            const long long cn = gn / tpc, tn = gn - cn * tpc;
-            const long long sn = (p.frame_begin + tn * kFT) * kHop - p.pad;
-            const float *xn = xbase + cn * p.clip_stride;
+            const long long sn = (p.frame_begin + static_cast<long long>(tn) * kFT) * kHop - p.pad;
+            const float *xn = xbase + static_cast<long long>(cn) * p.clip_stride;
             if (vec_ok && sn >= 0 && sn + kTileSamples <= p.n_samples) prefetch_tile_by_group<GW>(sig, xn + sn, wl, lane);
             else load_tile(sig, xn, sn, p.n_samples, vec_ok, gt, kGroupThreads, kTileSamples / 2);
         }
@@ -245,18 +269,17 @@ __global__ void __launch_bounds__(kGroups * GW * 32, 1) k_r2c_fused_n400_tm(cons
             y_row_request(lane_base, k1, yq);
             y_row_wait(yq);
             pass2_twiddle(yq, P.c.tw2[k1], k1, v);
-            pass2_finish(v, ptile, lane, k1);
+            pass2_finish_tm(v, ptile, lane, k1);
         }
         cp_async_commit_wait_all();
         tc::fence_before_sync();
         tc::bar_sync(bar, kGroupThreads);                    // P(g) complete, every Y row read, the next tile's samples have landed
         tc::fence_after_sync();
         // ---- phase A: the filterbank rows of tile g and pass 1 of the next tile, in opposite orders on alternate warps
-        const long long clip = g / tpc, tile = g - clip * tpc;
-        const long long f0 = p.frame_begin + tile * kFT;
+        const long long f0 = p.frame_begin + static_cast<long long>(tile) * kFT;
         const long long rem = p.frame_begin + p.frames_todo - f0;
         const int nf = rem < kFT ? static_cast<int>(rem) : kFT;
-        float *ocf = static_cast<float *>(p.out) + clip * p.out_clip_stride + (f0 - p.out_frame_origin);
+        float *ocf = static_cast<float *>(p.out) + static_cast<long long>(clip) * p.out_clip_stride + (f0 - p.out_frame_origin);
         if (wl & 1) rows_epilogue(p, ptile, S.quads, q0, q1, ocf, nf, lane);
         if (has_next) {
 #pragma unroll 1
@@ -267,6 +290,8 @@ __global__ void __launch_bounds__(kGroups * GW * 32, 1) k_r2c_fused_n400_tm(cons
         tc::fence_before_sync();
         tc::bar_sync(bar, kGroupThreads);                    // Y(next) complete; the power tile and the samples are free again
         tc::fence_after_sync();
+        clip = cn;
+        tile = tn;
     }
     tc::fence_before_sync();
     __syncthreads();

@@ -498,7 +498,7 @@ void select_family(sgx_plan &pl) {
             for (int q = 0; q < nq; ++q) {
                 cntU[q] = std::max(4, (qmax[q] + 3) & ~3);
                 for (int k = 0; k < 4; ++k) {
-                    const int r = order[4 * q + k];
+                    const int r = order[4 * q + k] >= 0 ? order[4 * q + k] : order[4 * q];
                     woq[4 * static_cast<size_t>(q) + k] = padded_tm;
                     padded_tm += (cntU[q] + 3) & ~3;
                     const int c0 = (r >= 0 && cnt[r]) ? pl.tab.col[pl.tab.row_ptr[r]] : 0;
@@ -523,7 +523,7 @@ void select_family(sgx_plan &pl) {
                 for (int q : per_warp[w]) {
                     tb[1 + Wt + 1 + idx] = cntU[q];
                     for (int k = 0; k < 4; ++k) {
-                        const int r = order[4 * q + k];
+                        const int r = order[4 * q + k] >= 0 ? order[4 * q + k] : order[4 * q];      // pad slots repeat the quad's first row
                         int *e = &tb[static_cast<size_t>(hdr) + 4 * (4 * static_cast<size_t>(idx) + k)];
                         e[0] = (r >= 0 && cnt[r]) ? pl.tab.col[pl.tab.row_ptr[r]] : 0;
                         e[1] = cntU[q];
