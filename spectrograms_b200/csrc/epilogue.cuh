@@ -126,35 +126,33 @@ __device__ __forceinline__ void epilogue_complex(const KParams &p, const typenam
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Variant for kernel families whose tile is "frames fastest": P[k * 32 + f], exactly 32 frames per tile, lane = frame.
-// One warp owns one output row at a time, so every filterbank weight / column index / DCT coefficient is warp-uniform
-// and every store is a 128-byte run of one output row. scratch: [row * 32 + f], >= n_bins * 32 elements (MFCC only).
-// lane_col: the column of this lane's frame inside a tile row (identity unless the family permutes frames in a row).
-template <typename T>
-__device__ __forceinline__ void epilogue_lane_frames(const KParams &p, T *__restrict__ P, T *__restrict__ scratch,
-                                                     int clip, long long f0, int nf, int lane_col) {
+// Variant for kernel families whose tile is "frames fastest", exactly 32 frames per tile, lane = frame. One warp owns one
+// output row at a time, so every filterbank weight / column index / DCT coefficient is warp-uniform and every store is a
+// 128-byte run of one output row. The tile is reached through two accessors bound to the calling lane's frame:
+// tile(k) = power of bin k (read / write), scratch(r) = row r of a second tile of >= n_bins rows (MFCC only).
+template <typename T, typename Tile, typename Scratch>
+__device__ __forceinline__ void epilogue_lane_frames_via(const KParams &p, Tile tile, Scratch scratch, int clip, long long f0, int nf) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const T eps = static_cast<T>(p.eps);
     T *out = static_cast<T *>(p.out) + static_cast<long long>(clip) * p.out_clip_stride + (f0 - p.out_frame_origin) + lane;
     const bool to_mfcc = (p.output == SGX_OUT_MFCC);
     const bool live = lane < nf;
-    const T *pl = P + lane_col;
 
     if (p.mapping == SGX_MAP_CHROMA) {
-        // same three steps as in epilogue_from_power; scratch rows are [c * 32 + lane]
-        for (int idx = threadIdx.x; idx < p.out_len * 32; idx += blockDim.x) P[idx] = t_sqrt(P[idx]);
+        // same three steps as in epilogue_from_power; scratch rows hold the un-normalised pitch classes
+        for (int k = warp; k < p.out_len; k += nwarps) tile(k) = t_sqrt(tile(k));
         __syncthreads();
         for (int row = warp; row < 12; row += nwarps) {
             const T *w = static_cast<const T *>(p.dense) + static_cast<long long>(row) * p.out_len;
             T acc = T(0);
-            for (int k = p.dense_c0; k < p.dense_c1; ++k) acc = t_add_rn(acc, t_mul_rn(__ldg(w + k), pl[k * 32]));
-            scratch[row * 32 + lane] = acc;
+            for (int k = p.dense_c0; k < p.dense_c1; ++k) acc = t_add_rn(acc, t_mul_rn(__ldg(w + k), tile(k)));
+            scratch(row) = acc;
         }
         __syncthreads();
         if (warp == 0) {
             T c[12];
 #pragma unroll
-            for (int i = 0; i < 12; ++i) c[i] = scratch[i * 32 + lane];
+            for (int i = 0; i < 12; ++i) c[i] = scratch(i);
             chroma_normalise<T>(c, p.chroma_norm);
             if (live) {
 #pragma unroll
@@ -166,19 +164,19 @@ __device__ __forceinline__ void epilogue_lane_frames(const KParams &p, T *__rest
     for (int row = warp; row < p.n_bins; row += nwarps) {
         T acc;
         if (p.mapping == SGX_MAP_LINEAR) {
-            acc = pl[row * 32];
+            acc = tile(row);
         } else if (p.mapping == SGX_MAP_ERB) {
             const T *w = static_cast<const T *>(p.dense) + static_cast<long long>(row) * p.out_len;
             acc = T(0);
-            for (int k = 0; k < p.out_len; ++k) acc = t_add_rn(acc, t_mul_rn(__ldg(w + k), pl[k * 32]));
+            for (int k = 0; k < p.out_len; ++k) acc = t_add_rn(acc, t_mul_rn(__ldg(w + k), tile(k)));
         } else {
             const T *val = static_cast<const T *>(p.val);
             const int e0 = __ldg(p.row_ptr + row), e1 = __ldg(p.row_ptr + row + 1);
             acc = T(0);
-            for (int e = e0; e < e1; ++e) acc = t_add_rn(acc, t_mul_rn(__ldg(val + e), pl[__ldg(p.col + e) * 32]));
+            for (int e = e0; e < e1; ++e) acc = t_add_rn(acc, t_mul_rn(__ldg(val + e), tile(__ldg(p.col + e))));
         }
         acc = amp_scale<T>(acc, p.amp, p.apply_db, eps);
-        if (to_mfcc) scratch[row * 32 + lane] = acc;
+        if (to_mfcc) scratch(row) = acc;
         else if (live) out[static_cast<long long>(row) * p.out_row_stride] = acc;
     }
     if (!to_mfcc) return;
@@ -186,14 +184,25 @@ __device__ __forceinline__ void epilogue_lane_frames(const KParams &p, T *__rest
     const T *dct = static_cast<const T *>(p.dct);
     const T *lift = static_cast<const T *>(p.lifter);
     const int rows = p.n_mfcc - p.mfcc_row0;
-    const T *ml = scratch + lane;
     for (int r = warp; r < rows; r += nwarps) {
         const int c = r + p.mfcc_row0;
         const T *b = dct + static_cast<long long>(c) * p.n_bins;
         T acc = T(0);
-        for (int i = 0; i < p.n_bins; ++i) acc = t_fma(ml[i * 32], __ldg(b + i), acc);
+        for (int i = 0; i < p.n_bins; ++i) acc = t_fma(scratch(i), __ldg(b + i), acc);
         if (live) out[static_cast<long long>(r) * p.out_row_stride] = acc * __ldg(lift + c);
     }
+}
+
+// the plain layout: P[k * 32 + f], scratch [row * 32 + f] (>= n_bins * 32 elements, MFCC only).
+// lane_col: the column of this lane's frame inside a tile row (identity unless the family permutes frames in a row).
+template <typename T> struct LinearTileAccess {
+    T *base;
+    __device__ __forceinline__ T &operator()(int k) const { return base[k * 32]; }
+};
+template <typename T>
+__device__ __forceinline__ void epilogue_lane_frames(const KParams &p, T *__restrict__ P, T *__restrict__ scratch,
+                                                     int clip, long long f0, int nf, int lane_col) {
+    epilogue_lane_frames_via<T>(p, LinearTileAccess<T>{P + lane_col}, LinearTileAccess<T>{scratch + (threadIdx.x & 31)}, clip, f0, nf);
 }
 
 }  // namespace sgx

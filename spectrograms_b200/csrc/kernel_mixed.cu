@@ -1,0 +1,230 @@
+// kernel_mixed.cu -- "r2c_fused_mixed": even n_fft = 2 L with L = R1 R2 R3 a product of small primes (2, 3, 5) that is
+// neither a power of two >= 256 nor the 400 / 160 f32 shape: 64 ... 1600 (f32) / 64 ... 800 (f64), e.g. 400 in f64 or at
+// any hop, 480, 800, 960, 1000, 1200 (the sizes the reference benches beside the powers of two,
+// benches/fft1d_benchmarks.rs:163-171). The per-frame work is SpectrogramPlan::compute (src/spectrogram.rs:240-294):
+// gather + centre zero padding + window (:1301-1320), real FFT (src/fft_backend.rs:423-431, here a packed L-point complex
+// FFT plus the split post pass), |X|^2 (:1332-1334), mapping, scaling, column store.
+//
+// Layout: one CTA = one tile of 32 consecutive frames of one clip, LANE = FRAME. The tile's packed spectra live in shared
+// memory as z[element][frame] with a row stride of 33 complex values: a warp reading or writing one element of all 32
+// frames touches 32 consecutive words (conflict free), and the load phase, where a warp walks along the elements of ONE
+// frame (coalesced global reads), is conflict free as well because of the odd stride. Everything that depends on the
+// position inside a frame -- butterfly index, twiddle, filterbank row, output row -- is warp uniform: no per-thread index
+// arithmetic, twiddles come through uniform loads, and every store is a 128-byte run of one output row.
+//
+//   load     frame by frame: x[2n], x[2n+1] (coalesced 8/16-byte reads, zero outside the clip) times the window -> z[n][f]
+//   stages   decimation-in-frequency, IN PLACE, radix R1, R2 (, R3) register butterflies (mixed_dft.cuh: compile-time
+//            Cooley-Tukey on 2^a 3^b 5^c sizes), one butterfly per warp step, twiddles W_Ls^(m k) from the plan's W_L table.
+//            In place means no ping-pong buffer (the tile is the whole shared memory of an SM for L = 800) and no values held
+//            across a barrier; the price is a digit-reversed spectrum: bin k sits at pos(k) = (k % R1) L/R1 + ...
+//   post     bins k and L - k from Z[pos(k)], Z[pos(L-k)] and W_N^k; |X|^2 (or X) written back in place
+//   epilogue the lane = frame epilogue (epilogue.cuh) reading the tile through pos(): any mapping, scaling, fused DCT
+#include "epilogue.cuh"
+#include "launch.hpp"
+#include "mixed_dft.cuh"
+
+namespace sgx {
+namespace {
+
+using mx::Cx;
+
+constexpr int kFrames = 32;          // frames per tile = lanes
+constexpr int kRow = 33;             // complex elements between consecutive positions of the tile
+
+template <typename T> __device__ __forceinline__ Cx<T> ldg_cx(const Cx<T> *p);
+template <> __device__ __forceinline__ Cx<float> ldg_cx<float>(const Cx<float> *p) {
+    const float2 v = __ldg(reinterpret_cast<const float2 *>(p));
+    return {v.x, v.y};
+}
+template <> __device__ __forceinline__ Cx<double> ldg_cx<double>(const Cx<double> *p) {
+    const double2 v = __ldg(reinterpret_cast<const double2 *>(p));
+    return {v.x, v.y};
+}
+
+// position of bin k (k < L) after the in-place decimation-in-frequency stages
+template <int R1, int R2, int R3> __host__ __device__ constexpr int pos_of(int k) {
+    constexpr int L = R1 * R2 * R3;
+    return (k % R1) * (L / R1) + ((k / R1) % R2) * R3 + k / (R1 * R2);
+}
+
+// One in-place stage on blocks of length LS: butterfly b = (blk, m), elements blk LS + m + j LS/R, outputs times W_LS^(m k)
+template <typename T, int L, int LS, int R, int W>
+__device__ __forceinline__ void stage(Cx<T> *zf, const Cx<T> *__restrict__ tw, int warp) {
+    constexpr int M = LS / R;
+#pragma unroll 1
+    for (int b = warp; b < L / R; b += W) {
+        const int blk = b / M, m = b - blk * M;
+        Cx<T> *zb = zf + (blk * LS + m) * kRow;
+        Cx<T> v[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) v[j] = zb[j * M * kRow];
+        mx::Dft<T, R>::run(v);
+        if (M > 1 && m > 0) {
+            // W_LS^(m k) = W_L^(m k L / LS); m k < LS, so the table index needs no reduction
+            const Cx<T> *twm = tw + m * (L / LS);
+#pragma unroll
+            for (int k = 1; k < R; ++k) v[k] = v[k] * ldg_cx<T>(twm + (k - 1) * m * (L / LS));
+        }
+#pragma unroll
+        for (int k = 0; k < R; ++k) zb[k * M * kRow] = v[k];
+    }
+}
+
+template <typename T, int R1, int R2, int R3> struct TileAccess {
+    static constexpr int L = R1 * R2 * R3;
+    T *base;                       // lane's column of the tile, as T (the .x word of position 0)
+    __device__ __forceinline__ T &operator()(int k) const { return base[(k == L ? L : pos_of<R1, R2, R3>(k)) * (2 * kRow)]; }
+};
+template <typename T> struct ScratchAccess {       // the .y words of the same tile: rows of the log-mel tile of the fused MFCC
+    T *base;
+    __device__ __forceinline__ T &operator()(int r) const { return base[r * (2 * kRow)]; }
+};
+
+template <typename T, int R1, int R2, int R3, int W>
+__global__ void __launch_bounds__(32 * W, 1) k_r2c_fused_mixed(const __grid_constant__ KParams p) {
+    constexpr int L = R1 * R2 * R3, N = 2 * L;
+    using C = Cx<T>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C *z = reinterpret_cast<C *>(smem_raw);                     // [(L + 1) * kRow]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int clip = blockIdx.x / p.tiles_per_clip;
+    const int tile = blockIdx.x - clip * p.tiles_per_clip;
+    const long long f0 = p.frame_begin + static_cast<long long>(tile) * kFrames;
+    const long long rem = p.frame_begin + p.frames_todo - f0;
+    const int nf = rem < kFrames ? static_cast<int>(rem) : kFrames;
+    const T *x = static_cast<const T *>(p.samples) + static_cast<long long>(clip) * p.clip_stride;
+    const T *win = static_cast<const T *>(p.window);
+
+    // ---- load + window: warp = frame (strided), lanes along the packed elements n (samples 2n, 2n+1)
+#pragma unroll 1
+    for (int f = warp; f < kFrames; f += W) {
+        const long long base = (f0 + f) * p.hop - p.pad;
+        C *zf = z + f;
+        if (f >= nf) {                                          // frames beyond the clip's last: zeros (never stored)
+            for (int n = lane; n < L; n += 32) zf[n * kRow] = C{T(0), T(0)};
+        } else if ((p.vec_ok & 1) && base >= 0 && base + N <= p.n_samples) {
+            const C *xf = reinterpret_cast<const C *>(x + base);
+            const C *wf = reinterpret_cast<const C *>(win);
+#pragma unroll 4
+            for (int n = lane; n < L; n += 32) {
+                const C s = ldg_cx<T>(xf + n), w = ldg_cx<T>(wf + n);
+                zf[n * kRow] = C{s.x * w.x, s.y * w.y};          // sample * window[i] (src/spectrogram.rs:1319)
+            }
+        } else {
+            for (int n = lane; n < L; n += 32) {
+                const long long s0 = base + 2 * n;
+                const T a = (s0 >= 0 && s0 < p.n_samples) ? __ldg(x + s0) : T(0);
+                const T b = (s0 + 1 >= 0 && s0 + 1 < p.n_samples) ? __ldg(x + s0 + 1) : T(0);
+                zf[n * kRow] = C{a * __ldg(win + 2 * n), b * __ldg(win + 2 * n + 1)};
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- stages (lane = frame from here on)
+    C *zl = z + lane;
+    const C *tw = static_cast<const C *>(p.tw);
+    stage<T, L, L, R1, W>(zl, tw, warp);
+    __syncthreads();
+    if constexpr (R2 > 1) {
+        stage<T, L, L / R1, R2, W>(zl, tw, warp);
+        __syncthreads();
+    }
+    if constexpr (R3 > 1) {
+        stage<T, L, L / (R1 * R2), R3, W>(zl, tw, warp);
+        __syncthreads();
+    }
+
+    // ---- post pass: X[k] = E + W_N^k O, X[L-k] = conj(E - W_N^k O) from Z[k], Z[L-k]; results written back in place
+    const C *post = static_cast<const C *>(p.post);
+    const bool want_complex = p.output == SGX_OUT_COMPLEX_STFT;
+#pragma unroll 1
+    for (int k = warp; k <= L / 2; k += W) {
+        if (k == 0) {
+            const C z0 = zl[0];
+            const C x0 = {z0.x + z0.y, T(0)}, xl = {z0.x - z0.y, T(0)};      // bins 0 and L
+            if (want_complex) { zl[0] = x0; zl[L * kRow] = xl; }
+            else { zl[0].x = x0.x * x0.x; zl[L * kRow].x = xl.x * xl.x; }
+        } else {
+            const int pa = pos_of<R1, R2, R3>(k), pb = pos_of<R1, R2, R3>(L - k);
+            const C a = zl[pa * kRow], b = zl[pb * kRow];
+            const C ev = {T(0.5) * (a.x + b.x), T(0.5) * (a.y - b.y)};
+            const C od = {T(0.5) * (a.y + b.y), T(0.5) * (b.x - a.x)};
+            const C wo = od * ldg_cx<T>(post + k);
+            const C xa = ev + wo;                               // bin k
+            const C d = ev - wo;
+            const C xb = {d.x, -d.y};                           // bin L - k
+            if (want_complex) {
+                zl[pa * kRow] = xa;
+                zl[pb * kRow] = xb;                             // k = L/2: pa == pb and xa == xb up to the sign of a zero
+            } else {
+                zl[pa * kRow].x = xa.x * xa.x + xa.y * xa.y;   // norm_sqr (src/spectrogram.rs:1332-1334)
+                zl[pb * kRow].x = xb.x * xb.x + xb.y * xb.y;
+            }
+        }
+    }
+    __syncthreads();
+
+    if (want_complex) {
+        // StftPlan::compute column copy (src/spectrogram.rs:1440-1442): one 128-byte (f32: 256-byte) run of frames per bin row
+        using OC = typename Cplx<T>::type;
+        OC *out = static_cast<OC *>(p.out) + static_cast<long long>(clip) * p.out_clip_stride + (f0 - p.out_frame_origin) + lane;
+        if (lane < nf) {
+#pragma unroll 1
+            for (int k = warp; k <= L; k += W) {
+                const C v = zl[(k == L ? L : pos_of<R1, R2, R3>(k)) * kRow];
+                out[static_cast<long long>(k) * p.out_row_stride] = mk<T>(v.x, v.y);
+            }
+        }
+        return;
+    }
+    T *col = reinterpret_cast<T *>(zl);
+    epilogue_lane_frames_via<T>(p, TileAccess<T, R1, R2, R3>{col}, ScratchAccess<T>{col + 1}, clip, f0, nf);
+}
+
+template <typename T, int R1, int R2, int R3, int W>
+cudaError_t launch_one(const KParams &p, cudaStream_t stream) {
+    constexpr int L = R1 * R2 * R3;
+    const size_t smem = sizeof(Cx<T>) * static_cast<size_t>(L + 1) * kRow;
+    const long long grid = static_cast<long long>(p.n_clips) * p.tiles_per_clip;
+    if (grid <= 0) return cudaSuccess;
+    if (grid > 2147483647LL) return cudaErrorInvalidConfiguration;
+    cudaError_t e = cudaFuncSetAttribute(k_r2c_fused_mixed<T, R1, R2, R3, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    k_r2c_fused_mixed<T, R1, R2, R3, W><<<static_cast<unsigned>(grid), 32 * W, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+// the sizes with a compiled instance: n_fft -> (R1, R2, R3)
+#define SGX_MIXED_SIZES(X) \
+    X(64, 8, 4, 1) X(128, 8, 8, 1) X(160, 10, 8, 1) X(200, 10, 10, 1) X(240, 12, 10, 1) X(320, 16, 10, 1) X(400, 20, 10, 1) \
+    X(480, 16, 15, 1) X(500, 25, 10, 1) X(600, 20, 15, 1) X(640, 20, 16, 1) X(800, 20, 20, 1) X(960, 24, 20, 1) \
+    X(1000, 25, 20, 1) X(1200, 25, 24, 1) X(1600, 10, 10, 8)
+
+}  // namespace
+
+bool mixed_supported(size_t n_fft, bool f64) {
+#define X(NFFT, A, B, C) if (n_fft == NFFT) return !f64 || NFFT <= 800;
+    SGX_MIXED_SIZES(X)
+#undef X
+    return false;
+}
+size_t mixed_smem_bytes(size_t n_fft, bool f64) { return (f64 ? 16 : 8) * (n_fft / 2 + 1) * static_cast<size_t>(kRow); }
+int mixed_tile_frames() { return kFrames; }
+// rows the fused MFCC can park in the tile (the .y words of positions 0 .. L)
+int mixed_max_scratch_rows(size_t n_fft) { return static_cast<int>(n_fft / 2 + 1); }
+
+cudaError_t launch_mixed(const KParams &p, bool f64, cudaStream_t stream) {
+    constexpr int W = 16;
+#define X(NFFT, A, B, C)                                                                     \
+    if (p.n_fft == NFFT) {                                                                   \
+        if (!f64) return launch_one<float, A, B, C, W>(p, stream);                           \
+        if constexpr (NFFT <= 800) return launch_one<double, A, B, C, W>(p, stream);         \
+    }
+    SGX_MIXED_SIZES(X)
+#undef X
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace sgx

@@ -53,6 +53,14 @@ int pow2_frame_elems(size_t n_fft, bool f64);
 size_t pow2_bulk_stage_bytes(size_t n_fft, size_t hop, bool f64);   // extra smem of the cp.async.bulk staged variant (0: none)
 cudaError_t launch_pow2(const KParams &p, bool f64, size_t smem_bytes, cudaStream_t stream);
 
+// r2c_fused_mixed: even n_fft = 2 R1 R2 R3 with small prime factors that no other fast family serves (kernel_mixed.cu):
+// 32-frame tiles, lane = frame, in-place register-radix stages. p.tw / p.post / p.window are the generic family's tables.
+bool mixed_supported(size_t n_fft, bool f64);
+size_t mixed_smem_bytes(size_t n_fft, bool f64);
+int mixed_tile_frames();
+int mixed_max_scratch_rows(size_t n_fft);
+cudaError_t launch_mixed(const KParams &p, bool f64, cudaStream_t stream);
+
 // standalone mfcc_from_log_mel (kernel_mfcc.cu): log_mel [n_clips][n_mels][n_frames] -> out [n_clips][rows][n_frames]
 cudaError_t launch_mfcc(bool f64, const void *log_mel, void *out, long long n_clips, int n_mels, long long n_frames,
                         int n_mfcc, int row0, const void *dct, const void *lifter, cudaStream_t stream);

@@ -143,6 +143,7 @@ struct sgx_plan {
     std::string kernel_name = "r2c_fused_generic";
     bool fast400 = false;            // eligible for r2c_fused_n400
     bool pow2 = false;               // eligible for r2c_fused_pow2
+    bool mixed = false;              // eligible for r2c_fused_mixed (even 2^a 3^b 5^c sizes with a compiled instance)
     int pow2_ft = 1, pow2_frame_stride = 0, pow2_tile_stride = 0;
     size_t pow2_smem = 0;
     bool fast400_sparse = false;     // ... with the shared-memory sparse table
@@ -420,6 +421,9 @@ void select_family(sgx_plan &pl) {
             pl.pow2_smem = smem;
         }
     }
+    // mixed-radix family: the other even 2^a 3^b 5^c sizes (n_fft 400 in f64 or at another hop included)
+    pl.mixed = !pl.fast400 && !pl.pow2 && mixed_supported(d.n_fft, pl.f64) &&
+               (d.output != SGX_OUT_MFCC || static_cast<int>(pl.tab.n_bins) <= mixed_max_scratch_rows(d.n_fft));
     const bool csr = d.mapping == SGX_MAP_MEL || d.mapping == SGX_MAP_LOGHZ;
     // The shared-memory sparse schedule needs rows with contiguous columns (mel triangles, loghz pairs). Rows are sorted
     // by column count, grouped four at a time ("quads", padded with row = -1), and the quads are dealt to the kernel's
@@ -574,7 +578,7 @@ void select_family(sgx_plan &pl) {
     pl.fast400_tc = pl.tc_steps > 0;
     pl.fast400_tm = pl.fast400 && csr && contiguous && d.output == SGX_OUT_SPECTROGRAM && !pl.wofs_tm.empty() &&
                     fast400_tm_fits(pl.sparse_quads, pl.tm_weights);
-    pl.kernel_name = pl.fast400 ? "r2c_fused_n400" : pl.pow2 ? "r2c_fused_pow2" : "r2c_fused_generic";
+    pl.kernel_name = pl.fast400 ? "r2c_fused_n400" : pl.pow2 ? "r2c_fused_pow2" : pl.mixed ? "r2c_fused_mixed" : "r2c_fused_generic";
     // folded DCT basis for the fused MFCC epilogue: B[c][n-1-i] = (-1)^c B[c][i] -> half basis, tasks of 4 coefficients of
     // one parity: [task][i < n/2][4], even-coefficient tasks first
     pl.dct_folded.clear();
@@ -718,7 +722,7 @@ void run_device(sgx_plan &pl, const void *d_samples, size_t n_clips, size_t n_sa
     p.out_row_stride = out_row_stride;
     p.out_clip_stride = out_clip_stride;
     p.out_frame_origin = frame_begin;
-    const int tile_frames = pl.force_generic ? p.FT : pl.fast400 ? 32 : pl.pow2 ? pl.pow2_ft : p.FT;
+    const int tile_frames = pl.force_generic ? p.FT : pl.fast400 ? 32 : pl.pow2 ? pl.pow2_ft : pl.mixed ? mixed_tile_frames() : p.FT;
     p.tiles_per_clip = static_cast<int>((frames_todo + tile_frames - 1) / tile_frames);
     // the grid is limited to 2^31-1 CTAs: split very large batches
     const long long max_clips = std::max<long long>(1, 2000000000LL / std::max(1, p.tiles_per_clip));
@@ -764,6 +768,12 @@ void run_device(sgx_plan &pl, const void *d_samples, size_t n_clips, size_t n_sa
                 smem += extra;
             }
             ck(launch_pow2(q, pl.f64, smem, stream), "kernel launch (r2c_fused_pow2)");
+        } else if (pl.mixed && !pl.force_generic) {
+            q.FT = mixed_tile_frames();
+            q.fd_FT = make_fastdiv(static_cast<unsigned>(q.FT));
+            q.vec_ok = (reinterpret_cast<uintptr_t>(q.samples) % (2 * pl.esize) == 0 && clip_stride % 2 == 0 &&
+                           pl.desc.hop_size % 2 == 0 && q.pad % 2 == 0) ? 1 : 0;
+            ck(launch_mixed(q, pl.f64, stream), "kernel launch (r2c_fused_mixed)");
         } else {
             ck(launch_generic(q, pl.f64, pl.smem_bytes, stream), "kernel launch (r2c_fused_generic)");
         }

@@ -76,7 +76,7 @@ def test_magphase_power_only_weights_the_itd_mask():
 
 
 # ------------------------------------------------------------------------------------------------- GPU parity
-CASES = [(512, 128, "r2c_fused_pow2"), (2048, 512, "r2c_fused_pow2"), (400, 160, "r2c_fused_generic"), (1000, 250, "r2c_fused_generic")]
+CASES = [(512, 128, "r2c_fused_pow2"), (2048, 512, "r2c_fused_pow2"), (400, 160, "r2c_fused_mixed"), (800, 200, "r2c_fused_mixed"), (1009, 250, "r2c_fused_generic")]
 
 
 @pytest.mark.gpu

@@ -93,7 +93,8 @@ CASES = [  # (n_fft, hop, sr, kernel family expected)
     (2048, 512, 22050.0, "r2c_fused_pow2"),      # the reference's own example shape (src/chroma.rs:476-477)
     (512, 128, 16000.0, "r2c_fused_pow2"),
     (400, 160, 16000.0, "r2c_fused_n400"),
-    (1000, 250, 16000.0, "r2c_fused_generic"),
+    (800, 200, 16000.0, "r2c_fused_mixed"),
+    (1009, 250, 16000.0, "r2c_fused_generic"),
 ]
 
 

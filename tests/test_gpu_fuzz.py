@@ -14,11 +14,13 @@ pytestmark = pytest.mark.gpu
 SR = 16000.0
 POW2 = [256, 512, 1024, 2048, 4096]
 OTHER = [400, 2, 3, 7, 30, 98, 250, 401, 600, 1000, 1009]
+MIXED = [64, 128, 160, 200, 240, 320, 400, 480, 500, 600, 640, 800, 960, 1000, 1200, 1600]      # r2c_fused_mixed
 WINDOWS = [("hanning", 0.0), ("hamming", 0.0), ("blackman", 0.0), ("rectangular", 0.0), ("kaiser", 8.6), ("gaussian", 40.0)]
 
 
 def draw(rng):
-    n_fft = int(rng.choice(POW2 if rng.random() < 0.5 else OTHER))
+    u = rng.random()
+    n_fft = int(rng.choice(POW2 if u < 0.35 else (MIXED if u < 0.7 else OTHER)))
     if n_fft == 400 and rng.random() < 0.6:
         hop = 160                                                   # the r2c_fused_n400 family
     else:
