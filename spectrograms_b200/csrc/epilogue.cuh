@@ -171,9 +171,17 @@ __device__ __forceinline__ void epilogue_lane_frames_via(const KParams &p, Tile 
             for (int k = 0; k < p.out_len; ++k) acc = t_add_rn(acc, t_mul_rn(__ldg(w + k), tile(k)));
         } else {
             const T *val = static_cast<const T *>(p.val);
-            const int e0 = __ldg(p.row_ptr + row), e1 = __ldg(p.row_ptr + row + 1);
             acc = T(0);
-            for (int e = e0; e < e1; ++e) acc = t_add_rn(acc, t_mul_rn(__ldg(val + e), tile(__ldg(p.col + e))));
+            if (p.rows_contig) {
+                // consecutive columns (every mel / loghz row): one descriptor load per row, no column indirection
+                const int4 d = __ldg(p.row_desc + row);          // {first entry, count, first column}
+                const T *w = val + d.x;
+#pragma unroll 4
+                for (int i = 0; i < d.y; ++i) acc = t_add_rn(acc, t_mul_rn(__ldg(w + i), tile(d.z + i)));
+            } else {
+                const int e0 = __ldg(p.row_ptr + row), e1 = __ldg(p.row_ptr + row + 1);
+                for (int e = e0; e < e1; ++e) acc = t_add_rn(acc, t_mul_rn(__ldg(val + e), tile(__ldg(p.col + e))));
+            }
         }
         acc = amp_scale<T>(acc, p.amp, p.apply_db, eps);
         if (to_mfcc) scratch(row) = acc;

@@ -17,8 +17,9 @@
 //            Cooley-Tukey on 2^a 3^b 5^c sizes), one butterfly per warp step, twiddles W_Ls^(m k) from the plan's W_L table.
 //            In place means no ping-pong buffer (the tile is the whole shared memory of an SM for L = 800) and no values held
 //            across a barrier; the price is a digit-reversed spectrum: bin k sits at pos(k) = (k % R1) L/R1 + ...
-//   post     bins k and L - k from Z[pos(k)], Z[pos(L-k)] and W_N^k; |X|^2 (or X) written back in place
-//   epilogue the lane = frame epilogue (epilogue.cuh) reading the tile through pos(): any mapping, scaling, fused DCT
+//   post     bins k and L - k from Z[pos(k)], Z[pos(L-k)] and W_N^k; |X|^2 (or X) is held in registers across one barrier
+//            and then written in NATURAL order over the (now dead) spectrum tile: P[bin][frame]
+//   epilogue the lane = frame epilogue (epilogue.cuh): any mapping, scaling, fused DCT; 128-byte row stores
 #include "epilogue.cuh"
 #include "launch.hpp"
 #include "mixed_dft.cuh"
@@ -70,18 +71,8 @@ __device__ __forceinline__ void stage(Cx<T> *zf, const Cx<T> *__restrict__ tw, i
     }
 }
 
-template <typename T, int R1, int R2, int R3> struct TileAccess {
-    static constexpr int L = R1 * R2 * R3;
-    T *base;                       // lane's column of the tile, as T (the .x word of position 0)
-    __device__ __forceinline__ T &operator()(int k) const { return base[(k == L ? L : pos_of<R1, R2, R3>(k)) * (2 * kRow)]; }
-};
-template <typename T> struct ScratchAccess {       // the .y words of the same tile: rows of the log-mel tile of the fused MFCC
-    T *base;
-    __device__ __forceinline__ T &operator()(int r) const { return base[r * (2 * kRow)]; }
-};
-
 template <typename T, int R1, int R2, int R3, int W>
-__global__ void __launch_bounds__(32 * W, 1) k_r2c_fused_mixed(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(32 * W, (32 * W <= 320 && sizeof(T) == 4) ? 2 : 1) k_r2c_fused_mixed(const __grid_constant__ KParams p) {
     constexpr int L = R1 * R2 * R3, N = 2 * L;
     using C = Cx<T>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -104,13 +95,21 @@ __global__ void __launch_bounds__(32 * W, 1) k_r2c_fused_mixed(const __grid_cons
         if (f >= nf) {                                          // frames beyond the clip's last: zeros (never stored)
             for (int n = lane; n < L; n += 32) zf[n * kRow] = C{T(0), T(0)};
         } else if ((p.vec_ok & 1) && base >= 0 && base + N <= p.n_samples) {
-            const C *xf = reinterpret_cast<const C *>(x + base);
-            const C *wf = reinterpret_cast<const C *>(win);
-#pragma unroll 4
-            for (int n = lane; n < L; n += 32) {
-                const C s = ldg_cx<T>(xf + n), w = ldg_cx<T>(wf + n);
-                zf[n * kRow] = C{s.x * w.x, s.y * w.y};          // sample * window[i] (src/spectrogram.rs:1319)
+            // interior frame: every load of the frame is issued before the first use (the latency is paid once per frame)
+            const C *xf = reinterpret_cast<const C *>(x + base) + lane;
+            const C *wf = reinterpret_cast<const C *>(win) + lane;
+            constexpr int NI = (L + 31) / 32;
+            C sv[NI], wv[NI];
+#pragma unroll
+            for (int i = 0; i < NI; ++i) {
+                if (32 * i + 31 < L || lane + 32 * i < L) {
+                    sv[i] = ldg_cx<T>(xf + 32 * i);
+                    wv[i] = ldg_cx<T>(wf + 32 * i);
+                }
             }
+#pragma unroll
+            for (int i = 0; i < NI; ++i)
+                if (32 * i + 31 < L || lane + 32 * i < L) zf[(lane + 32 * i) * kRow] = C{sv[i].x * wv[i].x, sv[i].y * wv[i].y};   // sample * window[i] (src/spectrogram.rs:1319)
         } else {
             for (int n = lane; n < L; n += 32) {
                 const long long s0 = base + 2 * n;
@@ -136,51 +135,65 @@ __global__ void __launch_bounds__(32 * W, 1) k_r2c_fused_mixed(const __grid_cons
         __syncthreads();
     }
 
-    // ---- post pass: X[k] = E + W_N^k O, X[L-k] = conj(E - W_N^k O) from Z[k], Z[L-k]; results written back in place
+    // ---- post pass: X[k] = E + W_N^k O, X[L-k] = conj(E - W_N^k O) from Z[pos(k)], Z[pos(L-k)]. Warp w owns the pairs
+    //      k = w, w + W, ... <= L/2; the results wait in registers for the barrier after which the spectrum tile is dead.
     const C *post = static_cast<const C *>(p.post);
     const bool want_complex = p.output == SGX_OUT_COMPLEX_STFT;
-#pragma unroll 1
-    for (int k = warp; k <= L / 2; k += W) {
+    constexpr int KPW = (L / 2 + 1 + W - 1) / W;                 // pairs per warp
+    auto pair_of = [&](int k, C &xa, C &xb) {
         if (k == 0) {
             const C z0 = zl[0];
-            const C x0 = {z0.x + z0.y, T(0)}, xl = {z0.x - z0.y, T(0)};      // bins 0 and L
-            if (want_complex) { zl[0] = x0; zl[L * kRow] = xl; }
-            else { zl[0].x = x0.x * x0.x; zl[L * kRow].x = xl.x * xl.x; }
+            xa = C{z0.x + z0.y, T(0)};                          // bin 0
+            xb = C{z0.x - z0.y, T(0)};                          // bin L
         } else {
-            const int pa = pos_of<R1, R2, R3>(k), pb = pos_of<R1, R2, R3>(L - k);
-            const C a = zl[pa * kRow], b = zl[pb * kRow];
+            const C a = zl[pos_of<R1, R2, R3>(k) * kRow], b = zl[pos_of<R1, R2, R3>(L - k) * kRow];
             const C ev = {T(0.5) * (a.x + b.x), T(0.5) * (a.y - b.y)};
             const C od = {T(0.5) * (a.y + b.y), T(0.5) * (b.x - a.x)};
             const C wo = od * ldg_cx<T>(post + k);
-            const C xa = ev + wo;                               // bin k
+            xa = ev + wo;                                       // bin k
             const C d = ev - wo;
-            const C xb = {d.x, -d.y};                           // bin L - k
-            if (want_complex) {
-                zl[pa * kRow] = xa;
-                zl[pb * kRow] = xb;                             // k = L/2: pa == pb and xa == xb up to the sign of a zero
-            } else {
-                zl[pa * kRow].x = xa.x * xa.x + xa.y * xa.y;   // norm_sqr (src/spectrogram.rs:1332-1334)
-                zl[pb * kRow].x = xb.x * xb.x + xb.y * xb.y;
-            }
+            xb = C{d.x, -d.y};                                  // bin L - k
         }
-    }
-    __syncthreads();
-
+    };
     if (want_complex) {
-        // StftPlan::compute column copy (src/spectrogram.rs:1440-1442): one 128-byte (f32: 256-byte) run of frames per bin row
+        // StftPlan::compute column copy (src/spectrogram.rs:1440-1442): the spectrum goes straight from registers to one run
+        // of frames per bin row
         using OC = typename Cplx<T>::type;
         OC *out = static_cast<OC *>(p.out) + static_cast<long long>(clip) * p.out_clip_stride + (f0 - p.out_frame_origin) + lane;
-        if (lane < nf) {
 #pragma unroll 1
-            for (int k = warp; k <= L; k += W) {
-                const C v = zl[(k == L ? L : pos_of<R1, R2, R3>(k)) * kRow];
-                out[static_cast<long long>(k) * p.out_row_stride] = mk<T>(v.x, v.y);
+        for (int k = warp; k <= L / 2; k += W) {
+            C xa, xb;
+            pair_of(k, xa, xb);
+            if (lane < nf) {
+                out[static_cast<long long>(k) * p.out_row_stride] = mk<T>(xa.x, xa.y);
+                out[static_cast<long long>(L - k) * p.out_row_stride] = mk<T>(xb.x, xb.y);
             }
         }
         return;
     }
-    T *col = reinterpret_cast<T *>(zl);
-    epilogue_lane_frames_via<T>(p, TileAccess<T, R1, R2, R3>{col}, ScratchAccess<T>{col + 1}, clip, f0, nf);
+    T pa[KPW], pb[KPW];
+#pragma unroll
+    for (int i = 0; i < KPW; ++i) {
+        const int k = warp + W * i;
+        if (k <= L / 2) {
+            C xa, xb;
+            pair_of(k, xa, xb);
+            pa[i] = xa.x * xa.x + xa.y * xa.y;                  // norm_sqr (src/spectrogram.rs:1332-1334)
+            pb[i] = xb.x * xb.x + xb.y * xb.y;
+        }
+    }
+    __syncthreads();
+    T *P = reinterpret_cast<T *>(smem_raw);                     // P[bin][32 frames], then the scratch rows of the fused MFCC
+#pragma unroll
+    for (int i = 0; i < KPW; ++i) {
+        const int k = warp + W * i;
+        if (k <= L / 2) {
+            P[k * 32 + lane] = pa[i];
+            P[(L - k) * 32 + lane] = pb[i];
+        }
+    }
+    __syncthreads();
+    epilogue_lane_frames<T>(p, P, P + (L + 1) * 32, clip, f0, nf, lane);
 }
 
 template <typename T, int R1, int R2, int R3, int W>
@@ -196,31 +209,31 @@ cudaError_t launch_one(const KParams &p, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
-// the sizes with a compiled instance: n_fft -> (R1, R2, R3)
+// the sizes with a compiled instance: n_fft -> (R1, R2, R3, warps). The warp count divides (or nearly divides) the butterfly
+// counts L / R of the stages, and stays at <= 10 warps up to n_fft 800 so that two CTAs share an SM.
 #define SGX_MIXED_SIZES(X) \
-    X(64, 8, 4, 1) X(128, 8, 8, 1) X(160, 10, 8, 1) X(200, 10, 10, 1) X(240, 12, 10, 1) X(320, 16, 10, 1) X(400, 20, 10, 1) \
-    X(480, 16, 15, 1) X(500, 25, 10, 1) X(600, 20, 15, 1) X(640, 20, 16, 1) X(800, 20, 20, 1) X(960, 24, 20, 1) \
-    X(1000, 25, 20, 1) X(1200, 25, 24, 1) X(1600, 10, 10, 8)
+    X(64, 8, 4, 1, 4) X(128, 8, 8, 1, 8) X(160, 10, 8, 1, 8) X(200, 10, 10, 1, 10) X(240, 12, 10, 1, 10) X(320, 16, 10, 1, 10) \
+    X(400, 20, 10, 1, 10) X(480, 16, 15, 1, 8) X(500, 25, 10, 1, 10) X(600, 20, 15, 1, 10) X(640, 20, 16, 1, 10) X(800, 20, 20, 1, 10) \
+    X(960, 24, 20, 1, 12) X(1000, 25, 20, 1, 10) X(1200, 25, 24, 1, 12) X(1600, 10, 10, 8, 20)
 
 }  // namespace
 
 bool mixed_supported(size_t n_fft, bool f64) {
-#define X(NFFT, A, B, C) if (n_fft == NFFT) return !f64 || NFFT <= 800;
+#define X(NFFT, A, B, C, WARPS) if (n_fft == NFFT) return !f64 || NFFT <= 800;
     SGX_MIXED_SIZES(X)
 #undef X
     return false;
 }
 size_t mixed_smem_bytes(size_t n_fft, bool f64) { return (f64 ? 16 : 8) * (n_fft / 2 + 1) * static_cast<size_t>(kRow); }
 int mixed_tile_frames() { return kFrames; }
-// rows the fused MFCC can park in the tile (the .y words of positions 0 .. L)
-int mixed_max_scratch_rows(size_t n_fft) { return static_cast<int>(n_fft / 2 + 1); }
+// rows of the log-mel tile the fused MFCC can park behind the power tile (both inside the dead spectrum tile)
+int mixed_max_scratch_rows(size_t n_fft) { return static_cast<int>((n_fft / 2 + 1) * (2 * kRow - 32) / 32); }
 
 cudaError_t launch_mixed(const KParams &p, bool f64, cudaStream_t stream) {
-    constexpr int W = 16;
-#define X(NFFT, A, B, C)                                                                     \
+#define X(NFFT, A, B, C, WARPS)                                                              \
     if (p.n_fft == NFFT) {                                                                   \
-        if (!f64) return launch_one<float, A, B, C, W>(p, stream);                           \
-        if constexpr (NFFT <= 800) return launch_one<double, A, B, C, W>(p, stream);         \
+        if (!f64) return launch_one<float, A, B, C, WARPS>(p, stream);                       \
+        if constexpr (NFFT <= 800) return launch_one<double, A, B, C, WARPS>(p, stream);     \
     }
     SGX_MIXED_SIZES(X)
 #undef X

@@ -15,7 +15,8 @@ sr, n, clips = 16000.0, 480000, 512
 dev = torch.device("cuda", 0)
 x = torch.randn((clips, n), device=dev, generator=torch.Generator(device=dev).manual_seed(3))
 rows = []
-for n_fft, hop, n_mels in ((400, 160, 80), (400, 160, 128), (512, 160, 80), (512, 128, 64), (1024, 256, 80), (1024, 256, 128), (2048, 512, 128), (800, 200, 80)):
+for n_fft, hop, n_mels in ((400, 160, 80), (400, 160, 128), (512, 160, 80), (512, 128, 64), (1024, 256, 80), (1024, 256, 128), (2048, 512, 128), (800, 200, 80),
+                           (400, 200, 80), (480, 160, 80), (960, 240, 80), (1000, 250, 128), (1200, 300, 128), (1600, 400, 128)):
     sp = sg.SpectrogramParams(sg.StftParams(n_fft, hop, "hanning", True), sr)
     plan = sg.SpectrogramPlanner(0).mel_plan(sp, sg.MelParams(n_mels, 0.0, sr / 2), sg.LogParams(-80.0), "db", "float32")
     out = plan.compute_batch(x)
@@ -31,6 +32,18 @@ for n_fft, hop, n_mels in ((400, 160, 80), (400, 160, 128), (512, 160, 80), (512
     ms = e0.elapsed_time(e1) / steps
     frames = clips * out.shape[2]
     byts = clips * n * 4 + out.numel() * 4
-    rows.append({"n_fft": n_fft, "hop": hop, "n_mels": n_mels, "kernel": plan.kernel_name(), "ms_per_step": round(ms, 4),
+    generic_ms = None
+    if plan.kernel_name() == "r2c_fused_mixed":          # the same plan on the generic family, for the ratio
+        plan.force_generic(True)
+        plan.compute_batch(x, out)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(3):
+            plan.compute_batch(x, out)
+        e1.record()
+        torch.cuda.synchronize()
+        generic_ms = round(e0.elapsed_time(e1) / 3, 4)
+        plan.force_generic(False)
+    rows.append({"generic_ms": generic_ms, "n_fft": n_fft, "hop": hop, "n_mels": n_mels, "kernel": plan.kernel_name(), "ms_per_step": round(ms, 4),
                  "frames_per_s": frames / (ms * 1e-3), "algorithmic_GBps": byts / (ms * 1e-3) / 1e9})
 print(json.dumps({"workload": f"{clips} clips x 30 s @16 kHz f32 mel dB", "rows": rows}))
