@@ -161,6 +161,37 @@ __device__ __forceinline__ void epilogue_lane_frames_via(const KParams &p, Tile 
         }
         return;
     }
+    if ((p.mapping == SGX_MAP_MEL || p.mapping == SGX_MAP_LOGHZ) && p.rows_contig && (p.n_bins + nwarps - 1) / nwarps <= 32) {
+        // Rows with consecutive columns (every mel / loghz row). The global-memory latency is taken off the per-row chain:
+        // lane i fetches the descriptor of the warp's i-th row once, and the weights of the NEXT row (lane i = weight i, one
+        // coalesced load) while the current row is summed; both reach the other lanes through shuffles. Accumulation order
+        // and rounding are those of the loop below (ascending columns, acc += T(w) * x without FMA).
+        const T *val = static_cast<const T *>(p.val);
+        const int my_rows = (p.n_bins - warp + nwarps - 1) / nwarps;          // rows warp, warp + nwarps, ...
+        int4 mine = make_int4(0, 0, 0, 0);
+        if (lane < my_rows) mine = __ldg(p.row_desc + warp + lane * nwarps);  // {first entry, count, first column}
+        int e0n = __shfl_sync(0xffffffffu, mine.x, 0), cntn = __shfl_sync(0xffffffffu, mine.y, 0), c0n = __shfl_sync(0xffffffffu, mine.z, 0);
+        T wn = (my_rows > 0 && lane < cntn) ? __ldg(val + e0n + lane) : T(0);
+        for (int r = 0; r < my_rows; ++r) {
+            const int row = warp + r * nwarps;
+            const int e0 = e0n, cnt = cntn, c0 = c0n;
+            const T wv = wn;
+            if (r + 1 < my_rows) {
+                e0n = __shfl_sync(0xffffffffu, mine.x, r + 1);
+                cntn = __shfl_sync(0xffffffffu, mine.y, r + 1);
+                c0n = __shfl_sync(0xffffffffu, mine.z, r + 1);
+                wn = lane < cntn ? __ldg(val + e0n + lane) : T(0);
+            }
+            T acc = T(0);
+            const int head = cnt < 32 ? cnt : 32;
+#pragma unroll 4
+            for (int i = 0; i < head; ++i) acc = t_add_rn(acc, t_mul_rn(__shfl_sync(0xffffffffu, wv, i), tile(c0 + i)));
+            for (int i = 32; i < cnt; ++i) acc = t_add_rn(acc, t_mul_rn(__ldg(val + e0 + i), tile(c0 + i)));
+            acc = amp_scale<T>(acc, p.amp, p.apply_db, eps);
+            if (to_mfcc) scratch(row) = acc;
+            else if (live) out[static_cast<long long>(row) * p.out_row_stride] = acc;
+        }
+    } else
     for (int row = warp; row < p.n_bins; row += nwarps) {
         T acc;
         if (p.mapping == SGX_MAP_LINEAR) {
@@ -171,17 +202,9 @@ __device__ __forceinline__ void epilogue_lane_frames_via(const KParams &p, Tile 
             for (int k = 0; k < p.out_len; ++k) acc = t_add_rn(acc, t_mul_rn(__ldg(w + k), tile(k)));
         } else {
             const T *val = static_cast<const T *>(p.val);
+            const int e0 = __ldg(p.row_ptr + row), e1 = __ldg(p.row_ptr + row + 1);
             acc = T(0);
-            if (p.rows_contig) {
-                // consecutive columns (every mel / loghz row): one descriptor load per row, no column indirection
-                const int4 d = __ldg(p.row_desc + row);          // {first entry, count, first column}
-                const T *w = val + d.x;
-#pragma unroll 4
-                for (int i = 0; i < d.y; ++i) acc = t_add_rn(acc, t_mul_rn(__ldg(w + i), tile(d.z + i)));
-            } else {
-                const int e0 = __ldg(p.row_ptr + row), e1 = __ldg(p.row_ptr + row + 1);
-                for (int e = e0; e < e1; ++e) acc = t_add_rn(acc, t_mul_rn(__ldg(val + e), tile(__ldg(p.col + e))));
-            }
+            for (int e = e0; e < e1; ++e) acc = t_add_rn(acc, t_mul_rn(__ldg(val + e), tile(__ldg(p.col + e))));
         }
         acc = amp_scale<T>(acc, p.amp, p.apply_db, eps);
         if (to_mfcc) scratch(row) = acc;
