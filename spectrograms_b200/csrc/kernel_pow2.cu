@@ -650,13 +650,24 @@ k_c2r_pow2(const __grid_constant__ KParams p, const typename Cplx<T>::type *__re
     const C *tw = static_cast<const C *>(p.tw);
     const C *post = static_cast<const C *>(p.post);
 
-    // ---- stage X[k][f0 .. f0 + nf) as S[f][k] (frames fastest across lanes)
+    // ---- stage X[k][f0 .. f0 + nf) as S[f][k]: thread (kb, f) = (tid / FT, tid % FT) walks the bins kb, kb + TPF, ... with all
+    //      17 loads issued before the first store (one DRAM round trip per tile)
     {
-        const C2 *X = stft + static_cast<long long>(clip) * (M + 1) * n_frames + f0;
-        C2 *S = reinterpret_cast<C2 *>(zbuf);
-        for (int idx = tid; idx < (M + 1) * FT; idx += NT) {
-            const int k = idx / FT, f = idx - k * FT;
-            S[f * ZS + k] = f < nf ? X[static_cast<long long>(k) * n_frames + f] : mk<T>(T(0), T(0));
+        const int kb = tid / FT, f = tid - kb * FT;
+        const bool live = f < nf;
+        const C2 *X = stft + static_cast<long long>(clip) * (M + 1) * n_frames + f0 + (live ? f : 0);
+        C2 *S = reinterpret_cast<C2 *>(zbuf) + f * ZS;
+        constexpr int KI = (M + 1 + TPF - 1) / TPF;
+        C2 xv[KI];
+#pragma unroll
+        for (int i = 0; i < KI; ++i) {
+            const int k = kb + i * TPF;
+            xv[i] = (live && k <= M) ? __ldg(X + static_cast<long long>(k) * n_frames) : mk<T>(T(0), T(0));
+        }
+#pragma unroll
+        for (int i = 0; i < KI; ++i) {
+            const int k = kb + i * TPF;
+            if (k <= M) S[k] = xv[i];
         }
     }
     __syncthreads();
@@ -713,6 +724,155 @@ k_c2r_pow2(const __grid_constant__ KParams p, const typename Cplx<T>::type *__re
         }
         dst[m] = x;
     }
+}
+
+// istft in ONE kernel (src/spectrogram.rs:4813-4911): inverse FFT, synthesis window, overlap-add and window-energy
+// normalisation on a halo tile, so the windowed time frames never travel through HBM (they were n_fft / hop times the signal
+// size written and read back). The overlap-add buffer is cut into slots of `hop` samples; a CTA owns FT - H consecutive slots
+// (H = ceil(n_fft / hop) - 1) and inverts the FT frames that reach into them: frames s0 - H .. s0 + FT - H - 1. The frames stay
+// in shared memory (conj, 1 / M scale and window applied in place by the thread that owns each pair); one thread per output
+// sample then adds the frames that cover it in ascending frame order -- the reference's accumulation order (:4874-4881) --
+// and divides by the accumulated squared window where it exceeds 1e-10 (:4885-4890). Redundancy: FT / (FT - H) inverse FFTs.
+template <typename T, int M, int FT>
+__global__ void __launch_bounds__(FT *(M / 16), (sizeof(T) == 4 ? 4 : 2) * 256 / (FT * (M / 16) > 256 ? FT * (M / 16) : 256))
+k_istft_pow2(const __grid_constant__ KParams p, const typename Cplx<T>::type *__restrict__ stft, T *__restrict__ out, long long n_frames,
+             int halo, long long out_len, long long trim) {
+    constexpr int TPF = M / 16, N = 2 * M, B = M / 16, NT = FT * TPF;
+    constexpr int ZS = zs_of(M, FT);
+    using C = Cx<T>;
+    using C2 = typename Cplx<T>::type;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C *zbuf = reinterpret_cast<C *>(smem_raw);
+    const int tid = threadIdx.x;
+    int fl, t;
+    ThreadMap<TPF, FT>::get(tid, fl, t);
+    const int clip = blockIdx.x / p.tiles_per_clip;
+    const int tile = blockIdx.x - clip * p.tiles_per_clip;
+    const int own = FT - halo;                                        // slots this CTA writes
+    const long long s0 = static_cast<long long>(tile) * own;           // first slot
+    const long long f_first = s0 - halo;                               // frame held in tile slot 0 (may be negative)
+    C *z = zbuf + fl * ZS;
+    const C *tw = static_cast<const C *>(p.tw);
+    const C *post = static_cast<const C *>(p.post);
+
+    // ---- stage X[k][f_first .. f_first + FT) bin-major as S[k][f] with rows of FT + 1 elements: the global reads run along
+    //      frames, the shared-memory writes are consecutive, and the per-frame reads below (lanes along n, stride FT + 1) are at
+    //      most 2-way conflicted. Frames outside the clip are zero.
+    constexpr int SR = FT + 1;
+    {
+        // thread (kb, f) = (tid / FT, tid % FT) walks the bins kb, kb + TPF, ...: 17 independent loads, all issued before the
+        // first store (one DRAM round trip per tile instead of 17)
+        const int kb = tid / FT, f = tid - kb * FT;
+        const long long fg = f_first + f;
+        const bool live = fg >= 0 && fg < n_frames;
+        const C2 *X = stft + static_cast<long long>(clip) * (M + 1) * n_frames + (live ? fg : 0);
+        C2 *S = reinterpret_cast<C2 *>(zbuf) + f;
+        constexpr int KI = (M + 1 + TPF - 1) / TPF;
+        C2 xv[KI];
+#pragma unroll
+        for (int i = 0; i < KI; ++i) {
+            const int k = kb + i * TPF;
+            xv[i] = (live && k <= M) ? __ldg(X + static_cast<long long>(k) * n_frames) : mk<T>(T(0), T(0));
+        }
+#pragma unroll
+        for (int i = 0; i < KI; ++i) {
+            const int k = kb + i * TPF;
+            if (k <= M) S[k * SR] = xv[i];
+        }
+    }
+    __syncthreads();
+    C v[16];
+    {
+        const C *S = zbuf + fl;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int n = t + j * B;
+            C a = S[n * SR], b = S[(M - n) * SR];
+            if (n == 0) { a.y = T(0); b.y = T(0); }
+            const C e = {T(0.5) * (a.x + b.x), T(0.5) * (a.y - b.y)};
+            const C d = {T(0.5) * (a.x - b.x), T(0.5) * (a.y + b.y)};
+            const C w = ldg_cx<T>(post + n);
+            const C o = {d.x * w.x + d.y * w.y, d.y * w.x - d.x * w.y};
+            v[j] = {e.x - o.y, -(e.y + o.x)};
+        }
+    }
+    __syncthreads();
+    pass_store<T, M, 16, 1>(z, t, v);
+    frame_sync<TPF, FT>(fl);
+    if constexpr (Radices<M>::P16 >= 2) {
+        pass_load<T, M, 16, 16>(z, tw, t, v);
+        frame_sync<TPF, FT>(fl);
+        pass_store<T, M, 16, 16>(z, t, v);
+        frame_sync<TPF, FT>(fl);
+    }
+    if constexpr (Radices<M>::P16 >= 3) {
+        pass_load<T, M, 16, 256>(z, tw, t, v);
+        frame_sync<TPF, FT>(fl);
+        pass_store<T, M, 16, 256>(z, t, v);
+        frame_sync<TPF, FT>(fl);
+    }
+    if constexpr (Radices<M>::LAST > 1) {
+        constexpr int CUR = M / Radices<M>::LAST;
+        pass_load<T, M, Radices<M>::LAST, CUR>(z, tw, t, v);
+        frame_sync<TPF, FT>(fl);
+        pass_store<T, M, Radices<M>::LAST, CUR>(z, t, v);
+        frame_sync<TPF, FT>(fl);
+    }
+    // ---- conj, scale, window in place: thread t owns packed samples m = t + TPF * u of its frame
+    {
+        const T scale = T(1) / static_cast<T>(M);
+        const C *win = reinterpret_cast<const C *>(static_cast<const T *>(p.window));
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int m = t + TPF * u;
+            const C y = z[pad16(m)];
+            const C w = ldg_cx<T>(win + m);
+            z[pad16(m)] = C{y.x * scale * w.x, -y.y * scale * w.y};        // time_frame[i] *= window[i] (:4868-4870)
+        }
+    }
+    __syncthreads();
+    // ---- overlap-add + normalisation of the slots this CTA owns. Slot s (tile-local), offset i0 < hop: position
+    //      (s0 + s) hop + i0 is covered by the frames s0 + s - j at sample i0 + j hop (< n_fft), j = 0 .. halo; ascending frame
+    //      order = descending j. No divisions: everything is tile-local 32-bit arithmetic.
+    const int hop = p.hop;
+    const long long total = (n_frames - 1) * static_cast<long long>(hop) + N;      // untrimmed length (:4837)
+    const T *winT = static_cast<const T *>(p.window);
+    T *oc = out + static_cast<long long>(clip) * out_len;
+    const FastDiv fd_hop = p.fd_out_len;                               // the host stores make_fastdiv(hop) here for this kernel
+    for (int idx = tid; idx < own * hop; idx += NT) {
+        const int sl = fd_div(idx, fd_hop), i0 = idx - sl * hop;
+        const long long slot = s0 + sl;                                 // this slot = frame index of its newest covering frame
+        const long long pos0 = slot * hop;
+        const long long o = pos0 + i0 - trim;
+        if (pos0 + i0 >= total || o < 0 || o >= out_len) continue;
+        // frames that exist: 0 <= slot - j <= n_frames - 1
+        const int j_min = slot > n_frames - 1 ? static_cast<int>(slot - (n_frames - 1)) : 0;
+        const int j_cap = slot < halo ? static_cast<int>(slot) : halo;
+        T acc = T(0), norm = T(0);
+        for (int j = j_cap; j >= j_min; --j) {                         // ascending frames (:4874-4881)
+            const int i = i0 + j * hop;
+            if (i >= N) continue;
+            const C y = zbuf[(sl + halo - j) * ZS + pad16(i >> 1)];
+            const T w = __ldg(winT + i);
+            acc = t_add_rn(acc, (i & 1) ? y.y : y.x);
+            norm = t_add_rn(norm, t_mul_rn(w, w));
+        }
+        if (norm > static_cast<T>(1e-10)) acc = acc / norm;            // :4885-4890
+        oc[o] = acc;
+    }
+}
+
+template <typename T, int M, int FT>
+cudaError_t launch_istft_one(const KParams &p, size_t smem, const void *stft, void *out, long long n_clips, long long n_frames, int halo,
+                             long long out_len, long long trim, cudaStream_t stream) {
+    const long long grid = n_clips * p.tiles_per_clip;
+    if (grid <= 0) return cudaSuccess;
+    if (grid > 2147483647LL) return cudaErrorInvalidConfiguration;
+    cudaError_t e = cudaFuncSetAttribute(k_istft_pow2<T, M, FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    k_istft_pow2<T, M, FT><<<static_cast<unsigned>(grid), FT *(M / 16), smem, stream>>>(p, static_cast<const typename Cplx<T>::type *>(stft),
+                                                                                        static_cast<T *>(out), n_frames, halo, out_len, trim);
+    return cudaGetLastError();
 }
 
 template <typename T, int M, int FT>
@@ -807,6 +967,31 @@ cudaError_t launch_c2r_pow2(const KParams &p, bool f64, const void *stft, void *
         default: return cudaErrorInvalidValue;
     }
 #undef SGX_POW2_C2R
+}
+
+// complex elements of the fused istft's shared memory: the pass buffers, or the bin-major staging tile if that is larger
+static constexpr size_t istft_elems(int M) {
+    const size_t a = static_cast<size_t>(ft16_of(M)) * zs_of(M, ft16_of(M)), b = static_cast<size_t>(M + 1) * (ft16_of(M) + 1);
+    return a > b ? a : b;
+}
+// fused istft on a halo tile (k_istft_pow2): p.tiles_per_clip = ceil(ceil(total / hop) / (FT - halo)) with FT =
+// pow2_c2r_frames_per_tile(n_fft); requires halo < FT
+cudaError_t launch_istft_pow2(const KParams &p, bool f64, const void *stft, void *out, long long n_clips, long long n_frames, int halo,
+                              long long out_len, long long trim, cudaStream_t stream) {
+#define SGX_POW2_ISTFT(MM)                                                                                                       \
+    case MM:                                                                                                                     \
+        return f64 ? launch_istft_one<double, MM, ft16_of(MM)>(p, sizeof(double) * 2 * istft_elems(MM), stft, out, n_clips, n_frames, halo, out_len, trim, stream) \
+                   : launch_istft_one<float, MM, ft16_of(MM)>(p, sizeof(float) * 2 * istft_elems(MM), stft, out, n_clips, n_frames, halo, out_len, trim, stream);
+    switch (p.n_fft / 2) {
+        SGX_POW2_ISTFT(128)
+        SGX_POW2_ISTFT(256)
+        SGX_POW2_ISTFT(512)
+        SGX_POW2_ISTFT(1024)
+        SGX_POW2_ISTFT(2048)
+        SGX_POW2_ISTFT(4096)
+        default: return cudaErrorInvalidValue;
+    }
+#undef SGX_POW2_ISTFT
 }
 
 }  // namespace sgx

@@ -84,7 +84,11 @@ cudaError_t launch_c2r_frames(const KParams &p, bool f64, size_t smem, const voi
 // the same on the register radix-16 passes of r2c_fused_pow2 (kernel_pow2.cu); p.tiles_per_clip = ceil(n_frames / FT)
 cudaError_t launch_c2r_pow2(const KParams &p, bool f64, const void *stft, void *frames_out, long long n_clips,
                             long long n_frames, int apply_window, cudaStream_t stream);
-int pow2_c2r_frames_per_tile(size_t n_fft);      // tiles of the inverse kernel: p.tiles_per_clip = ceil(n_frames / this)
+int pow2_c2r_frames_per_tile(size_t n_fft);
+// istft fused on a halo tile (kernel_pow2.cu: k_istft_pow2): Hermitian STFT -> out [n_clips][out_len] directly. halo =
+// ceil(n_fft / hop) - 1 < pow2_c2r_frames_per_tile(n_fft); p.tiles_per_clip = ceil(ceil(total / hop) / (FT - halo))
+cudaError_t launch_istft_pow2(const KParams &p, bool f64, const void *stft, void *out, long long n_clips, long long n_frames, int halo,
+                              long long out_len, long long trim, cudaStream_t stream);      // tiles of the inverse kernel: p.tiles_per_clip = ceil(n_frames / this)
 cudaError_t launch_ola_gather(bool f64, const void *frames, const void *window, void *out, long long n_clips, long long n_frames,
                               int n_fft, int hop, long long out_len, long long trim, cudaStream_t stream);
 

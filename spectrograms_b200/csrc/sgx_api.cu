@@ -1377,8 +1377,26 @@ sgx_status sgx_plan_istft(sgx_plan *plan, const void *stft, size_t n_clips, size
                 ck(cudaMemcpyAsync(s.d_in, src, nc * stft_bytes, cudaMemcpyHostToDevice, st), "H2D copy");
                 src = s.d_in;
             }
-            run_inverse(pl, src, nc, n_frames, pl.d_frames, 1, st);
             void *dst = host ? s.d_out : static_cast<char *>(out) + c0 * out_len * es;
+            // power-of-two plans: inverse FFT + window + overlap-add + normalisation in one kernel on a halo tile, as long as
+            // the frames that overlap one hop slot fit a tile with slots to spare
+            const int halo = static_cast<int>((n + hop - 1) / hop) - 1;
+            const int ft = pl.pow2 ? pow2_c2r_frames_per_tile(n) : 0;
+            static const bool unfused_env = std::getenv("SGX_ISTFT_UNFUSED") && std::atoi(std::getenv("SGX_ISTFT_UNFUSED")) != 0;
+            if (pl.pow2 && !pl.force_generic && !unfused_env && hop <= n && 2 * halo <= ft) {
+                KParams q;
+                fill_params(pl, q);
+                q.n_clips = static_cast<int>(nc);
+                const size_t slots = (full + hop - 1) / hop;
+                q.tiles_per_clip = static_cast<int>((slots + static_cast<size_t>(ft - halo) - 1) / static_cast<size_t>(ft - halo));
+                q.fd_out_len = make_fastdiv(static_cast<unsigned>(hop));        // the kernel's divisor for position -> (slot, offset)
+                ck(launch_istft_pow2(q, pl.f64, src, dst, static_cast<long long>(nc), static_cast<long long>(n_frames), halo,
+                                     static_cast<long long>(out_len), static_cast<long long>(trim ? pad : 0), st), "kernel launch (istft_pow2)");
+                pl.last_launches += 1;
+                if (host) ck(cudaMemcpyAsync(static_cast<char *>(out) + c0 * out_len * es, s.d_out, nc * out_len * es, cudaMemcpyDeviceToHost, st), "D2H copy");
+                continue;
+            }
+            run_inverse(pl, src, nc, n_frames, pl.d_frames, 1, st);
             ck(launch_ola_gather(pl.f64, pl.d_frames, pl.d_window, dst, static_cast<long long>(nc), static_cast<long long>(n_frames),
                                  static_cast<int>(n), static_cast<int>(hop), static_cast<long long>(out_len),
                                  static_cast<long long>(trim ? pad : 0), st), "kernel launch (ola_gather)");

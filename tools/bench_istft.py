@@ -39,5 +39,6 @@ frames = clips * S.shape[2]
 err = float((y[:, n_fft:-n_fft] - x[:, n_fft:y.shape[1] - n_fft]).abs().max())
 print(json.dumps({"workload": f"{clips} clips x 30 s @16 kHz, n_fft=512 hop=128 f32", "frames": frames,
                   "stft": {"kernel": plan.kernel_name(), "ms_per_step": ms_fwd, "frames_per_s": frames / (ms_fwd * 1e-3)},
-                  "istft": {"kernels": "c2r_pow2 + ola_gather", "ms_per_step": ms_inv, "frames_per_s": frames / (ms_inv * 1e-3)},
+                  "istft": {"kernels": "c2r_pow2 + ola_gather" if os.environ.get("SGX_ISTFT_UNFUSED") == "1" else "istft_pow2 (fused, halo tile)",
+                            "launches": plan.last_launch_count(), "ms_per_step": ms_inv, "frames_per_s": frames / (ms_inv * 1e-3)},
                   "round_trip_max_abs_error": err}))
