@@ -461,7 +461,9 @@ def main():
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    alg_bytes = algorithmic_bytes(w)
+    # a step may take several launches (chunks of one kernel, or the log-mel kernel followed by the DCT kernel): the roofline
+    # is bytes per launch over the average launch duration = bytes per step over the step duration
+    alg_bytes = algorithmic_bytes(w) / max(1, launches_per_step)
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     # DRAM bytes per launch from the committed `ncu --set full` capture of this kernel -- reported only while the kernel
     # sources still hash to what was captured (profiles/traffic.json: src_sha), otherwise null (a stale number is worse)
@@ -513,7 +515,7 @@ def main():
         "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f32" if w["dtype"] == "float32" else "f64", "data": "synthetic (seeded white noise, generated on device)",
         "config": config_of(w, world, args.scaling, total_clips),
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
         "clocks": clk, "host_numa_bound": bool(numa_bound),
     }
     if strong is not None:

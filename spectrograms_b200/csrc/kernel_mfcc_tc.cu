@@ -1,0 +1,234 @@
+// kernel_mfcc_tc.cu -- "dct2_lifter_tc": mfcc_from_log_mel (src/mfcc.rs:224-273) as a tensor-core GEMM, f32.
+//
+// The DCT-II of a log-mel spectrogram is the dense contraction MFCC[frames x n_mfcc] = LogMel[frames x n_mels] . B[n_mels x
+// n_mfcc] (dct_ii, src/mfcc.rs:278-292): 5 120 multiply-adds per frame at 128 mels / 40 coefficients, as much FP32 work as
+// the FFT of the frame. Here it runs on the tcgen05 tensor cores with a 3xTF32 split (A_hi B_hi + A_hi B_lo + A_lo B_hi,
+// relative error 5e-7: tools/ubench/tmem_probe.cu), FP32 accumulation in tensor memory, lifter and c0 drop fused on the way
+// out (src/mfcc.rs:294-316).
+//
+//   one persistent CTA per SM, 8 warps; a tile = 128 consecutive frames of one clip = the 128 rows (TMEM lanes) of the MMA.
+//   Warps q and q + 4 share SM sub-partition q (TMEM lanes 32q .. 32q+31, lane = frame) and split the mels between them.
+//   load     per 64-mel half a thread reads 32 values of its frame straight from global memory (a warp instruction covers 32
+//            consecutive frames of one mel row = 128 bytes); the loads of the NEXT half are issued before the current one is
+//            converted, on two register sets, so the memory latency hides behind the conversion and the MMAs
+//   split    each value into a TF32-exact hi part and the f32 remainder, written into tensor memory (tcgen05.st) as the A
+//            operand: two A buffers (one per register set), so half h+1 is converted while the MMAs of half h run
+//   mma      a ninth warp's lane 0 waits for a converted half (mbarrier) and issues tcgen05.mma.cta_group::1.kind::tf32, A from TMEM, B = the DCT basis from shared memory
+//            (K-major SWIZZLE_NONE core matrices, hi and lo tiles per 8-mel K step, built on the host), M = 128,
+//            N = n_mfcc rounded up to 16, three MMAs per K step; completion through tcgen05.commit -> mbarrier
+//   out      tcgen05.ld of the frame's coefficients (two D buffers: tile t-1 is drained while tile t multiplies) ->
+//            lifter -> one 128-byte run of frames per coefficient row
+#include "launch.hpp"
+#include "tcgen05.cuh"
+
+namespace sgx {
+namespace {
+
+constexpr int kTile = 128;                 // frames per tile = MMA rows
+constexpr int kThreads = 256;              // 8 conversion warps: two per SM sub-partition
+constexpr int kAllThreads = kThreads + 32; // + one warp whose lane 0 issues the MMAs
+constexpr int kHalf = 64;                  // mels per A buffer
+constexpr int kPart = 32;                  // mels per thread and half
+constexpr uint32_t kColA = 0;              // A buffers: [buf][hi 64 | lo 64]
+constexpr uint32_t kColD = 256;            // D buffers: [buf][64]
+constexpr uint32_t kTmemCols = 512;
+
+struct DctParams {
+    const float *log_mel;      // [n_clips][n_mels][in_row_stride]
+    float *out;                // [n_clips][rows][n_frames]
+    const float *blob;         // per 8-mel K step: N x 8 hi tile then lo tile (K-major core matrices), then lifter[n_mfcc]
+    long long n_frames, in_row_stride;
+    int n_clips, n_mels, kp, n_mfcc, row0, N, tiles_per_clip;
+};
+
+__global__ void __launch_bounds__(kAllThreads, 1) k_dct2_lifter_tc(const __grid_constant__ DctParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int n_steps = p.kp / 8;
+    const int b_floats = n_steps * 2 * p.N * 8;
+    float *sB = reinterpret_cast<float *>(smem_raw);                                  // basis tiles
+    float *sLift = sB + b_floats;                                                     // [64]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sLift + 64);                        // abar[2] (A buffer free), dbar[2] (D complete), rbar[2] (A buffer ready)
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 6);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp & 3, hp = warp >> 2;                    // SM sub-partition / TMEM lane quarter; which 32 mels of a half
+    const int frame_in_tile = 32 * q + lane;
+
+    for (int i = tid; i < b_floats; i += kAllThreads) sB[i] = __ldg(p.blob + i);
+    for (int i = tid; i < 64; i += kAllThreads) sLift[i] = i < p.n_mfcc ? __ldg(p.blob + b_floats + i) : 0.f;
+    if (warp == 0) tc::alloc(tmem_ptr, kTmemCols);
+    if (tid == 32) {
+        for (int i = 0; i < 4; ++i) tc::mbar_init(&bars[i], 1);
+        for (int i = 4; i < 6; ++i) tc::mbar_init(&bars[i], kThreads / 32);      // one arrival per conversion warp
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    tc::fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tm = *tmem_ptr;
+    const uint32_t lane_base = tm + (static_cast<uint32_t>(32 * q) << 16);
+    const uint32_t b_base = tc::smem_addr(sB);
+    const uint32_t idesc = tc::idesc_tf32(128, p.N);
+    const int n_halves = (p.kp + kHalf - 1) / kHalf;
+
+    const long long total = static_cast<long long>(p.n_clips) * p.tiles_per_clip;
+    const long long my_tiles = blockIdx.x < total ? (total - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long n_jobs = my_tiles * n_halves;              // job g = (tile g / n_halves of this CTA, half g % n_halves)
+
+    // the 32 values of this thread's frame for job g (zeros past the clip's last frame / the last mel)
+    auto load_job = [&](float (&v)[kPart], long long g) {
+        const long long it = g / n_halves;
+        const int h = static_cast<int>(g - it * n_halves);
+        const long long t = blockIdx.x + it * gridDim.x;
+        const long long clip = t / p.tiles_per_clip, tile = t - clip * p.tiles_per_clip;
+        const long long f = tile * kTile + frame_in_tile;
+        const int m0 = h * kHalf + hp * kPart;
+        const bool live = f < p.n_frames;
+        const float *src = p.log_mel + (clip * p.n_mels + m0) * p.in_row_stride + (live ? f : 0);
+#pragma unroll
+        for (int i = 0; i < kPart; ++i) v[i] = (live && m0 + i < p.n_mels) ? __ldg(src + static_cast<long long>(i) * p.in_row_stride) : 0.f;
+    };
+    // coefficients of tile `it` of this CTA: D buffer it & 1 -> lifter -> rows of the output; the two warps of a sub-partition
+    // split the 16-column chunks
+    auto drain = [&](long long it, uint32_t parity) {
+        const int pb = static_cast<int>(it & 1);
+        tc::mbar_wait(&bars[2 + pb], parity);
+        tc::fence_after_sync();
+        const long long t = blockIdx.x + it * gridDim.x;
+        const long long clip = t / p.tiles_per_clip, tile = t - clip * p.tiles_per_clip;
+        const long long f = tile * kTile + frame_in_tile;
+        float *o = p.out + clip * (p.n_mfcc - p.row0) * p.n_frames + f;
+        for (int c0 = 16 * hp; c0 < p.N; c0 += 32) {
+            uint32_t v[16];
+            tc::ld16(lane_base + kColD + 64u * pb + c0, v);
+            tc::wait_ld();
+            if (f < p.n_frames) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int c = c0 + i;
+                    if (c >= p.row0 && c < p.n_mfcc) o[static_cast<long long>(c - p.row0) * p.n_frames] = __uint_as_float(v[i]) * sLift[c];
+                }
+            }
+        }
+        tc::fence_before_sync();
+    };
+    uint32_t a_uses[2] = {0, 0};          // MMA groups committed on each A buffer so far (mbarrier parity)
+    uint32_t d_done = 0;                  // tiles whose MMAs have been committed
+    // one job: job g + 1 is requested into `nxt`, job g is converted from `cur` into A buffer g & 1 and multiplied
+    auto step = [&](float (&cur)[kPart], float (&nxt)[kPart], long long g) {
+        const long long it = g / n_halves;
+        const int h = static_cast<int>(g - it * n_halves), b = static_cast<int>(g & 1);
+        if (g + 1 < n_jobs) load_job(nxt, g + 1);
+        if (a_uses[b] > 0) {                                   // the MMAs that last read this A buffer are done
+            tc::mbar_wait(&bars[b], (a_uses[b] - 1) & 1);
+            tc::fence_after_sync();
+        }
+        const uint32_t acol = kColA + 128u * b + kPart * hp;
+#pragma unroll
+        for (int k = 0; k < kPart; k += 8) {
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float vh = tc::tf32_hi(cur[k + i]);
+                hi[i] = __float_as_uint(vh);
+                lo[i] = __float_as_uint(cur[k + i] - vh);
+            }
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(lane_base + acol + k), "r"(hi[0]),
+                         "r"(hi[1]), "r"(hi[2]), "r"(hi[3]), "r"(hi[4]), "r"(hi[5]), "r"(hi[6]), "r"(hi[7])
+                         : "memory");
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(lane_base + acol + 64 + k), "r"(lo[0]),
+                         "r"(lo[1]), "r"(lo[2]), "r"(lo[3]), "r"(lo[4]), "r"(lo[5]), "r"(lo[6]), "r"(lo[7])
+                         : "memory");
+        }
+        tc::wait_st();
+        tc::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&bars[4 + b]);          // this warp's 32 rows x 32 mels of the half are in TMEM
+        a_uses[b] += 1;
+        if (h == n_halves - 1) d_done += 1;
+        // drain the previous tile's coefficients while this tile multiplies (tile it - 1 was the ((it - 1) / 2)-th user of its buffer)
+        if (h == 0 && it > 0) drain(it - 1, static_cast<uint32_t>(((it - 1) >> 1) & 1));
+    };
+
+    if (warp == kThreads / 32) {
+        // ---- the MMA warp: waits for a converted half, multiplies it, signals the A buffer free (and the tile complete)
+        if (lane == 0) {
+            const uint64_t bdesc0 = tc::smem_desc_kmajor(b_base, 128, 256);
+            const uint64_t step_units = static_cast<uint64_t>(4 * p.N), lo_units = static_cast<uint64_t>(2 * p.N);
+            auto mma_first = [&](uint32_t d, uint32_t a, uint64_t bd, uint32_t id, bool acc) { tc::mma_tf32_ts(d, a, bd, id, acc ? 1u : 0u); };
+            for (long long g = 0; g < n_jobs; ++g) {
+                const long long it = g / n_halves;
+                const int h = static_cast<int>(g - it * n_halves), b = static_cast<int>(g & 1);
+                tc::mbar_wait(&bars[4 + b], static_cast<uint32_t>((g >> 1) & 1));
+                tc::fence_after_sync();
+                const int k0 = h * kHalf, kn = (p.kp - k0) < kHalf ? (p.kp - k0) : kHalf;      // mels of this half (multiple of 8)
+                const uint32_t a0 = tm + kColA + 128u * b, dcol = tm + kColD + 64u * static_cast<uint32_t>(it & 1);
+                // descriptors advance by constants: a K step's hi tile is 4 N, its lo tile 2 N sixteen-byte units further on
+                uint64_t bhi = bdesc0 + static_cast<uint64_t>(k0 / 8) * step_units;
+                mma_first(dcol, a0, bhi, idesc, h != 0);
+                tc::mma_tf32_ts(dcol, a0, bhi + lo_units, idesc, 1u);
+                tc::mma_tf32_ts(dcol, a0 + 64, bhi, idesc, 1u);
+                for (int k = 8; k < kn; k += 8) {
+                    bhi += step_units;
+                    tc::mma_tf32_ts(dcol, a0 + k, bhi, idesc, 1u);
+                    tc::mma_tf32_ts(dcol, a0 + k, bhi + lo_units, idesc, 1u);
+                    tc::mma_tf32_ts(dcol, a0 + 64 + k, bhi, idesc, 1u);
+                }
+                tc::commit(&bars[b]);
+                if (h == n_halves - 1) tc::commit(&bars[2 + (it & 1)]);
+            }
+        }
+    } else {
+        float va[kPart], vb[kPart];
+        if (n_jobs > 0) load_job(va, 0);
+        for (long long g = 0; g < n_jobs; g += 2) {
+            step(va, vb, g);
+            if (g + 1 < n_jobs) step(vb, va, g + 1);
+        }
+        if (my_tiles > 0) drain(my_tiles - 1, static_cast<uint32_t>(((my_tiles - 1) >> 1) & 1));
+    }
+    (void)d_done;
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::dealloc(tm, kTmemCols);
+}
+
+}  // namespace
+
+bool mfcc_tc_supported(int n_mels, int n_mfcc) { return n_mels >= 8 && n_mels <= 128 && n_mfcc >= 1 && n_mfcc <= 64; }
+int mfcc_tc_padded_mels(int n_mels) { return (n_mels + 7) & ~7; }
+int mfcc_tc_padded_coeffs(int n_mfcc) { return (n_mfcc + 15) & ~15; }
+// floats of the basis blob: per 8-mel K step an N x 8 hi tile and an N x 8 lo tile (float index (n / 8) * 64 + (k / 4) * 32 +
+// (n % 8) * 4 + k % 4 inside a tile), then n_mfcc lifter weights
+size_t mfcc_tc_blob_floats(int n_mels, int n_mfcc) {
+    return static_cast<size_t>(mfcc_tc_padded_mels(n_mels) / 8) * 2 * mfcc_tc_padded_coeffs(n_mfcc) * 8 + static_cast<size_t>(n_mfcc);
+}
+
+cudaError_t launch_mfcc_tc(const float *log_mel, long long in_row_stride, float *out, long long n_clips, int n_mels, long long n_frames, int n_mfcc,
+                           int row0, const float *blob, int sm_count, cudaStream_t stream) {
+    DctParams p;
+    p.log_mel = log_mel;
+    p.in_row_stride = in_row_stride;
+    p.out = out;
+    p.blob = blob;
+    p.n_frames = n_frames;
+    p.n_clips = static_cast<int>(n_clips);
+    p.n_mels = n_mels;
+    p.kp = mfcc_tc_padded_mels(n_mels);
+    p.n_mfcc = n_mfcc;
+    p.row0 = row0;
+    p.N = mfcc_tc_padded_coeffs(n_mfcc);
+    p.tiles_per_clip = static_cast<int>((n_frames + kTile - 1) / kTile);
+    const long long total = n_clips * p.tiles_per_clip;
+    if (total <= 0) return cudaSuccess;
+    const size_t b_floats = static_cast<size_t>(p.kp / 8) * 2 * p.N * 8;
+    size_t smem = sizeof(float) * (b_floats + 64) + sizeof(uint64_t) * 6 + 16;
+    smem = std::max<size_t>(smem, 120 * 1024);          // one CTA per SM: it owns all 512 TMEM columns
+    cudaError_t e = cudaFuncSetAttribute(k_dct2_lifter_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    const long long grid = std::min<long long>(total, sm_count);
+    k_dct2_lifter_tc<<<static_cast<unsigned>(grid), kAllThreads, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace sgx

@@ -65,6 +65,18 @@ cudaError_t launch_mixed(const KParams &p, bool f64, cudaStream_t stream);
 cudaError_t launch_mfcc(bool f64, const void *log_mel, void *out, long long n_clips, int n_mels, long long n_frames,
                         int n_mfcc, int row0, const void *dct, const void *lifter, cudaStream_t stream);
 
+// the same as a tcgen05 GEMM (kernel_mfcc_tc.cu, f32): frames x n_mels times the DCT basis, 3xTF32, FP32 accumulation in tensor
+// memory, lifter / c0 drop fused. blob: per 8-mel K step an N x 8 hi tile and an N x 8 lo tile of the basis as K-major core
+// matrices (float (n / 8) * 64 + (k / 4) * 32 + (n % 8) * 4 + k % 4 inside a tile; N = n_mfcc rounded up to 16, mels zero padded
+// to a multiple of 8), then the n_mfcc lifter weights.
+bool mfcc_tc_supported(int n_mels, int n_mfcc);
+int mfcc_tc_padded_mels(int n_mels);
+int mfcc_tc_padded_coeffs(int n_mfcc);
+size_t mfcc_tc_blob_floats(int n_mels, int n_mfcc);
+// log_mel rows are in_row_stride floats apart (>= n_frames), clips n_mels rows apart.
+cudaError_t launch_mfcc_tc(const float *log_mel, long long in_row_stride, float *out, long long n_clips, int n_mels, long long n_frames, int n_mfcc,
+                           int row0, const float *blob, int sm_count, cudaStream_t stream);
+
 // standalone chromagram_from_spectrogram (kernel_chroma.cu): spec [n_clips][n_bins][n_frames] -> out [n_clips][12][n_frames];
 // w_transposed is the chroma filterbank as T[n_bins][12], non-zero only for bins in [k0, k1)
 cudaError_t launch_chroma(bool f64, const void *spec, void *out, long long n_clips, int n_bins, long long n_frames,

@@ -89,6 +89,41 @@ template <typename T> void *upload_as(const std::vector<double> &src) {
     return d;
 }
 void *upload(const std::vector<double> &src, bool f64) { return f64 ? upload_as<double>(src) : upload_as<float>(src); }
+
+// B operand of dct2_lifter_tc (launch.hpp): basis[n_mfcc][n_mels] (f64) cast to f32 and split into a TF32-exact hi part and the
+// f32 remainder, per 8-mel K step as K-major core matrices; lifter weights behind
+std::vector<float> build_dct_tc_blob(size_t n_mels, size_t n_mfcc, const std::vector<double> &basis, const std::vector<double> &lift) {
+    const size_t kp = static_cast<size_t>(mfcc_tc_padded_mels(static_cast<int>(n_mels))), N = static_cast<size_t>(mfcc_tc_padded_coeffs(static_cast<int>(n_mfcc)));
+    std::vector<float> blob(mfcc_tc_blob_floats(static_cast<int>(n_mels), static_cast<int>(n_mfcc)), 0.0f);
+    const size_t half = N * 8;
+    for (size_t step = 0; step < kp / 8; ++step)
+        for (size_t n = 0; n < N; ++n)
+            for (size_t k = 0; k < 8; ++k) {
+                const size_t mel = 8 * step + k;
+                const float w = (n < n_mfcc && mel < n_mels) ? static_cast<float>(basis[n * n_mels + mel]) : 0.0f;
+                uint32_t bits;
+                std::memcpy(&bits, &w, 4);
+                bits &= 0xffffe000u;
+                float hi;
+                std::memcpy(&hi, &bits, 4);
+                const size_t idx = (n / 8) * 64 + (k / 4) * 32 + (n % 8) * 4 + (k % 4);
+                blob[step * 2 * half + idx] = hi;
+                blob[step * 2 * half + half + idx] = w - hi;
+            }
+    for (size_t c = 0; c < n_mfcc; ++c) blob[(kp / 8) * 2 * half + c] = static_cast<float>(lift[c]);
+    return blob;
+}
+float *upload_floats(const std::vector<float> &v) {
+    float *d = nullptr;
+    if (v.empty()) return nullptr;
+    ck(cudaMalloc(&d, v.size() * sizeof(float)), "cudaMalloc(table)");
+    ck(cudaMemcpy(d, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice), "cudaMemcpy(table)");
+    return d;
+}
+bool mfcc_tc_enabled() {
+    static const bool off = std::getenv("SGX_MFCC_TC") && std::atoi(std::getenv("SGX_MFCC_TC")) == 0;
+    return !off;
+}
 int *upload_int(const std::vector<int> &src) {
     if (src.empty()) return nullptr;
     int *d = nullptr;
@@ -164,6 +199,10 @@ struct sgx_plan {
     std::vector<double> lane_w;      // ... and its lane-major weights
     int *d_lane_rows = nullptr;
     void *d_frames = nullptr;               // istft: windowed time frames of a chunk of clips
+    bool mfcc_split = false;                // n400 f32 mfcc(): log-mel by r2c_fused_n400_tm, DCT-II by dct2_lifter_tc (tcgen05)
+    float *d_dct_tc = nullptr;              // ... basis blob of dct2_lifter_tc
+    void *d_logmel = nullptr;               // ... log-mel scratch of a chunk of clips
+    size_t logmel_cap = 0;
     size_t frames_cap = 0;
     void *d_pair[2] = {nullptr, nullptr};   // binaural: complex STFTs of the two channels of a chunk of pairs
     // Device-pointer istft / binaural calls return asynchronously but stage through the plan-owned scratch above: the last
@@ -200,6 +239,8 @@ struct sgx_plan {
         if (d_dense_t) cudaFree(d_dense_t);
         for (void *q : d_pair) if (q) cudaFree(q);
         if (d_frames) cudaFree(d_frames);
+        if (d_dct_tc) cudaFree(d_dct_tc);
+        if (d_logmel) cudaFree(d_logmel);
         if (scratch_done) cudaEventDestroy(scratch_done);
         for (auto &s : slot) {
             if (s.d_in) cudaFree(s.d_in);
@@ -431,6 +472,7 @@ void select_family(sgx_plan &pl) {
     // pad to 16 bytes; int4 {c0, cnt, padded weight offset, row}[4 * n_quads] in warp order.
     bool contiguous = csr;
     int padded = 0;
+    pl.mfcc_split = false;
     {
         const char *e = std::getenv("SGX_N400_TM_WARPS");      // experiments only: 4 (default), 5 or 6 warps per group
         const int w = e ? std::atoi(e) : 4;
@@ -578,6 +620,9 @@ void select_family(sgx_plan &pl) {
     pl.fast400_tc = pl.tc_steps > 0;
     pl.fast400_tm = pl.fast400 && csr && contiguous && d.output == SGX_OUT_SPECTROGRAM && !pl.wofs_tm.empty() &&
                     fast400_tm_fits(pl.sparse_quads, pl.tm_weights);
+    // fused mfcc() on the n400 family: the log-mel spectrogram by the TMEM-exchange kernel, the DCT-II on the tensor cores
+    pl.mfcc_split = pl.fast400 && csr && contiguous && d.output == SGX_OUT_MFCC && !pl.wofs_tm.empty() && mfcc_tc_enabled() &&
+                    fast400_tm_fits(pl.sparse_quads, pl.tm_weights) && mfcc_tc_supported(static_cast<int>(pl.tab.n_bins), static_cast<int>(d.n_mfcc));
     pl.kernel_name = pl.fast400 ? "r2c_fused_n400" : pl.pow2 ? "r2c_fused_pow2" : pl.mixed ? "r2c_fused_mixed" : "r2c_fused_generic";
     // folded DCT basis for the fused MFCC epilogue: B[c][n-1-i] = (-1)^c B[c][i] -> half basis, tasks of 4 coefficients of
     // one parity: [task][i < n/2][4], even-coefficient tasks first
@@ -653,6 +698,7 @@ void ensure_device(sgx_plan &pl) {
     pl.d_dct = upload(pl.tab.dct, pl.f64);
     pl.d_lifter = upload(pl.tab.lifter, pl.f64);
     pl.d_dct_folded = upload(pl.dct_folded, pl.f64);
+    if (pl.mfcc_split) pl.d_dct_tc = upload_floats(build_dct_tc_blob(pl.tab.n_bins, pl.desc.n_mfcc, pl.tab.dct, pl.tab.lifter));
     cudaDeviceProp prop;
     ck(cudaGetDeviceProperties(&prop, dev), "cudaGetDeviceProperties");
     pl.sm_count = prop.multiProcessorCount;
@@ -724,6 +770,41 @@ void run_device(sgx_plan &pl, const void *d_samples, size_t n_clips, size_t n_sa
     p.out_frame_origin = frame_begin;
     const int tile_frames = pl.force_generic ? p.FT : pl.fast400 ? 32 : pl.pow2 ? pl.pow2_ft : pl.mixed ? mixed_tile_frames() : p.FT;
     p.tiles_per_clip = static_cast<int>((frames_todo + tile_frames - 1) / tile_frames);
+    // mfcc() on the n400 family, dense outputs: log-mel spectrogram of a chunk of clips into plan scratch by r2c_fused_n400_tm,
+    // then the DCT-II + lifter as a tcgen05 GEMM (dct2_lifter_tc). Two launches; only the log-mel tile (a sixth of the input's
+    // bytes) makes a round trip through HBM / L2.
+    const long long mfcc_rows = static_cast<long long>(pl.desc.n_mfcc) - p.mfcc_row0;
+    if (pl.mfcc_split && !pl.force_generic && pl.tm_mode != 0 && out_row_stride == frames_todo && out_clip_stride == mfcc_rows * frames_todo) {
+        const size_t nb = pl.tab.n_bins;
+        const size_t per_clip = nb * static_cast<size_t>(frames_todo) * sizeof(float);
+        size_t chunk = std::max<size_t>(1, (size_t(1) << 30) / per_clip);
+        chunk = std::min(chunk, n_clips);
+        if (pl.logmel_cap < chunk * per_clip) {
+            if (pl.d_logmel) { ck(cudaDeviceSynchronize(), "sync"); cudaFree(pl.d_logmel); pl.d_logmel = nullptr; pl.logmel_cap = 0; }
+            ck(cudaMalloc(&pl.d_logmel, chunk * per_clip), "cudaMalloc(log-mel scratch)");
+            pl.logmel_cap = chunk * per_clip;
+        }
+        pl.scratch_acquire(stream);
+        for (size_t c0 = 0; c0 < n_clips; c0 += chunk) {
+            const size_t nc = std::min(chunk, n_clips - c0);
+            KParams q = p;
+            q.n_clips = static_cast<int>(nc);
+            q.samples = static_cast<const char *>(d_samples) + c0 * clip_stride * pl.esize;
+            q.output = SGX_OUT_SPECTROGRAM;
+            q.out = pl.d_logmel;
+            q.out_row_stride = frames_todo;
+            q.out_clip_stride = static_cast<long long>(nb) * frames_todo;
+            q.vec_ok = (reinterpret_cast<uintptr_t>(q.samples) % 8 == 0 && clip_stride % 2 == 0) ? 1 : 0;
+            q.sched = pl.d_wofs_tm;
+            ck(launch_fast400_tm(q, pl.window_f32.data(), pl.sparse_quads, pl.tm_weights, pl.tm_warps, pl.sm_count, stream), "kernel launch (r2c_fused_n400_tm)");
+            ck(launch_mfcc_tc(static_cast<const float *>(pl.d_logmel), frames_todo, static_cast<float *>(d_out) + c0 * static_cast<size_t>(out_clip_stride),
+                              static_cast<long long>(nc), static_cast<int>(nb), frames_todo, static_cast<int>(pl.desc.n_mfcc), p.mfcc_row0,
+                              pl.d_dct_tc, pl.sm_count, stream), "kernel launch (dct2_lifter_tc)");
+            pl.last_launches += 2;
+        }
+        pl.scratch_release(stream);
+        return;
+    }
     // the grid is limited to 2^31-1 CTAs: split very large batches
     const long long max_clips = std::max<long long>(1, 2000000000LL / std::max(1, p.tiles_per_clip));
     for (size_t c0 = 0; c0 < n_clips; c0 += static_cast<size_t>(max_clips)) {
@@ -893,6 +974,7 @@ sgx_status sgx_plan_filterbank(const sgx_plan *plan, double *dense_out, size_t *
 const char *sgx_plan_kernel_name(const sgx_plan *plan) {
     if (!plan) return "";
     if (plan->force_generic) return "r2c_fused_generic";
+    if (plan->mfcc_split && plan->tm_mode != 0) return "r2c_fused_n400_tm+dct2_lifter_tc";
     if (use_tm(*plan)) return "r2c_fused_n400_tm";
     if (use_tc(*plan)) return "r2c_fused_n400_tc";
     return plan->kernel_name.c_str();
@@ -1034,10 +1116,22 @@ sgx_status sgx_mfcc_from_log_mel(sgx_dtype dtype, const void *log_mel, size_t n_
         void *d_dct = upload(basis, f64), *d_lift = upload(lift, f64);
         const PtrKind ki = ptr_kind(log_mel), ko = ptr_kind(out);
         cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-        auto cleanup = [&] { cudaFree(d_dct); cudaFree(d_lift); };
+        float *d_blob = nullptr;
+        int sm_count = 148;
+        auto cleanup = [&] { cudaFree(d_dct); cudaFree(d_lift); if (d_blob) cudaFree(d_blob); };
         try {
             if (ki != ko) invalid("log_mel and out must both be host pointers or both be device pointers");
+            // f32, n_mels <= 128, n_mfcc <= 64: the tensor-core form (dct2_lifter_tc); otherwise the CUDA-core kernel
+            const bool tc_ok = !f64 && mfcc_tc_enabled() && mfcc_tc_supported(static_cast<int>(n_mels), static_cast<int>(n_mfcc));
+            if (tc_ok) {
+                d_blob = upload_floats(build_dct_tc_blob(n_mels, n_mfcc, basis, lift));
+                ck(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute");
+            }
             if (ki == PtrKind::Device) {
+                if (tc_ok)
+                    ck(launch_mfcc_tc(static_cast<const float *>(log_mel), static_cast<long long>(n_frames), static_cast<float *>(out), static_cast<long long>(n_clips), static_cast<int>(n_mels),
+                                      static_cast<long long>(n_frames), static_cast<int>(n_mfcc), row0, d_blob, sm_count, st), "kernel launch (dct2_lifter_tc)");
+                else
                 ck(launch_mfcc(f64, log_mel, out, static_cast<long long>(n_clips), static_cast<int>(n_mels),
                                static_cast<long long>(n_frames), static_cast<int>(n_mfcc), row0, d_dct, d_lift, st), "kernel launch (dct2_lifter)");
                 ck(cudaStreamSynchronize(st), "cudaStreamSynchronize");   // tables are freed below
@@ -1047,8 +1141,11 @@ sgx_status sgx_mfcc_from_log_mel(sgx_dtype dtype, const void *log_mel, size_t n_
                 ck(cudaMalloc(&d_in, ib), "cudaMalloc");
                 if (cudaMalloc(&d_out, ob) != cudaSuccess) { cudaFree(d_in); backend("cudaMalloc failed"); }
                 cudaError_t e = cudaMemcpyAsync(d_in, log_mel, ib, cudaMemcpyHostToDevice, st);
-                if (e == cudaSuccess) e = launch_mfcc(f64, d_in, d_out, static_cast<long long>(n_clips), static_cast<int>(n_mels),
-                                                      static_cast<long long>(n_frames), static_cast<int>(n_mfcc), row0, d_dct, d_lift, st);
+                if (e == cudaSuccess)
+                    e = tc_ok ? launch_mfcc_tc(static_cast<const float *>(d_in), static_cast<long long>(n_frames), static_cast<float *>(d_out), static_cast<long long>(n_clips), static_cast<int>(n_mels),
+                                               static_cast<long long>(n_frames), static_cast<int>(n_mfcc), row0, d_blob, sm_count, st)
+                              : launch_mfcc(f64, d_in, d_out, static_cast<long long>(n_clips), static_cast<int>(n_mels),
+                                            static_cast<long long>(n_frames), static_cast<int>(n_mfcc), row0, d_dct, d_lift, st);
                 if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, ob, cudaMemcpyDeviceToHost, st);
                 if (e == cudaSuccess) e = cudaStreamSynchronize(st);
                 cudaFree(d_in); cudaFree(d_out);

@@ -164,8 +164,11 @@ def test_fused_mfcc_on_magnitude_mel_matches_the_generic_family():
     outs = {}
     for amp in ("magnitude", "power"):
         n = _NativePlan(P(), "float32", "mel", sg.MelParams(128, 0.0, 8000.0), amp, None, _OUT_MFCC, sg.MfccParams(13, True, 0))
-        assert n.kernel_name() == "r2c_fused_n400"
+        assert n.kernel_name() == "r2c_fused_n400_tm+dct2_lifter_tc"
         a = n.compute_one(t).cpu().numpy()
+        n.set_tmem_exchange(False)
+        assert n.kernel_name() == "r2c_fused_n400"
+        assert rel_l2(n.compute_one(t).cpu().numpy(), a) <= TOL_F32
         n.force_generic(True)
         b = n.compute_one(t).cpu().numpy()
         assert rel_l2(a, b) <= TOL_F32

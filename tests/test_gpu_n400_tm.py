@@ -171,7 +171,9 @@ def test_tm_selection_rule():
     assert not pl.mel_plan(P(), sg.MelParams(128, 0.0, 8000.0), None, "power", "float64").kernel_name().startswith("r2c_fused_n400")
     from spectrograms_b200.plan import _NativePlan, _OUT_MFCC
     mf = _NativePlan(P(), "float32", "mel", sg.MelParams(128, 0.0, 8000.0), "db", sg.LogParams(-80.0), _OUT_MFCC, sg.MfccParams(13, True, 0))
-    assert mf.kernel_name() == "r2c_fused_n400"                                                        # fused DCT stays on the shared-memory kernel
+    assert mf.kernel_name() == "r2c_fused_n400_tm+dct2_lifter_tc"                                      # log-mel by this kernel, DCT-II on the tensor cores
+    mf.set_tmem_exchange(False)
+    assert mf.kernel_name() == "r2c_fused_n400"                                                        # opt-out: the fused shared-memory kernel
     p = pl.mel_plan(P(), sg.MelParams(128, 0.0, 8000.0), None, "power", "float32")
     p.set_tensor_cores(True)
     assert p.kernel_name() == "r2c_fused_n400_tc"                                                      # an explicit request wins
