@@ -15,9 +15,10 @@
 //            operand: two A buffers (one per register set), so half h+1 is converted while the MMAs of half h run
 //   mma      a ninth warp's lane 0 waits for a converted half (mbarrier) and issues tcgen05.mma.cta_group::1.kind::tf32, A from TMEM, B = the DCT basis from shared memory
 //            (K-major SWIZZLE_NONE core matrices, hi and lo tiles per 8-mel K step, built on the host), M = 128,
-//            N = n_mfcc rounded up to 16, three MMAs per K step; completion through tcgen05.commit -> mbarrier
-//   out      tcgen05.ld of the frame's coefficients (two D buffers: tile t-1 is drained while tile t multiplies) ->
-//            lifter -> one 128-byte run of frames per coefficient row
+//            N = n_mfcc rounded up to 16, two MMAs per K step: A_hi [B_hi | B_lo] (N doubled) and A_lo B_hi; completion through tcgen05.commit -> mbarrier
+//   out      four more warps (one per sub-partition) wait for a tile's MMAs, tcgen05.ld the frame's coefficients (two D buffers:
+//            tile t-1 is drained while tile t multiplies), add the two column halves, apply the lifter and store one 128-byte
+//            run of frames per coefficient row; the conversion warps never wait for an MMA to complete
 #include "launch.hpp"
 #include "tcgen05.cuh"
 
@@ -26,11 +27,11 @@ namespace {
 
 constexpr int kTile = 128;                 // frames per tile = MMA rows
 constexpr int kThreads = 256;              // 8 conversion warps: two per SM sub-partition
-constexpr int kAllThreads = kThreads + 32; // + one warp whose lane 0 issues the MMAs
+constexpr int kAllThreads = kThreads + 32 + 128; // + one warp that issues the MMAs + four warps (one per sub-partition) that drain D
 constexpr int kHalf = 64;                  // mels per A buffer
 constexpr int kPart = 32;                  // mels per thread and half
 constexpr uint32_t kColA = 0;              // A buffers: [buf][hi 64 | lo 64]
-constexpr uint32_t kColD = 256;            // D buffers: [buf][64]
+constexpr uint32_t kColD = 256;            // D buffers: [buf][128]: columns [0, N) += A_hi B_hi + A_lo B_hi, columns [N, 2N) += A_hi B_lo
 constexpr uint32_t kTmemCols = 512;
 
 struct DctParams {
@@ -47,8 +48,8 @@ __global__ void __launch_bounds__(kAllThreads, 1) k_dct2_lifter_tc(const __grid_
     const int b_floats = n_steps * 2 * p.N * 8;
     float *sB = reinterpret_cast<float *>(smem_raw);                                  // basis tiles
     float *sLift = sB + b_floats;                                                     // [64]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sLift + 64);                        // abar[2] (A buffer free), dbar[2] (D complete), rbar[2] (A buffer ready)
-    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 6);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sLift + 64);                        // abar[2] (A buffer free), dbar[2] (D complete), rbar[2] (A buffer ready), fbar[2] (D buffer drained)
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 8);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q = warp & 3, hp = warp >> 2;                    // SM sub-partition / TMEM lane quarter; which 32 mels of a half
     const int frame_in_tile = 32 * q + lane;
@@ -59,16 +60,21 @@ __global__ void __launch_bounds__(kAllThreads, 1) k_dct2_lifter_tc(const __grid_
     if (tid == 32) {
         for (int i = 0; i < 4; ++i) tc::mbar_init(&bars[i], 1);
         for (int i = 4; i < 6; ++i) tc::mbar_init(&bars[i], kThreads / 32);      // one arrival per conversion warp
+        for (int i = 6; i < 8; ++i) tc::mbar_init(&bars[i], 4);                  // one arrival per drain warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     tc::fence_proxy_async();
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
-    const uint32_t tm = *tmem_ptr;
+    // The CTA allocates all 512 columns, so the allocation starts at lane 0, column 0. Using the constant (checked here) keeps
+    // every MMA operand provably warp-uniform: the compiler then issues UTCHMMA straight from uniform registers instead of a
+    // per-lane elect / broadcast loop around each instruction (~125 cycles per MMA on the issuing thread).
+    if (*tmem_ptr != 0u) __trap();
+    constexpr uint32_t tm = 0u;
     const uint32_t lane_base = tm + (static_cast<uint32_t>(32 * q) << 16);
     const uint32_t b_base = tc::smem_addr(sB);
-    const uint32_t idesc = tc::idesc_tf32(128, p.N);
+    const uint32_t idesc = tc::idesc_tf32(128, p.N), idesc2 = tc::idesc_tf32(128, 2 * p.N);
     const int n_halves = (p.kp + kHalf - 1) / kHalf;
 
     const long long total = static_cast<long long>(p.n_clips) * p.tiles_per_clip;
@@ -88,8 +94,7 @@ __global__ void __launch_bounds__(kAllThreads, 1) k_dct2_lifter_tc(const __grid_
 #pragma unroll
         for (int i = 0; i < kPart; ++i) v[i] = (live && m0 + i < p.n_mels) ? __ldg(src + static_cast<long long>(i) * p.in_row_stride) : 0.f;
     };
-    // coefficients of tile `it` of this CTA: D buffer it & 1 -> lifter -> rows of the output; the two warps of a sub-partition
-    // split the 16-column chunks
+    // coefficients of tile `it` of this CTA: D buffer it & 1 -> lifter -> rows of the output (drain warps)
     auto drain = [&](long long it, uint32_t parity) {
         const int pb = static_cast<int>(it & 1);
         tc::mbar_wait(&bars[2 + pb], parity);
@@ -98,19 +103,23 @@ __global__ void __launch_bounds__(kAllThreads, 1) k_dct2_lifter_tc(const __grid_
         const long long clip = t / p.tiles_per_clip, tile = t - clip * p.tiles_per_clip;
         const long long f = tile * kTile + frame_in_tile;
         float *o = p.out + clip * (p.n_mfcc - p.row0) * p.n_frames + f;
-        for (int c0 = 16 * hp; c0 < p.N; c0 += 32) {
+        for (int c0 = 0; c0 < p.N; c0 += 16) {
             uint32_t v[16];
-            tc::ld16(lane_base + kColD + 64u * pb + c0, v);
+            uint32_t u[16];
+            tc::ld16(lane_base + kColD + 128u * pb + c0, v);
+            tc::ld16(lane_base + kColD + 128u * pb + p.N + c0, u);
             tc::wait_ld();
             if (f < p.n_frames) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const int c = c0 + i;
-                    if (c >= p.row0 && c < p.n_mfcc) o[static_cast<long long>(c - p.row0) * p.n_frames] = __uint_as_float(v[i]) * sLift[c];
+                    if (c >= p.row0 && c < p.n_mfcc) o[static_cast<long long>(c - p.row0) * p.n_frames] = (__uint_as_float(v[i]) + __uint_as_float(u[i])) * sLift[c];
                 }
             }
         }
         tc::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&bars[6 + pb]);         // this sub-partition's quarter of the D buffer is free again
     };
     uint32_t a_uses[2] = {0, 0};          // MMA groups committed on each A buffer so far (mbarrier parity)
     uint32_t d_done = 0;                  // tiles whose MMAs have been committed
@@ -146,38 +155,63 @@ __global__ void __launch_bounds__(kAllThreads, 1) k_dct2_lifter_tc(const __grid_
         if (lane == 0) tc::mbar_arrive(&bars[4 + b]);          // this warp's 32 rows x 32 mels of the half are in TMEM
         a_uses[b] += 1;
         if (h == n_halves - 1) d_done += 1;
-        // drain the previous tile's coefficients while this tile multiplies (tile it - 1 was the ((it - 1) / 2)-th user of its buffer)
-        if (h == 0 && it > 0) drain(it - 1, static_cast<uint32_t>(((it - 1) >> 1) & 1));
     };
 
-    if (warp == kThreads / 32) {
-        // ---- the MMA warp: waits for a converted half, multiplies it, signals the A buffer free (and the tile complete)
-        if (lane == 0) {
+    if (__shfl_sync(0xffffffffu, warp, 0) == kThreads / 32) {
+        // ---- the MMA warp: waits for a converted half, multiplies it, signals the A buffer free (and the tile complete). All 32
+        //      lanes run the loop with identical (warp-uniform) operands and one elected lane issues: the operands then live
+        //      in uniform registers and every tcgen05.mma is a single UTCHMMA (issued from divergent code, each one is wrapped
+        //      in an elect / broadcast loop that costs the issuing thread ~125 cycles -- tools/ubench/mma_rate_probe.cu)
+        {
             const uint64_t bdesc0 = tc::smem_desc_kmajor(b_base, 128, 256);
             const uint64_t step_units = static_cast<uint64_t>(4 * p.N), lo_units = static_cast<uint64_t>(2 * p.N);
-            auto mma_first = [&](uint32_t d, uint32_t a, uint64_t bd, uint32_t id, bool acc) { tc::mma_tf32_ts(d, a, bd, id, acc ? 1u : 0u); };
+            auto mma = [&](uint32_t d, uint32_t a, uint64_t bd, uint32_t id, uint32_t acc) {
+                asm volatile(
+                    "{\n"
+                    ".reg .pred p, q;\n"
+                    "elect.sync _|q, 0xffffffff;\n"
+                    "setp.ne.b32 p, %4, 0;\n"
+                    "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+                    "}\n" ::"r"(d),
+                    "r"(a), "l"(bd), "r"(id), "r"(acc)
+                    : "memory");
+            };
+            auto commit = [&](uint64_t *bar) {
+                asm volatile(
+                    "{\n"
+                    ".reg .pred q;\n"
+                    "elect.sync _|q, 0xffffffff;\n"
+                    "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+                    "}\n" ::"r"(tc::smem_addr(bar))
+                    : "memory");
+            };
             for (long long g = 0; g < n_jobs; ++g) {
                 const long long it = g / n_halves;
                 const int h = static_cast<int>(g - it * n_halves), b = static_cast<int>(g & 1);
                 tc::mbar_wait(&bars[4 + b], static_cast<uint32_t>((g >> 1) & 1));
+                if (h == 0 && it >= 2) tc::mbar_wait(&bars[6 + (it & 1)], static_cast<uint32_t>(((it - 2) >> 1) & 1));   // tile it - 2 has left this D buffer
                 tc::fence_after_sync();
                 const int k0 = h * kHalf, kn = (p.kp - k0) < kHalf ? (p.kp - k0) : kHalf;      // mels of this half (multiple of 8)
-                const uint32_t a0 = tm + kColA + 128u * b, dcol = tm + kColD + 64u * static_cast<uint32_t>(it & 1);
+                const uint32_t a0 = tm + kColA + 128u * b, dcol = tm + kColD + 128u * static_cast<uint32_t>(it & 1);
                 // descriptors advance by constants: a K step's hi tile is 4 N, its lo tile 2 N sixteen-byte units further on
                 uint64_t bhi = bdesc0 + static_cast<uint64_t>(k0 / 8) * step_units;
-                mma_first(dcol, a0, bhi, idesc, h != 0);
-                tc::mma_tf32_ts(dcol, a0, bhi + lo_units, idesc, 1u);
-                tc::mma_tf32_ts(dcol, a0 + 64, bhi, idesc, 1u);
+                // an MMA costs the tensor core ~125 cycles whatever N <= 128 (the A operand's 128 rows x 32 bytes arrive at 32 B/clk), so
+                // A_hi meets [B_hi | B_lo] -- the lo tile directly follows the hi tile, one 2N-row operand -- in ONE instruction;
+                // A_lo B_hi goes on top of the first N columns; the two column halves are added on the way out
+                mma(dcol, a0, bhi, idesc2, h != 0 ? 1u : 0u);
+                mma(dcol, a0 + 64, bhi, idesc, 1u);
                 for (int k = 8; k < kn; k += 8) {
                     bhi += step_units;
-                    tc::mma_tf32_ts(dcol, a0 + k, bhi, idesc, 1u);
-                    tc::mma_tf32_ts(dcol, a0 + k, bhi + lo_units, idesc, 1u);
-                    tc::mma_tf32_ts(dcol, a0 + 64 + k, bhi, idesc, 1u);
+                    mma(dcol, a0 + k, bhi, idesc2, 1u);
+                    mma(dcol, a0 + 64 + k, bhi, idesc, 1u);
                 }
-                tc::commit(&bars[b]);
-                if (h == n_halves - 1) tc::commit(&bars[2 + (it & 1)]);
+                commit(&bars[b]);
+                if (h == n_halves - 1) commit(&bars[2 + (it & 1)]);
             }
         }
+    } else if (warp > kThreads / 32) {
+        // ---- drain warps (one per sub-partition: warp_id % 4 selects the TMEM lanes): tile after tile as the MMAs complete
+        for (long long it = 0; it < my_tiles; ++it) drain(it, static_cast<uint32_t>((it >> 1) & 1));
     } else {
         float va[kPart], vb[kPart];
         if (n_jobs > 0) load_job(va, 0);
@@ -185,7 +219,6 @@ __global__ void __launch_bounds__(kAllThreads, 1) k_dct2_lifter_tc(const __grid_
             step(va, vb, g);
             if (g + 1 < n_jobs) step(vb, va, g + 1);
         }
-        if (my_tiles > 0) drain(my_tiles - 1, static_cast<uint32_t>(((my_tiles - 1) >> 1) & 1));
     }
     (void)d_done;
     tc::fence_before_sync();
@@ -222,7 +255,7 @@ cudaError_t launch_mfcc_tc(const float *log_mel, long long in_row_stride, float 
     const long long total = n_clips * p.tiles_per_clip;
     if (total <= 0) return cudaSuccess;
     const size_t b_floats = static_cast<size_t>(p.kp / 8) * 2 * p.N * 8;
-    size_t smem = sizeof(float) * (b_floats + 64) + sizeof(uint64_t) * 6 + 16;
+    size_t smem = sizeof(float) * (b_floats + 64) + sizeof(uint64_t) * 8 + 16;
     smem = std::max<size_t>(smem, 120 * 1024);          // one CTA per SM: it owns all 512 TMEM columns
     cudaError_t e = cudaFuncSetAttribute(k_dct2_lifter_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;

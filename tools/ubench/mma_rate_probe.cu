@@ -8,7 +8,7 @@
 using namespace sgx;
 
 template <int N>
-__global__ void __launch_bounds__(128, 1) probe(long long *out, int n_mma, int d_stride, int a_stride, int a_tmem) {
+__global__ void __launch_bounds__(128, 1) probe(long long *out, int n_mma, int d_stride, int a_stride, int a_tmem, int swz) {
     extern __shared__ __align__(1024) float sb[];          // zeros
     __shared__ uint32_t s_tmem;
     __shared__ __align__(8) uint64_t bar;
@@ -34,7 +34,10 @@ __global__ void __launch_bounds__(128, 1) probe(long long *out, int n_mma, int d
         for (int rep = 0; rep < 3; ++rep) {
             const long long t0 = clock64();
             for (int i = 0; i < n_mma; ++i) {
-                const uint64_t bd = tc::smem_desc_kmajor(b0 + (i & 7) * N * 32, 128, 256);
+                // swz: SWIZZLE_128B K-major tiles (rows of 128 bytes = 4 K steps, 8-row groups 1024 bytes apart; layout type 2 in
+                // bits 61..63) instead of the SWIZZLE_NONE core matrices -- timing only, the operands are zeros
+                const uint64_t bd = swz ? (tc::smem_desc_kmajor(b0 + (i & 3) * 32, 16, 1024) | (2ull << 61))
+                                        : tc::smem_desc_kmajor(b0 + (i & 7) * N * 32, 128, 256);
                 const uint32_t d = tm + 256 + ((i * d_stride) & 255) % (256 - N + 1);
                 if (a_tmem) tc::mma_tf32_ts(d, tm + ((i * a_stride) & 127), bd, idesc, 1u);
                 else asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d), "l"(adesc), "l"(bd), "r"(idesc), "r"(1u) : "memory");
@@ -53,11 +56,11 @@ __global__ void __launch_bounds__(128, 1) probe(long long *out, int n_mma, int d
 }
 
 template <int N>
-void run(int n_mma, int d_stride, int a_stride, int a_tmem, const char *what) {
+void run(int n_mma, int d_stride, int a_stride, int a_tmem, const char *what, int swz = 0) {
     long long *d, h[6];
     cudaMalloc(&d, 48);
     cudaFuncSetAttribute(probe<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    probe<N><<<1, 128, 100 * 1024>>>(d, n_mma, d_stride, a_stride, a_tmem);
+    probe<N><<<1, 128, 100 * 1024>>>(d, n_mma, d_stride, a_stride, a_tmem, swz);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); exit(1); }
     cudaMemcpy(h, d, 48, cudaMemcpyDeviceToHost);
@@ -78,5 +81,10 @@ int main() {
     run<16>(100, 0, 8, 0, "same D");
     run<64>(100, 0, 8, 0, "same D");
     run<128>(100, 0, 8, 0, "same D");
+    run<16>(100, 0, 8, 1, "same D, B SWIZZLE_128B", 1);
+    run<48>(100, 0, 8, 1, "same D, B SWIZZLE_128B", 1);
+    run<64>(100, 64, 8, 1, "rotating D, B SWIZZLE_128B", 1);
+    run<128>(100, 0, 8, 1, "same D, B SWIZZLE_128B", 1);
+    run<256>(100, 0, 8, 1, "same D, B SWIZZLE_128B", 1);
     return 0;
 }
