@@ -38,20 +38,22 @@ __device__ __forceinline__ void cp_async_commit_wait_all() {
 }
 
 // stage one tile's samples [s0, s0 + 5360) of a clip into a padded signal buffer
-// float2 units j = first, first + step, ... < last of the tile are handled by the calling thread
+// float2 units j = first, first + step, ... < last of the tile are handled by the calling thread. PADW = pad words per hop
+// block (2: the 162-word layout of fft400_core.cuh; 4: the 164-word layout of the bulk-staged r2c_fused_n400_tm)
+template <int PADW = 2>
 __device__ __forceinline__ void load_tile(float *sig, const float *x, long long s0, long long n, bool vec_ok, int first, int step,
                                           int last) {
     if (vec_ok && s0 >= 0 && s0 + kTileSamples <= n) {
         // interior tile (all but the first / last tile of a clip): no bounds logic at all
         const float *src = x + s0;
 #pragma unroll 4
-        for (int j = first; j < last; j += step) cp_async8(sig + 2 * j + 2 * (j / (kHop / 2)), src + 2 * j, 8);
+        for (int j = first; j < last; j += step) cp_async8(sig + 2 * j + PADW * (j / (kHop / 2)), src + 2 * j, 8);
     } else if (vec_ok) {
         for (int j = first; j < last; j += step) {
             const long long s = s0 + 2 * j;
             const long long avail = n - s;                // samples available from s on
             const int bytes = (s < 0 || avail <= 0) ? 0 : (avail >= 2 ? 8 : 4);
-            cp_async8(sig + 2 * j + 2 * (j / (kHop / 2)), bytes ? x + s : x, bytes);
+            cp_async8(sig + 2 * j + PADW * (j / (kHop / 2)), bytes ? x + s : x, bytes);
         }
     } else {
         for (int j = first; j < last; j += step) {
@@ -59,7 +61,7 @@ __device__ __forceinline__ void load_tile(float *sig, const float *x, long long 
             float2 v;
             v.x = (s >= 0 && s < n) ? __ldg(x + s) : 0.f;
             v.y = (s + 1 >= 0 && s + 1 < n) ? __ldg(x + s + 1) : 0.f;
-            *reinterpret_cast<float2 *>(sig + 2 * j + 2 * (j / (kHop / 2))) = v;
+            *reinterpret_cast<float2 *>(sig + 2 * j + PADW * (j / (kHop / 2))) = v;
         }
     }
 }

@@ -22,6 +22,8 @@
 // Arithmetic is the arithmetic of kernel_fast400.cu (same task functions, same epilogue); only where Y travels differs.
 // Measured steps of this design (dedicated filterbank warps behind full / free barriers lost: one or two such warps per
 // group are latency bound) are in profiles/r2_n400_tm_experiments.md.
+#include <cstdlib>
+
 #include "fast400_common.cuh"
 #include "launch.hpp"
 #include "tcgen05.cuh"
@@ -36,48 +38,48 @@ constexpr int kMaxGroupWarps = 8;
 constexpr uint32_t kTmemCols = 512;                         // Y needs 400 columns; allocations are powers of two
 constexpr int kPadRows = 8;                                 // zero rows behind the power tile (padded quad rows read them)
 constexpr int kPWordsTm = (kBins + kPadRows) * kFT;
+// Bulk-staged signal tile (SIG = 1): hop block b of the tile lives at word 164 b (4 pad words = 16 bytes per hop), so every
+// block is a legal cp.async.bulk destination and lanes = frames read 16-byte sample quads conflict free (164 / 4 odd).
+constexpr int kSigStrideB = 164;
+constexpr int kSigWordsTm = kSigBlocks * kSigStrideB;      // 5576 >= kSigWords: both layouts fit
+constexpr uint32_t kTileBytes = kTileSamples * 4u;
 
 struct TmSmem {
-    float *sig;        // [4][kSigWords]   one signal tile per group
+    float *sig;        // [4][kSigWordsTm] one signal tile per group
     float *ptile;      // [4][kPWordsTm]   one power tile per group (+ zero rows)
     float *win;        // [400]
     int4 *quads;       // [4 * n_quads]    {byte offset of P[c0], padded cnt, weights address, row}
     int *qrange;       // [group warps + 1] quad range of every warp of a group
     float *w;          // padded weights
+    uint64_t *bars;    // [4] one mbarrier per group: bulk-copy completion of the group's next signal tile
     uint32_t *tmem_ptr;
 };
 
 __host__ __device__ inline size_t tm_smem_bytes(int n_quads, int padded_weights) {
-    return sizeof(float) * (kGroups * (kSigWords + kPWordsTm) + kN) + sizeof(int4) * 4 * static_cast<size_t>(n_quads) +
-           sizeof(int) * 12 + sizeof(float) * static_cast<size_t>(padded_weights + 8) + 16;
+    return sizeof(float) * (kGroups * (kSigWordsTm + kPWordsTm) + kN) + sizeof(int4) * 4 * static_cast<size_t>(n_quads) +
+           sizeof(int) * 12 + sizeof(float) * static_cast<size_t>(padded_weights + 8) + 8 + sizeof(uint64_t) * kGroups + 16;
 }
 
 __device__ __forceinline__ TmSmem carve(unsigned char *base, int n_quads, int padded_weights) {
     TmSmem s;
     size_t o = 0;
-    s.sig = reinterpret_cast<float *>(base + o);        o += sizeof(float) * kGroups * kSigWords;
+    s.sig = reinterpret_cast<float *>(base + o);        o += sizeof(float) * kGroups * kSigWordsTm;
     s.ptile = reinterpret_cast<float *>(base + o);      o += sizeof(float) * kGroups * kPWordsTm;
     s.quads = reinterpret_cast<int4 *>(base + o);       o += sizeof(int4) * 4 * static_cast<size_t>(n_quads);
     s.win = reinterpret_cast<float *>(base + o);        o += sizeof(float) * kN;
     s.qrange = reinterpret_cast<int *>(base + o);       o += sizeof(int) * 12;
     s.w = reinterpret_cast<float *>(base + o);          o += sizeof(float) * static_cast<size_t>(padded_weights + 8);
+    o = (o + 7) & ~static_cast<size_t>(7);
+    s.bars = reinterpret_cast<uint64_t *>(base + o);    o += sizeof(uint64_t) * kGroups;
     s.tmem_ptr = reinterpret_cast<uint32_t *>(base + o);
     return s;
 }
 
 // ---- pass 1, one task = (frame = lane, column pair t): f400::pass1_task with Y going to the thread's TMEM lane.
 // Y layout (columns): row 0 = (Y[0][n2], Y[10][n2]) pairs, rows 1..9 = Y[k1][n2] complex; column 40 * row + 2 * n2 (+1).
-__device__ __forceinline__ void pass1_tm(const float *__restrict__ sig, const float *__restrict__ win, int f, int t, uint32_t ybase) {
-    float2 v[20];
-    const float *s = sig + kSigBlockStride * f + 2 * t;
-#pragma unroll
-    for (int n1 = 0; n1 < 20; ++n1) {
-        const float2 x = *reinterpret_cast<const float2 *>(s + 20 * n1 + 2 * (n1 / 8));
-        const float2 w = *reinterpret_cast<const float2 *>(win + 20 * n1 + 2 * t);
-        v[n1] = cmul2(x, w);                          // sample * window[i] (src/spectrogram.rs:1319)
-    }
-    dft20(v);
-    const uint32_t y = ybase + 4 * t;
+// STRIDE: words between hop blocks of the signal tile (162, or 164 in the bulk-staged layout, where these 8-byte reads are
+// two-way bank conflicted -- only the two tasks that do not fill a quad use them there).
+__device__ __forceinline__ void pass1_store(const float2 (&v)[20], uint32_t y) {
     {
         const float2 z0 = v[reg_of_bin(0)], z10 = v[reg_of_bin(10)];
         tc::st4(y, __float_as_uint(z0.x), __float_as_uint(z10.x), __float_as_uint(z0.y), __float_as_uint(z10.y));
@@ -88,6 +90,65 @@ __device__ __forceinline__ void pass1_tm(const float *__restrict__ sig, const fl
         const float2 sa = cadd(A, make_float2(B.x, -B.y));                      // A + conj(B)
         const float2 sb = cadd(make_float2(A.y, -A.x), make_float2(B.y, B.x));  // (A - conj(B)) / i
         tc::st4(y + 40 * k1, __float_as_uint(sa.x), __float_as_uint(sa.y), __float_as_uint(sb.x), __float_as_uint(sb.y));
+    }
+}
+template <int STRIDE = kSigBlockStride>
+__device__ __forceinline__ void pass1_tm(const float *__restrict__ sig, const float *__restrict__ win, int f, int t, uint32_t ybase) {
+    float2 v[20];
+    const float *s = sig + STRIDE * f + 2 * t;
+#pragma unroll
+    for (int n1 = 0; n1 < 20; ++n1) {
+        const float2 x = *reinterpret_cast<const float2 *>(s + 20 * n1 + (STRIDE - kHop) * (n1 / 8));
+        const float2 w = *reinterpret_cast<const float2 *>(win + 20 * n1 + 2 * t);
+        v[n1] = cmul2(x, w);                          // sample * window[i] (src/spectrogram.rs:1319)
+    }
+    dft20(v);
+    pass1_store(v, ybase + 4 * t);
+}
+// One task = (frame = lane, column quad u): columns n2 = 4u .. 4u+3 = the column pairs 2u and 2u+1 from ONE 16-byte sample read
+// and one 16-byte window read per n1 (bulk-staged layout only): half the shared-memory instructions of two pair tasks.
+__device__ __forceinline__ void pass1_quad_tm(const float *__restrict__ sig, const float *__restrict__ win, int f, int u, uint32_t ybase) {
+    float2 va[20], vb[20];
+    const float *s = sig + kSigStrideB * f + 4 * u;
+#pragma unroll
+    for (int n1 = 0; n1 < 20; ++n1) {
+        const float4 x = *reinterpret_cast<const float4 *>(s + 20 * n1 + (kSigStrideB - kHop) * (n1 / 8));
+        const float4 w = *reinterpret_cast<const float4 *>(win + 20 * n1 + 4 * u);
+        va[n1] = cmul2(make_float2(x.x, x.y), make_float2(w.x, w.y));     // sample * window[i] (src/spectrogram.rs:1319)
+        vb[n1] = cmul2(make_float2(x.z, x.w), make_float2(w.z, w.w));
+    }
+    dft20(va);
+    pass1_store(va, ybase + 8 * u);
+    dft20(vb);
+    pass1_store(vb, ybase + 8 * u + 4);
+}
+
+// The next tile's samples by the TMA unit's 1-D form (cp.async.bulk, SASS UBLKCP): one thread of the group issues one copy per
+// hop block (34 per tile) against the group's mbarrier -- no per-lane address arithmetic, no LDGSTS issue slots.
+__device__ __forceinline__ void bulk_tile(float *sig, const float *src, uint64_t *bar) {
+    // Called by a whole converged warp with warp-uniform operands; one elected lane issues (operands in uniform registers, each
+    // copy a single UBLKCP -- issued from divergent code every copy is wrapped in an elect / broadcast loop).
+    const uint32_t b = tc::smem_addr(bar), d = tc::smem_addr(sig);
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        "elect.sync _|q, 0xffffffff;\n"
+        "@q fence.proxy.async.shared::cta;\n"        // earlier generic-proxy accesses of the tile before the async-proxy writes
+        "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
+        "}\n" ::"r"(b),
+        "r"(kTileBytes)
+        : "memory");
+#pragma unroll
+    for (int blk = 0; blk < kSigBlocks; ++blk) {
+        const uint32_t bytes = blk < kSigBlocks - 1 ? kHop * 4u : (kTileSamples - (kSigBlocks - 1) * kHop) * 4u;
+        asm volatile(
+            "{\n"
+            ".reg .pred q;\n"
+            "elect.sync _|q, 0xffffffff;\n"
+            "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+            "}\n" ::"r"(d + blk * (kSigStrideB * 4u)),
+            "l"(src + blk * kHop), "r"(bytes), "r"(b)
+            : "memory");
     }
 }
 
@@ -186,9 +247,11 @@ __device__ __forceinline__ void rows_epilogue(const KParams &p, const float *pti
     else sparse_quads_pipelined<0>(p, ptile, quads, q0, q1, ocf, nf, lane);
 }
 
-// GW: warps per group (4 or 6)
-template <int GW>
+// GW: warps per group (4; 5 / 6 for experiments). SIG: 0 = signal tile staged by cp.async (LDGSTS) in the 162-word layout, 1 = by
+// cp.async.bulk in the 164-word layout with 16-byte pass-1 reads (GW = 4, 16-byte aligned input).
+template <int GW, int SIG>
 __global__ void __launch_bounds__(kGroups * GW * 32, 1) k_r2c_fused_n400_tm(const __grid_constant__ F400Params P) {
+    constexpr int kPadW = SIG ? kSigStrideB - kHop : kSigBlockStride - kHop;
     constexpr int kGroupWarps = GW, kTmThreads = kGroups * GW * 32, kGroupThreads = GW * 32;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const KParams &p = P.k;
@@ -197,7 +260,9 @@ __global__ void __launch_bounds__(kGroups * GW * 32, 1) k_r2c_fused_n400_tm(cons
     const int nq = __ldg(blob);
     const int padded_weights = p.buf_elems;
     const TmSmem S = carve(smem_raw, nq, padded_weights);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // the warp index through a shuffle: the compiler then treats it -- and the group, tile and address arithmetic that follows
+    // from it -- as warp-uniform (uniform registers, single-instruction bulk copies)
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
 
     // ---- one-time setup: tables -> shared memory, zero rows behind the power tiles, TMEM allocation
     {
@@ -216,6 +281,8 @@ __global__ void __launch_bounds__(kGroups * GW * 32, 1) k_r2c_fused_n400_tm(cons
             const int cnt = e.w >= 0 ? __ldg(p.row_ptr + e.w + 1) - e0 : 0;
             for (int k = 0; k < ((e.y + 3) & ~3); ++k) S.w[e.z + k] = k < cnt ? __ldg(val + e0 + k) : 0.f;
         }
+        if (SIG && tid < kGroups) tc::mbar_init(S.bars + tid, 1);
+        if (SIG && tid == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if (warp == 0) tc::alloc(S.tmem_ptr, kTmemCols);
         tc::fence_before_sync();
         __syncthreads();
@@ -230,22 +297,35 @@ __global__ void __launch_bounds__(kGroups * GW * 32, 1) k_r2c_fused_n400_tm(cons
     const int q = warp & 3, wl = warp >> 2;                  // group = SM sub-partition = TMEM lane quarter; warp within the group
     const int gt = wl * 32 + lane;                           // thread within the group
     const uint32_t lane_base = tm + (static_cast<uint32_t>(32 * q) << 16);
-    float *sig = S.sig + q * kSigWords;
+    float *sig = S.sig + q * kSigWordsTm;
+    uint64_t *bar_sig = S.bars + q;
+    uint32_t bulk_parity = 0;                                // completed bulk-staged tiles of this group, mod 2
+    const bool bulk_ok = SIG && (p.vec_ok & 2);
     float *ptile = S.ptile + q * kPWordsTm;
     const float *xbase = static_cast<const float *>(p.samples);
     const bool vec_ok = p.vec_ok != 0;
     const int q0 = S.qrange[wl], q1 = S.qrange[wl + 1];
     const int bar = 1 + q;
 
+    // pass 1 of a whole tile by this warp: column pairs t = wl, wl + GW, ... (SIG = 0); column quad wl and, on warps 0 / 1, the
+    // pair 8 + wl (SIG = 1) -- three, three, two and two pairs either way
+    auto pass1_all = [&](const float *sg, const float *wn, int f, int w, uint32_t yb) {
+        if (SIG) {
+            pass1_quad_tm(sg, wn, f, w, yb);
+            if (w < 2) pass1_tm<kSigStrideB>(sg, wn, f, 8 + w, yb);
+        } else {
+#pragma unroll 1
+            for (int t = w; t < 10; t += kGroupWarps) pass1_tm(sg, wn, f, t, yb);
+        }
+    };
     int g = 4 * static_cast<int>(blockIdx.x) + q;            // this group's global tile index
     int clip = g / tpc, tile = g % tpc;                      // ... and its (clip, tile); both advance by carry
     if (g < total_tiles) {                                   // prologue: pass 1 of the group's first tile
-        load_tile(sig, xbase + static_cast<long long>(clip) * p.clip_stride, (p.frame_begin + static_cast<long long>(tile) * kFT) * kHop - p.pad, p.n_samples, vec_ok, gt, kGroupThreads,
-                  kTileSamples / 2);
+        load_tile<kPadW>(sig, xbase + static_cast<long long>(clip) * p.clip_stride, (p.frame_begin + static_cast<long long>(tile) * kFT) * kHop - p.pad, p.n_samples, vec_ok, gt,
+                         kGroupThreads, kTileSamples / 2);
         cp_async_commit_wait_all();
         tc::bar_sync(bar, kGroupThreads);
-#pragma unroll 1
-        for (int t = wl; t < 10; t += kGroupWarps) pass1_tm(sig, S.win, lane, t, lane_base);
+        pass1_all(sig, S.win, lane, wl, lane_base);
         tc::wait_st();
         tc::fence_before_sync();
         tc::bar_sync(bar, kGroupThreads);
@@ -254,13 +334,22 @@ __global__ void __launch_bounds__(kGroups * GW * 32, 1) k_r2c_fused_n400_tm(cons
     for (; g < total_tiles; g += gstep) {
         // ---- phase B: Y(g) is complete in TMEM, the samples are dead, the power tile is free
         const bool has_next = g + gstep < total_tiles;
+        bool bulk_now = false;
         int cn = clip + step_clip, tn = tile + step_tile;
         if (tn >= tpc) { tn -= tpc; ++cn; }
         if (has_next) {
             const long long sn = (p.frame_begin + static_cast<long long>(tn) * kFT) * kHop - p.pad;
             const float *xn = xbase + static_cast<long long>(cn) * p.clip_stride;
-            if (vec_ok && sn >= 0 && sn + kTileSamples <= p.n_samples) prefetch_tile_by_group<GW>(sig, xn + sn, wl, lane);
-            else load_tile(sig, xn, sn, p.n_samples, vec_ok, gt, kGroupThreads, kTileSamples / 2);
+            const bool interior = sn >= 0 && sn + kTileSamples <= p.n_samples;
+            if (SIG) {
+                bulk_now = bulk_ok && interior;
+                if (!bulk_now) load_tile<kPadW>(sig, xn, sn, p.n_samples, vec_ok, gt, kGroupThreads, kTileSamples / 2);
+                else if (wl == kGroupWarps - 1) bulk_tile(sig, xn + sn, bar_sig);      // the warp with the fewest pass-2 rows
+            } else if (vec_ok && interior) {
+                prefetch_tile_by_group<GW>(sig, xn + sn, wl, lane);
+            } else {
+                load_tile<kPadW>(sig, xn, sn, p.n_samples, vec_ok, gt, kGroupThreads, kTileSamples / 2);
+            }
         }
 #pragma unroll 1
         for (int k1 = wl; k1 <= 10; k1 += kGroupWarps) {
@@ -272,6 +361,10 @@ __global__ void __launch_bounds__(kGroups * GW * 32, 1) k_r2c_fused_n400_tm(cons
             pass2_finish_tm(v, ptile, lane, k1);
         }
         cp_async_commit_wait_all();
+        if (SIG && bulk_now) {
+            tc::mbar_wait(bar_sig, bulk_parity);
+            bulk_parity ^= 1u;
+        }
         tc::fence_before_sync();
         tc::bar_sync(bar, kGroupThreads);                    // P(g) complete, every Y row read, the next tile's samples have landed
         tc::fence_after_sync();
@@ -281,10 +374,7 @@ __global__ void __launch_bounds__(kGroups * GW * 32, 1) k_r2c_fused_n400_tm(cons
         const int nf = rem < kFT ? static_cast<int>(rem) : kFT;
         float *ocf = static_cast<float *>(p.out) + static_cast<long long>(clip) * p.out_clip_stride + (f0 - p.out_frame_origin);
         if (wl & 1) rows_epilogue(p, ptile, S.quads, q0, q1, ocf, nf, lane);
-        if (has_next) {
-#pragma unroll 1
-            for (int t = wl; t < 10; t += kGroupWarps) pass1_tm(sig, S.win, lane, t, lane_base);
-        }
+        if (has_next) pass1_all(sig, S.win, lane, wl, lane_base);
         if (!(wl & 1)) rows_epilogue(p, ptile, S.quads, q0, q1, ocf, nf, lane);
         tc::wait_st();
         tc::fence_before_sync();
@@ -307,11 +397,11 @@ int fast400_tm_max_group_warps() { return kMaxGroupWarps; }
 int fast400_tm_pad_rows() { return kPadRows; }
 
 namespace {
-template <int GW>
+template <int GW, int SIG = 0>
 cudaError_t launch_tm(const F400Params &P, long long grid, size_t smem, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(k_r2c_fused_n400_tm<GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaError_t e = cudaFuncSetAttribute(k_r2c_fused_n400_tm<GW, SIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    k_r2c_fused_n400_tm<GW><<<static_cast<unsigned>(grid), kGroups * GW * 32, smem, stream>>>(P);
+    k_r2c_fused_n400_tm<GW, SIG><<<static_cast<unsigned>(grid), kGroups * GW * 32, smem, stream>>>(P);
     return cudaGetLastError();
 }
 }  // namespace
@@ -329,6 +419,15 @@ cudaError_t launch_fast400_tm(const KParams &p, const float *window_f32, int n_q
     if (total <= 0) return cudaSuccess;
     const long long grid = std::min<long long>((total + 3) / 4, sm_count);        // persistent: one CTA per SM
     const size_t smem = fast400_tm_smem_bytes(n_quads, padded_weights);
+    // bulk-copy staging needs 16-byte aligned tiles: base, clip stride and the centre padding (200 or 0 samples; a tile starts at
+    // a multiple of 160 samples minus the padding)
+    static const bool bulk_off = std::getenv("SGX_N400_TM_SIG") && std::atoi(std::getenv("SGX_N400_TM_SIG")) == 0;
+    const bool bulk = !bulk_off && group_warps == 4 && (p.vec_ok & 1) && reinterpret_cast<uintptr_t>(p.samples) % 16 == 0 && p.clip_stride % 4 == 0 &&
+                      p.pad % 4 == 0;
+    if (bulk) {
+        P.k.vec_ok |= 2;
+        return launch_tm<4, 1>(P, grid, smem, stream);
+    }
     switch (group_warps) {
         case 4: return launch_tm<4>(P, grid, smem, stream);
         case 5: return launch_tm<5>(P, grid, smem, stream);
