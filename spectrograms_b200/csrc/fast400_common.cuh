@@ -174,15 +174,28 @@ struct QuadRegs {
     float4 w, x0, x1, x2, x3;      // first 4-column step
     unsigned pe;
 };
+// 16-byte shared-memory read if col < cnt, else the register keeps its (finite) old contents: it then meets a zero weight. A lane
+// group of 8 = one row = one quarter-warp wavefront, so a skipped read is a wavefront the L1 pipe never sees.
+__device__ __forceinline__ void lds_v4_if(float4 &v, unsigned a, int col, int cnt) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.lt.s32 p, %5, %6;\n"
+        "@p ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n"
+        "}\n"
+        : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
+        : "r"(a), "r"(col), "r"(cnt));
+}
 __device__ __forceinline__ void quad_fetch(QuadRegs &r, float4 d, unsigned pbase) {
     constexpr unsigned kRow = kFT * 4u;
     r.d = d;
     r.pe = pbase + __float_as_uint(d.x);
+    const int cnt = __float_as_int(d.y) >> 16;         // this row's own column count
     r.w = lds_v4(__float_as_uint(d.z));
-    r.x0 = lds_v4(r.pe);
-    r.x1 = lds_v4(r.pe + kRow);
-    r.x2 = lds_v4(r.pe + 2 * kRow);
-    r.x3 = lds_v4(r.pe + 3 * kRow);
+    lds_v4_if(r.x0, r.pe, 0, cnt);
+    lds_v4_if(r.x1, r.pe + kRow, 1, cnt);
+    lds_v4_if(r.x2, r.pe + 2 * kRow, 2, cnt);
+    lds_v4_if(r.x3, r.pe + 3 * kRow, 3, cnt);
 }
 template <int AMP, bool FULL>
 __device__ __forceinline__ void quad_finish(const QuadRegs &r, float eps, char *ob, unsigned ors4, int j, int nf) {
@@ -192,12 +205,15 @@ __device__ __forceinline__ void quad_finish(const QuadRegs &r, float eps, char *
     lo = cfma2(bc2(r.w.y), make_float2(r.x1.x, r.x1.y), lo); hi = cfma2(bc2(r.w.y), make_float2(r.x1.z, r.x1.w), hi);
     lo = cfma2(bc2(r.w.z), make_float2(r.x2.x, r.x2.y), lo); hi = cfma2(bc2(r.w.z), make_float2(r.x2.z, r.x2.w), hi);
     lo = cfma2(bc2(r.w.w), make_float2(r.x3.x, r.x3.y), lo); hi = cfma2(bc2(r.w.w), make_float2(r.x3.z, r.x3.w), hi);
-    const int steps = __float_as_int(r.d.y) >> 2;
+    const int steps = (__float_as_int(r.d.y) & 0xffff) >> 2, cnt = __float_as_int(r.d.y) >> 16;
 #pragma unroll 1
     for (int e4 = 1; e4 < steps; ++e4) {               // rows longer than four columns (warp-uniform count)
         const float4 we = lds_v4(__float_as_uint(r.d.z) + 16u * e4);
-        const float4 z0 = lds_v4(r.pe + kRow * (4 * e4)), z1 = lds_v4(r.pe + kRow * (4 * e4 + 1));
-        const float4 z2 = lds_v4(r.pe + kRow * (4 * e4 + 2)), z3 = lds_v4(r.pe + kRow * (4 * e4 + 3));
+        float4 z0 = r.x0, z1 = r.x0, z2 = r.x0, z3 = r.x0;      // any finite values: columns beyond the row's own meet zero weights
+        lds_v4_if(z0, r.pe + kRow * (4 * e4), 4 * e4, cnt);
+        lds_v4_if(z1, r.pe + kRow * (4 * e4 + 1), 4 * e4 + 1, cnt);
+        lds_v4_if(z2, r.pe + kRow * (4 * e4 + 2), 4 * e4 + 2, cnt);
+        lds_v4_if(z3, r.pe + kRow * (4 * e4 + 3), 4 * e4 + 3, cnt);
         lo = cfma2(bc2(we.x), make_float2(z0.x, z0.y), lo); hi = cfma2(bc2(we.x), make_float2(z0.z, z0.w), hi);
         lo = cfma2(bc2(we.y), make_float2(z1.x, z1.y), lo); hi = cfma2(bc2(we.y), make_float2(z1.z, z1.w), hi);
         lo = cfma2(bc2(we.z), make_float2(z2.x, z2.y), lo); hi = cfma2(bc2(we.z), make_float2(z2.z, z2.w), hi);
@@ -230,6 +246,7 @@ __device__ __forceinline__ void sparse_quads_pipelined_impl(const KParams &p, co
     char *ob = reinterpret_cast<char *>(out_clip_frame) + 4 * j;
     const int last = q1 - 1;
     QuadRegs A, B;
+    A.x0 = A.x1 = A.x2 = A.x3 = B.x0 = B.x1 = B.x2 = B.x3 = make_float4(0.f, 0.f, 0.f, 0.f);
     quad_fetch(A, lds_v4(qbase + 64u * q0), pbase);
     float4 dn = lds_v4(qbase + 64u * (q0 + 1 < q1 ? q0 + 1 : last));      // descriptor one quad ahead of the fetches
 #pragma unroll 1

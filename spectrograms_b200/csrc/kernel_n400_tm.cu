@@ -23,6 +23,7 @@
 // Measured steps of this design (dedicated filterbank warps behind full / free barriers lost: one or two such warps per
 // group are latency bound) are in profiles/r2_n400_tm_experiments.md.
 #include <cstdlib>
+#include <vector>
 
 #include "fast400_common.cuh"
 #include "launch.hpp"
@@ -43,6 +44,15 @@ constexpr int kPWordsTm = (kBins + kPadRows) * kFT;
 constexpr int kSigStrideB = 164;
 constexpr int kSigWordsTm = kSigBlocks * kSigStrideB;      // 5576 >= kSigWords: both layouts fit
 constexpr uint32_t kTileBytes = kTileSamples * 4u;
+
+// kernel parameter block: the window comes from the plan's device copy (it is staged into shared memory once per CTA anyway),
+// which leaves room for the pass-2 twiddles in both forms inside the classic 4 KiB
+struct TmParams {
+    KParams k;
+    float2 tw2[10][20];     // s(k1) * W400^(n2 k1) (f400::Consts::tw2) for k1 = 1 .. 10 (row 0 is all ones)
+    float2 tw2r[9][20];     // i * tw2 = (-tw2.y, tw2.x) for k1 = 1 .. 9 (row 10 multiplies real values)
+};
+static_assert(sizeof(TmParams) <= 4096, "kernel parameter block must fit the classic 4 KiB limit");
 
 struct TmSmem {
     float *sig;        // [4][kSigWordsTm] one signal tile per group
@@ -118,9 +128,21 @@ __device__ __forceinline__ void pass1_quad_tm(const float *__restrict__ sig, con
         vb[n1] = cmul2(make_float2(x.z, x.w), make_float2(w.z, w.w));
     }
     dft20(va);
-    pass1_store(va, ybase + 8 * u);
     dft20(vb);
-    pass1_store(vb, ybase + 8 * u + 4);
+    const uint32_t y = ybase + 8 * u;
+    {
+        const float2 a0 = va[reg_of_bin(0)], a10 = va[reg_of_bin(10)], b0 = vb[reg_of_bin(0)], b10 = vb[reg_of_bin(10)];
+        tc::st8(y, __float_as_uint(a0.x), __float_as_uint(a10.x), __float_as_uint(a0.y), __float_as_uint(a10.y), __float_as_uint(b0.x),
+                __float_as_uint(b10.x), __float_as_uint(b0.y), __float_as_uint(b10.y));
+    }
+#pragma unroll
+    for (int k1 = 1; k1 < 10; ++k1) {
+        const float2 A = va[reg_of_bin(k1)], B = va[reg_of_bin(20 - k1)], C = vb[reg_of_bin(k1)], D = vb[reg_of_bin(20 - k1)];
+        const float2 sa = cadd(A, make_float2(B.x, -B.y)), sb = cadd(make_float2(A.y, -A.x), make_float2(B.y, B.x));
+        const float2 sc = cadd(C, make_float2(D.x, -D.y)), sd = cadd(make_float2(C.y, -C.x), make_float2(D.y, D.x));
+        tc::st8(y + 40 * k1, __float_as_uint(sa.x), __float_as_uint(sa.y), __float_as_uint(sb.x), __float_as_uint(sb.y), __float_as_uint(sc.x),
+                __float_as_uint(sc.y), __float_as_uint(sd.x), __float_as_uint(sd.y));
+    }
 }
 
 // The next tile's samples by the TMA unit's 1-D form (cp.async.bulk, SASS UBLKCP): one thread of the group issues one copy per
@@ -175,7 +197,10 @@ __device__ __forceinline__ void y_row_wait(uint32_t (&q)[40]) {
                  :
                  : "memory");
 }
-__device__ __forceinline__ void pass2_twiddle(const uint32_t (&q)[40], const float2 *__restrict__ tw2, int k1, float2 (&v)[20]) {
+// tw2 / tw2r: this k1's twiddles w and i w = (-w.y, w.x) from the constant bank (forming the rotation in registers cost an FADD per
+// twiddle; reading both from shared memory cost 200 wavefronts per tile on the L1 pipe, the busiest unit)
+__device__ __forceinline__ void pass2_twiddle(const uint32_t (&q)[40], const float2 *__restrict__ tw2, const float2 *__restrict__ tw2r, int k1,
+                                              float2 (&v)[20]) {
     if (k1 == 0) {
 #pragma unroll
         for (int j = 0; j < 10; ++j) {
@@ -191,9 +216,8 @@ __device__ __forceinline__ void pass2_twiddle(const uint32_t (&q)[40], const flo
     } else {
 #pragma unroll
         for (int j = 0; j < 10; ++j) {
-            const float2 w0 = tw2[2 * j], w1 = tw2[2 * j + 1];
-            v[2 * j] = cfma2(bc2(__uint_as_float(q[4 * j + 1])), make_float2(-w0.y, w0.x), cmul2(bc2(__uint_as_float(q[4 * j])), w0));
-            v[2 * j + 1] = cfma2(bc2(__uint_as_float(q[4 * j + 3])), make_float2(-w1.y, w1.x), cmul2(bc2(__uint_as_float(q[4 * j + 2])), w1));
+            v[2 * j] = cfma2(bc2(__uint_as_float(q[4 * j + 1])), tw2r[2 * j], cmul2(bc2(__uint_as_float(q[4 * j])), tw2[2 * j]));
+            v[2 * j + 1] = cfma2(bc2(__uint_as_float(q[4 * j + 3])), tw2r[2 * j + 1], cmul2(bc2(__uint_as_float(q[4 * j + 2])), tw2[2 * j + 1]));
         }
     }
 }
@@ -250,7 +274,7 @@ __device__ __forceinline__ void rows_epilogue(const KParams &p, const float *pti
 // GW: warps per group (4; 5 / 6 for experiments). SIG: 0 = signal tile staged by cp.async (LDGSTS) in the 162-word layout, 1 = by
 // cp.async.bulk in the 164-word layout with 16-byte pass-1 reads (GW = 4, 16-byte aligned input).
 template <int GW, int SIG>
-__global__ void __launch_bounds__(kGroups * GW * 32, 1) k_r2c_fused_n400_tm(const __grid_constant__ F400Params P) {
+__global__ void __launch_bounds__(kGroups * GW * 32, 1) k_r2c_fused_n400_tm(const __grid_constant__ TmParams P) {
     constexpr int kPadW = SIG ? kSigStrideB - kHop : kSigBlockStride - kHop;
     constexpr int kGroupWarps = GW, kTmThreads = kGroups * GW * 32, kGroupThreads = GW * 32;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -270,15 +294,16 @@ __global__ void __launch_bounds__(kGroups * GW * 32, 1) k_r2c_fused_n400_tm(cons
         const int4 *gq = reinterpret_cast<const int4 *>(blob + hdr);
         const float *val = static_cast<const float *>(p.val);
         const unsigned wbase = smem_u32(S.w);
-        for (int i = tid; i < kN; i += kTmThreads) S.win[i] = P.c.win[i];
+        for (int i = tid; i < kN; i += kTmThreads) S.win[i] = __ldg(static_cast<const float *>(p.window) + i);
         if (tid <= kGroupWarps) S.qrange[tid] = __ldg(blob + 1 + tid);
         for (int i = tid; i < kGroups * kPadRows * kFT; i += kTmThreads)
             S.ptile[(i / (kPadRows * kFT)) * kPWordsTm + kBins * kFT + i % (kPadRows * kFT)] = 0.f;
         for (int i = tid; i < 4 * nq; i += kTmThreads) {
             const int4 e = __ldg(gq + i);
-            S.quads[i] = make_int4(e.x * (kFT * 4), e.y, static_cast<int>(wbase + 4u * e.z), e.w);
             const int e0 = e.w >= 0 ? __ldg(p.row_ptr + e.w) : 0;
             const int cnt = e.w >= 0 ? __ldg(p.row_ptr + e.w + 1) - e0 : 0;
+            // .y: the quad's padded (warp-uniform) column count, and above it the row's own count (tile reads beyond it are skipped)
+            S.quads[i] = make_int4(e.x * (kFT * 4), e.y | (cnt << 16), static_cast<int>(wbase + 4u * e.z), e.w);
             for (int k = 0; k < ((e.y + 3) & ~3); ++k) S.w[e.z + k] = k < cnt ? __ldg(val + e0 + k) : 0.f;
         }
         if (SIG && tid < kGroups) tc::mbar_init(S.bars + tid, 1);
@@ -307,12 +332,12 @@ __global__ void __launch_bounds__(kGroups * GW * 32, 1) k_r2c_fused_n400_tm(cons
     const int q0 = S.qrange[wl], q1 = S.qrange[wl + 1];
     const int bar = 1 + q;
 
-    // pass 1 of a whole tile by this warp: column pairs t = wl, wl + GW, ... (SIG = 0); column quad wl and, on warps 0 / 1, the
-    // pair 8 + wl (SIG = 1) -- three, three, two and two pairs either way
+    // pass 1 of a whole tile by this warp: column pairs t = wl, wl + GW, ... (SIG = 0); column quad wl and, on warp 0, quad 4 as
+    // well (SIG = 1; the host deals that warp correspondingly fewer filterbank rows)
     auto pass1_all = [&](const float *sg, const float *wn, int f, int w, uint32_t yb) {
         if (SIG) {
             pass1_quad_tm(sg, wn, f, w, yb);
-            if (w < 2) pass1_tm<kSigStrideB>(sg, wn, f, 8 + w, yb);
+            if (w == 0) pass1_quad_tm(sg, wn, f, 4, yb);
         } else {
 #pragma unroll 1
             for (int t = w; t < 10; t += kGroupWarps) pass1_tm(sg, wn, f, t, yb);
@@ -357,7 +382,7 @@ __global__ void __launch_bounds__(kGroups * GW * 32, 1) k_r2c_fused_n400_tm(cons
             float2 v[20];
             y_row_request(lane_base, k1, yq);
             y_row_wait(yq);
-            pass2_twiddle(yq, P.c.tw2[k1], k1, v);
+            pass2_twiddle(yq, P.tw2[k1 ? k1 - 1 : 0], P.tw2r[k1 - 1 < 9u ? k1 - 1 : 0], k1, v);
             pass2_finish_tm(v, ptile, lane, k1);
         }
         cp_async_commit_wait_all();
@@ -398,7 +423,7 @@ int fast400_tm_pad_rows() { return kPadRows; }
 
 namespace {
 template <int GW, int SIG = 0>
-cudaError_t launch_tm(const F400Params &P, long long grid, size_t smem, cudaStream_t stream) {
+cudaError_t launch_tm(const TmParams &P, long long grid, size_t smem, cudaStream_t stream) {
     cudaError_t e = cudaFuncSetAttribute(k_r2c_fused_n400_tm<GW, SIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     k_r2c_fused_n400_tm<GW, SIG><<<static_cast<unsigned>(grid), kGroups * GW * 32, smem, stream>>>(P);
@@ -408,13 +433,21 @@ cudaError_t launch_tm(const F400Params &P, long long grid, size_t smem, cudaStre
 
 cudaError_t launch_fast400_tm(const KParams &p, const float *window_f32, int n_quads, int padded_weights, int group_warps, int sm_count,
                               cudaStream_t stream) {
-    F400Params P;
+    TmParams P;
     P.k = p;
     P.k.FT = f400::kFT;
     P.k.fd_FT = make_fastdiv(static_cast<unsigned>(f400::kFT));
     P.k.tiles_per_clip = static_cast<int>((p.frames_todo + f400::kFT - 1) / f400::kFT);
     P.k.buf_elems = padded_weights;
-    fast400_fill_consts(P.c, window_f32);
+    {
+        static const f400::Consts c = [] { f400::Consts t; std::vector<float> w(f400::kN, 0.f); fast400_fill_consts(t, w.data()); return t; }();
+        for (int k1 = 1; k1 <= 10; ++k1)
+            for (int n2 = 0; n2 < 20; ++n2) {
+                P.tw2[k1 - 1][n2] = c.tw2[k1][n2];
+                if (k1 < 10) P.tw2r[k1 - 1][n2] = make_float2(-c.tw2[k1][n2].y, c.tw2[k1][n2].x);
+            }
+    }
+    (void)window_f32;                                       // the kernel reads the plan's device window (p.window)
     const long long total = static_cast<long long>(p.n_clips) * P.k.tiles_per_clip;
     if (total <= 0) return cudaSuccess;
     const long long grid = std::min<long long>((total + 3) / 4, sm_count);        // persistent: one CTA per SM

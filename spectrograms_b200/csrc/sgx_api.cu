@@ -537,7 +537,7 @@ void select_family(sgx_plan &pl) {
         // also run one more pass-1 task than warps 2 and 3 in the same phase: they start with that much load.
         {
             const int Wt = pl.tm_warps;
-            static const long bias = std::getenv("SGX_N400_TM_BIAS") ? std::atol(std::getenv("SGX_N400_TM_BIAS")) : 150;
+            static const long bias = std::getenv("SGX_N400_TM_BIAS") ? std::atol(std::getenv("SGX_N400_TM_BIAS")) : 200;
             std::vector<int> cntU(nq), woq(4 * static_cast<size_t>(nq));
             int padded_tm = 0;
             bool ok = nq > 0;
@@ -553,7 +553,9 @@ void select_family(sgx_plan &pl) {
             }
             std::vector<std::vector<int>> per_warp(Wt);
             std::vector<long> load(Wt, 0);
-            for (int w = 0; w < Wt; ++w) load[w] = bias * ((10 - w + Wt - 1) / Wt);      // pass-1 tasks w, w + Wt, ... < 10
+            // pass-1 column pairs of warp w: w, w + Wt, ... < 10 -- with four warps the bulk-staged kernel runs them as column quads
+            // w and, on warp 0, quad 4: four, two, two and two pairs
+            for (int w = 0; w < Wt; ++w) load[w] = bias * (Wt == 4 ? (w == 0 ? 4 : 2) : (10 - w + Wt - 1) / Wt);
             for (int q = 0; q < nq; ++q) {
                 int best = 0;
                 for (int w = 1; w < Wt; ++w) if (load[w] < load[best]) best = w;
