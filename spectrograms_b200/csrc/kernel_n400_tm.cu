@@ -173,6 +173,52 @@ __device__ __forceinline__ void bulk_tile(float *sig, const float *src, uint64_t
             : "memory");
     }
 }
+// First / last tiles of a clip (centre zero padding, clip end): the hop blocks [b0, b1) that lie wholly inside the clip still come
+// by bulk copy (same calling convention as bulk_tile; src = the tile's first sample, possibly before the clip) ...
+__device__ __forceinline__ void bulk_blocks(float *sig, const float *src, uint64_t *bar, int b0, int b1) {
+    const uint32_t b = tc::smem_addr(bar), d = tc::smem_addr(sig);
+    const uint32_t total = static_cast<uint32_t>(b1 - b0) * (kHop * 4u) - (b1 == kSigBlocks ? (kSigBlocks * kHop - kTileSamples) * 4u : 0u);
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        "elect.sync _|q, 0xffffffff;\n"
+        "@q fence.proxy.async.shared::cta;\n"
+        "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
+        "}\n" ::"r"(b),
+        "r"(total)
+        : "memory");
+#pragma unroll 1
+    for (int blk = b0; blk < b1; ++blk) {
+        const uint32_t bytes = blk < kSigBlocks - 1 ? kHop * 4u : (kTileSamples - (kSigBlocks - 1) * kHop) * 4u;
+        asm volatile(
+            "{\n"
+            ".reg .pred q;\n"
+            "elect.sync _|q, 0xffffffff;\n"
+            "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+            "}\n" ::"r"(d + blk * (kSigStrideB * 4u)),
+            "l"(src + blk * kHop), "r"(bytes), "r"(b)
+            : "memory");
+    }
+}
+// ... and the group's threads fill the others: zeros where a block lies wholly outside the clip, sample by sample (zero outside,
+// the reference's centre zero padding src/spectrogram.rs:1309-1320) for the at most two blocks that straddle an end of the clip.
+__device__ __forceinline__ void edge_blocks(float *sig, const float *x, long long sn, long long n, int b0, int b1, int gt, int threads) {
+#pragma unroll 1
+    for (int blk = 0; blk < kSigBlocks; ++blk) {
+        if (blk == b0 && b0 < b1) { blk = b1 - 1; continue; }
+        const long long sb = sn + static_cast<long long>(blk) * kHop;
+        const int len = blk < kSigBlocks - 1 ? kHop : kTileSamples - (kSigBlocks - 1) * kHop;
+        float *d = sig + blk * kSigStrideB;
+        if (sb + len <= 0 || sb >= n) {
+            for (int i = gt; i < len / 4; i += threads) reinterpret_cast<float4 *>(d)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+            for (int i = gt; i < len; i += threads) {
+                const long long sidx = sb + i;
+                d[i] = (sidx >= 0 && sidx < n) ? __ldg(x + sidx) : 0.f;
+            }
+        }
+    }
+}
 
 // ---- pass 2, one task = (frame = lane, k1): Y row from TMEM -> twiddle -> DFT20 -> |X|^2 into P[bin][frame].
 // The TMEM read port of a sub-partition delivers 14 B/clk (a 40-column row of 32 lanes takes ~360 cycles); the other warps of
@@ -317,8 +363,10 @@ __global__ void __launch_bounds__(kGroups * GW * 32, 1) k_r2c_fused_n400_tm(cons
 
     const int tpc = p.tiles_per_clip;
     const int total_tiles = p.n_clips * tpc;                 // the host splits batches so that this fits an int
-    const int gstep = 4 * static_cast<int>(gridDim.x);
-    const int step_clip = gstep / tpc, step_tile = gstep % tpc;
+    // Every group owns a CONTIGUOUS run of tiles [g, g_end): the first / last tiles of the clips (slower: zero-filled cp.async
+    // staging, partial stores) then spread evenly over the groups. With a grid-strided walk a group whose stride resonates with
+    // the tiles per clip (592 groups, 32 tiles per 10 s clip: the same two tile positions for ever) took the kernel's time.
+    const long long n_groups = 4LL * gridDim.x;
     const int q = warp & 3, wl = warp >> 2;                  // group = SM sub-partition = TMEM lane quarter; warp within the group
     const int gt = wl * 32 + lane;                           // thread within the group
     const uint32_t lane_base = tm + (static_cast<uint32_t>(32 * q) << 16);
@@ -343,9 +391,11 @@ __global__ void __launch_bounds__(kGroups * GW * 32, 1) k_r2c_fused_n400_tm(cons
             for (int t = w; t < 10; t += kGroupWarps) pass1_tm(sg, wn, f, t, yb);
         }
     };
-    int g = 4 * static_cast<int>(blockIdx.x) + q;            // this group's global tile index
+    const long long gid = 4LL * blockIdx.x + q;
+    int g = static_cast<int>(gid * total_tiles / n_groups);  // this group's global tile index
+    const int g_end = static_cast<int>((gid + 1) * total_tiles / n_groups);
     int clip = g / tpc, tile = g % tpc;                      // ... and its (clip, tile); both advance by carry
-    if (g < total_tiles) {                                   // prologue: pass 1 of the group's first tile
+    if (g < g_end) {                                   // prologue: pass 1 of the group's first tile
         load_tile<kPadW>(sig, xbase + static_cast<long long>(clip) * p.clip_stride, (p.frame_begin + static_cast<long long>(tile) * kFT) * kHop - p.pad, p.n_samples, vec_ok, gt,
                          kGroupThreads, kTileSamples / 2);
         cp_async_commit_wait_all();
@@ -356,20 +406,33 @@ __global__ void __launch_bounds__(kGroups * GW * 32, 1) k_r2c_fused_n400_tm(cons
         tc::bar_sync(bar, kGroupThreads);
         tc::fence_after_sync();
     }
-    for (; g < total_tiles; g += gstep) {
+    for (; g < g_end; ++g) {
         // ---- phase B: Y(g) is complete in TMEM, the samples are dead, the power tile is free
-        const bool has_next = g + gstep < total_tiles;
+        const bool has_next = g + 1 < g_end;
         bool bulk_now = false;
-        int cn = clip + step_clip, tn = tile + step_tile;
-        if (tn >= tpc) { tn -= tpc; ++cn; }
+        int cn = clip, tn = tile + 1;
+        if (tn >= tpc) { tn = 0; ++cn; }
         if (has_next) {
             const long long sn = (p.frame_begin + static_cast<long long>(tn) * kFT) * kHop - p.pad;
             const float *xn = xbase + static_cast<long long>(cn) * p.clip_stride;
             const bool interior = sn >= 0 && sn + kTileSamples <= p.n_samples;
             if (SIG) {
-                bulk_now = bulk_ok && interior;
-                if (!bulk_now) load_tile<kPadW>(sig, xn, sn, p.n_samples, vec_ok, gt, kGroupThreads, kTileSamples / 2);
-                else if (wl == kGroupWarps - 1) bulk_tile(sig, xn + sn, bar_sig);      // the warp with the fewest pass-2 rows
+                if (bulk_ok && interior) {
+                    bulk_now = true;
+                    if (wl == kGroupWarps - 1) bulk_tile(sig, xn + sn, bar_sig);       // the warp with the fewest pass-2 rows
+                } else if (bulk_ok) {
+                    // hop blocks [b0, b1) lie wholly inside the clip
+                    const int b0 = sn < 0 ? static_cast<int>((-sn + kHop - 1) / kHop) : 0;
+                    const long long fb = p.n_samples > sn ? (p.n_samples - sn) / kHop : 0;
+                    int b1 = fb < kSigBlocks - 1 ? static_cast<int>(fb) : kSigBlocks - 1;
+                    if (b1 == kSigBlocks - 1 && sn + kTileSamples <= p.n_samples) b1 = kSigBlocks;
+                    if (b1 < b0) b1 = b0;
+                    bulk_now = b1 > b0;
+                    if (bulk_now && wl == kGroupWarps - 1) bulk_blocks(sig, xn + sn, bar_sig, b0, b1);
+                    edge_blocks(sig, xn, sn, p.n_samples, b0, b1, gt, kGroupThreads);
+                } else {
+                    load_tile<kPadW>(sig, xn, sn, p.n_samples, vec_ok, gt, kGroupThreads, kTileSamples / 2);
+                }
             } else if (vec_ok && interior) {
                 prefetch_tile_by_group<GW>(sig, xn + sn, wl, lane);
             } else {
