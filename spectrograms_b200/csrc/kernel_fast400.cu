@@ -133,10 +133,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_r2c_fused_n400(const __grid_con
         }
     }
 
-    // persistent walk over tiles t = blockIdx.x, += gridDim.x; (clip, tile) advance by carry instead of dividing
+    // persistent walk over a CONTIGUOUS run of tiles [t_cur, t_end) per CTA (the slower first / last tiles of the clips spread evenly
+    // over the CTAs; a grid-strided walk can resonate with the tiles per clip); (clip, tile) advance by carry instead of dividing
     const int tpc = p.tiles_per_clip;
-    const int step_clip = static_cast<int>(gridDim.x / tpc), step_tile = static_cast<int>(gridDim.x % tpc);
-    int clip = static_cast<int>(blockIdx.x / tpc), tile = static_cast<int>(blockIdx.x % tpc);
+    const long long total_tiles = static_cast<long long>(p.n_clips) * tpc;
+    long long t_cur = blockIdx.x * total_tiles / gridDim.x;
+    const long long t_end = (blockIdx.x + 1LL) * total_tiles / gridDim.x;
+    int clip = t_cur < t_end ? static_cast<int>(t_cur / tpc) : p.n_clips, tile = static_cast<int>(t_cur % tpc);
     const float *xbase = static_cast<const float *>(p.samples);
     int buf = 0;
     if (clip < p.n_clips)
@@ -153,9 +156,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_r2c_fused_n400(const __grid_con
         cp_async_commit_wait_all();
         __syncthreads();                       // tile t has landed; everyone is done with the previous tile's P
 
-        clip += step_clip;                     // next tile of this CTA
-        tile += step_tile;
-        if (tile >= tpc) { tile -= tpc; ++clip; }
+        ++tile;                                // next tile of this CTA
+        if (tile >= tpc) { tile = 0; ++clip; }
+        if (++t_cur >= t_end) clip = p.n_clips;
         // Prefetch of the next tile into the other buffer, overlapped with pass 1: warp 10 has no pass-1 role and issues
         // the whole tile (about as many instructions as one pass-1 task). Edge tiles (first / last of a clip, or unaligned
         // input) take the general path, shared by all warps.

@@ -16,6 +16,8 @@
 // runtime division from the index math (all radices, strides and shifts are template constants).
 #include "binaural.cuh"
 #include "epilogue.cuh"
+#include <type_traits>
+
 #include "launch.hpp"
 #include "tcgen05.cuh"
 
@@ -235,6 +237,17 @@ template <int M> struct Radices {          // M = 16^P16 * LAST, LAST in {1, 2, 
 // Complex values a thread holds. 32 (f32, M = 512 / 1024: n_fft 1024 / 2048) makes the FFT two passes -- radix 32 then radix
 // M / 32 -- with ONE exchange instead of two: the L1 / shared-memory data pipe is what these sizes run out of (94 % busy on
 // BASELINE configs[2] with three passes). f64 and the other sizes keep 16 (64 f64 registers of data per thread are too many).
+template <typename T> __device__ __forceinline__ T lds_t(unsigned a);
+template <> __device__ __forceinline__ float lds_t<float>(unsigned a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+template <> __device__ __forceinline__ double lds_t<double>(unsigned a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
 template <typename T> constexpr int rpt_of(int M) { return (sizeof(T) == 4 && (M == 512 || M == 1024)) ? 32 : 16; }
 
 template <typename T, int M, int FT, bool PAIR>
@@ -269,6 +282,19 @@ k_r2c_fused_pow2(const __grid_constant__ KParams p) {
     const T *win = static_cast<const T *>(p.window);
     const C *tw = static_cast<const C *>(p.tw);
     C v[RPT];
+
+    // Rows-per-thread epilogue (small tiles, sparse mapping): its lane-major weights start their way into shared memory now
+    // (cp.async, no registers held) and are read from there after the FFT -- from global memory every batch of weight loads
+    // was an exposed L2 round trip with 16 warps per SM (10 % of the music shard's stall samples).
+    if constexpr (!PAIR) {
+        if (p.lane_w_smem) {
+            const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(smem_raw + p.lane_w_smem));
+            const char *src = static_cast<const char *>(p.lane_w);
+            for (int o = 16 * tid; o < p.lane_w_bytes; o += 16 * FT * TPF)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + o), "l"(src + o) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+    }
 
     // ---- load + window + first pass (CUR = 1: no twiddles). Element n of the packed frame = samples 2n, 2n+1.
     {
@@ -516,34 +542,45 @@ k_r2c_fused_pow2(const __grid_constant__ KParams p) {
             P[(M - k) * FT + fl] = pb[u];
         }
         if (t == 0) P[(M / 2) * FT + fl] = pm;
+        if (p.lane_w_smem) asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
         const T eps = static_cast<T>(p.eps);
-        const T *lw = static_cast<const T *>(p.lane_w);
         T *out = static_cast<T *>(p.out) + static_cast<long long>(clip) * p.out_clip_stride + (f0 - p.out_frame_origin);
         // lane slots from the host-built schedule (sgx_api.cu, build_lane_rows): rows of similar length share a warp, the
-        // weight of entry i of the warp's 32 rows is one coalesced line, the tile read is a 16-byte vector per column
-        for (int slot = tid; slot < p.n_lane_slots; slot += FT * TPF) {
-            const int4 d = __ldg(p.lane_rows + slot);            // {row, first column, count, weight block}
-            const T *wl = lw + d.w + (slot & 31);
-            const T *pc = P + d.y * FT;
-            T acc[FT];
+        // weight of entry i of the warp's 32 rows is one coalesced line, the tile read is a 16-byte vector per column.
+        // Two copies of the loop so that the weight reads are plain shared-memory loads in one and read-only global loads in the other.
+        auto rows = [&](auto staged) {
+            constexpr bool STAGED = decltype(staged)::value;
+            const unsigned ws = static_cast<unsigned>(__cvta_generic_to_shared(smem_raw)) + static_cast<unsigned>(p.lane_w_smem);
+            const T *lw = static_cast<const T *>(p.lane_w);
+            for (int slot = tid; slot < p.n_lane_slots; slot += FT * TPF) {
+                const int4 d = __ldg(p.lane_rows + slot);            // {row, first column, count, weight block}
+                const T *wl = lw + d.w + (slot & 31);
+                const unsigned wsl = ws + static_cast<unsigned>(sizeof(T)) * static_cast<unsigned>(d.w + (slot & 31));
+                const T *pc = P + d.y * FT;
+                T acc[FT];
 #pragma unroll
-            for (int f = 0; f < FT; ++f) acc[f] = T(0);
+                for (int f = 0; f < FT; ++f) acc[f] = T(0);
 #pragma unroll 4
-            for (int i = 0; i < d.z; ++i) {
-                const T w = __ldg(wl + i * 32);
-                T x[FT];
+                for (int i = 0; i < d.z; ++i) {
+                    T w;
+                    if constexpr (STAGED) w = lds_t<T>(wsl + static_cast<unsigned>(sizeof(T)) * 32u * static_cast<unsigned>(i));
+                    else w = __ldg(wl + i * 32);
+                    T x[FT];
 #pragma unroll
-                for (int f = 0; f < FT; ++f) x[f] = pc[i * FT + f];
+                    for (int f = 0; f < FT; ++f) x[f] = pc[i * FT + f];
 #pragma unroll
-                for (int f = 0; f < FT; ++f) acc[f] = t_add_rn(acc[f], t_mul_rn(w, x[f]));
+                    for (int f = 0; f < FT; ++f) acc[f] = t_add_rn(acc[f], t_mul_rn(w, x[f]));
+                }
+                if (d.x < 0) continue;
+                T *orow = out + static_cast<long long>(d.x) * p.out_row_stride;
+#pragma unroll
+                for (int f = 0; f < FT; ++f)
+                    if (f < nf) orow[f] = amp_scale<T>(acc[f], p.amp, p.apply_db, eps);
             }
-            if (d.x < 0) continue;
-            T *orow = out + static_cast<long long>(d.x) * p.out_row_stride;
-#pragma unroll
-            for (int f = 0; f < FT; ++f)
-                if (f < nf) orow[f] = amp_scale<T>(acc[f], p.amp, p.apply_db, eps);
-        }
+        };
+        if (!PAIR && p.lane_w_smem != 0) rows(std::true_type{});
+        else rows(std::false_type{});
         return;
     }
     if (p.output == SGX_OUT_SPECTROGRAM && p.mapping == SGX_MAP_LINEAR) {
@@ -925,6 +962,13 @@ size_t pow2_bulk_stage_bytes(size_t n_fft, size_t hop, bool f64) {
     const int M = static_cast<int>(n_fft / 2);
     if (f64 || rpt_of<float>(M) != 32 || hop > 1024 || hop % 4 != 0) return 0;
     return sizeof(float) * (static_cast<size_t>(ft_of(M, false) - 1) * 1024 + n_fft) + 16;
+}
+// CTAs per SM the forward kernel's launch bounds ask for (the shared-memory budget of a CTA follows from it)
+int pow2_min_blocks(size_t n_fft, bool f64) {
+    const int M = static_cast<int>(n_fft / 2), ft = ft_of(M, f64);
+    if (!f64 && rpt_of<float>(M) == 32) return 512 / (ft * (M / 32));
+    const int threads = ft * (M / 16);
+    return (f64 ? 2 : 4) * 256 / (threads > 256 ? threads : 256);
 }
 int pow2_frame_elems(size_t n_fft, bool f64) {
     const int M = static_cast<int>(n_fft / 2);

@@ -78,6 +78,9 @@ struct KParams {
     FastDiv fd_L, fd_out_len, fd_FT, fd_r0, fd_stage_B[kFdStages], fd_stage_cur[kFdStages];   // fd_r0: radix of stage 0 (the only stage that can be a cofactor stage)
     int frame_stride;     // complex elements between frames in a buffer (>= L+1)
     int tile_stride;      // T elements between frames in the power / mel tile
+    // ---- r2c_fused_pow2, rows-per-thread epilogue: the lane-major weights staged into shared memory by cp.async at kernel start
+    int lane_w_smem;      // byte offset of the staged copy in dynamic shared memory (0: read the weights from global memory)
+    int lane_w_bytes;     // its size (a multiple of 16)
 };
 
 template <typename T> struct Cplx;

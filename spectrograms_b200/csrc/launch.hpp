@@ -50,6 +50,7 @@ int fast400_tm_pad_rows();
 bool pow2_supported(size_t n_fft);
 int pow2_frames_per_tile(size_t n_fft, bool f64);
 int pow2_frame_elems(size_t n_fft, bool f64);
+int pow2_min_blocks(size_t n_fft, bool f64);                        // CTAs per SM of the forward kernel's launch bounds
 size_t pow2_bulk_stage_bytes(size_t n_fft, size_t hop, bool f64);   // extra smem of the cp.async.bulk staged variant (0: none)
 cudaError_t launch_pow2(const KParams &p, bool f64, size_t smem_bytes, cudaStream_t stream);
 

@@ -850,6 +850,22 @@ void run_device(sgx_plan &pl, const void *d_samples, size_t n_clips, size_t n_sa
                 q.vec_ok |= 2;
                 smem += extra;
             }
+            // rows-per-thread epilogue (FT <= 8, sparse mapping): stage the lane-major weights in shared memory when that does not
+            // cost a resident CTA (kernel_pow2.cu); SGX_POW2_STAGE_W=0 keeps them in global memory
+            static const bool stage_w_off = std::getenv("SGX_POW2_STAGE_W") && std::atoi(std::getenv("SGX_POW2_STAGE_W")) == 0;
+            q.lane_w_smem = 0;
+            q.lane_w_bytes = 0;
+            // (measured: n_fft 2048 -9 .. -11 %, n_fft 1024 +1.7 % -- its rows are half as long -- so from 2048 points on)
+            if (!stage_w_off && !(q.vec_ok & 2) && q.FT <= 8 && pl.desc.n_fft >= 2048 && pl.desc.output == SGX_OUT_SPECTROGRAM && pl.desc.mapping != SGX_MAP_LINEAR &&
+                q.n_lane_slots > 0 && !pl.lane_w.empty()) {
+                const size_t wbytes = pl.lane_w.size() * pl.esize, base = (smem + 15) & ~size_t(15);
+                const size_t budget = size_t(227) * 1024 / static_cast<size_t>(std::max(1, pow2_min_blocks(pl.desc.n_fft, pl.f64))) - 1024;
+                if (wbytes % 16 == 0 && base + wbytes <= budget) {
+                    q.lane_w_smem = static_cast<int>(base);
+                    q.lane_w_bytes = static_cast<int>(wbytes);
+                    smem = base + wbytes;
+                }
+            }
             ck(launch_pow2(q, pl.f64, smem, stream), "kernel launch (r2c_fused_pow2)");
         } else if (pl.mixed && !pl.force_generic) {
             q.FT = mixed_tile_frames();
