@@ -283,6 +283,24 @@ k_r2c_fused_pow2(const __grid_constant__ KParams p) {
     const C *tw = static_cast<const C *>(p.tw);
     C v[RPT];
 
+    // The CTA that will take this one's place on the SM (about blockIdx.x + resident CTAs, in launch order) finds its samples in L2:
+    // one 128-byte line per thread, no register or scoreboard held. The first global load of a CTA is otherwise an exposed HBM
+    // round trip with 16 warps per SM.
+    if constexpr (!PAIR) {
+        if (p.l2_ahead) {
+            const long long b2 = static_cast<long long>(blockIdx.x) + p.l2_ahead;
+            const long long clip2 = b2 / p.tiles_per_clip;
+            if (clip2 < p.n_clips) {
+                constexpr int EPL = 128 / static_cast<int>(sizeof(T));       // elements per 128-byte line
+                const long long s0 = (p.frame_begin + (b2 - clip2 * p.tiles_per_clip) * FT) * p.hop - p.pad;
+                const T *x2 = static_cast<const T *>(p.samples) + clip2 * p.clip_stride;
+                for (int o = EPL * tid; o < (FT - 1) * p.hop + N + EPL; o += EPL * FT * TPF) {
+                    const long long s2 = s0 + o;
+                    if (s2 >= 0 && s2 < p.n_samples) asm volatile("prefetch.global.L2 [%0];" ::"l"(x2 + s2));
+                }
+            }
+        }
+    }
     // Rows-per-thread epilogue (small tiles, sparse mapping): its lane-major weights start their way into shared memory now
     // (cp.async, no registers held) and are read from there after the FFT -- from global memory every batch of weight loads
     // was an exposed L2 round trip with 16 warps per SM (10 % of the music shard's stall samples).

@@ -81,6 +81,7 @@ struct KParams {
     // ---- r2c_fused_pow2, rows-per-thread epilogue: the lane-major weights staged into shared memory by cp.async at kernel start
     int lane_w_smem;      // byte offset of the staged copy in dynamic shared memory (0: read the weights from global memory)
     int lane_w_bytes;     // its size (a multiple of 16)
+    int l2_ahead;         // r2c_fused_pow2: prefetch the samples of CTA blockIdx.x + l2_ahead into L2 at kernel start (0: off)
 };
 
 template <typename T> struct Cplx;
