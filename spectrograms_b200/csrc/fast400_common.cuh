@@ -176,26 +176,33 @@ struct QuadRegs {
 };
 // 16-byte shared-memory read if col < cnt, else the register keeps its (finite) old contents: it then meets a zero weight. A lane
 // group of 8 = one row = one quarter-warp wavefront, so a skipped read is a wavefront the L1 pipe never sees.
+template <int OFS>
 __device__ __forceinline__ void lds_v4_if(float4 &v, unsigned a, int col, int cnt) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "setp.lt.s32 p, %5, %6;\n"
-        "@p ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n"
+        "@p ld.shared.v4.f32 {%0, %1, %2, %3}, [%4 + %7];\n"
         "}\n"
         : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
-        : "r"(a), "r"(col), "r"(cnt));
+        : "r"(a), "r"(col), "r"(cnt), "n"(OFS));
+}
+template <int OFS>
+__device__ __forceinline__ float4 lds_v4_ofs(unsigned a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4 + %5];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a), "n"(OFS));
+    return v;
 }
 __device__ __forceinline__ void quad_fetch(QuadRegs &r, float4 d, unsigned pbase) {
-    constexpr unsigned kRow = kFT * 4u;
+    constexpr int kRow = kFT * 4;
     r.d = d;
     r.pe = pbase + __float_as_uint(d.x);
-    const int cnt = __float_as_int(d.y) >> 16;         // this row's own column count
+    const int cnt = __float_as_int(d.y) >> 16;         // this row's own column count (>= 1 for every row the host schedules)
     r.w = lds_v4(__float_as_uint(d.z));
-    lds_v4_if(r.x0, r.pe, 0, cnt);
-    lds_v4_if(r.x1, r.pe + kRow, 1, cnt);
-    lds_v4_if(r.x2, r.pe + 2 * kRow, 2, cnt);
-    lds_v4_if(r.x3, r.pe + 3 * kRow, 3, cnt);
+    r.x0 = lds_v4_ofs<0>(r.pe);
+    lds_v4_if<kRow>(r.x1, r.pe, 1, cnt);
+    lds_v4_if<2 * kRow>(r.x2, r.pe, 2, cnt);
+    lds_v4_if<3 * kRow>(r.x3, r.pe, 3, cnt);
 }
 template <int AMP, bool FULL>
 __device__ __forceinline__ void quad_finish(const QuadRegs &r, float eps, char *ob, unsigned ors4, int j, int nf) {
@@ -210,10 +217,11 @@ __device__ __forceinline__ void quad_finish(const QuadRegs &r, float eps, char *
     for (int e4 = 1; e4 < steps; ++e4) {               // rows longer than four columns (warp-uniform count)
         const float4 we = lds_v4(__float_as_uint(r.d.z) + 16u * e4);
         float4 z0 = r.x0, z1 = r.x0, z2 = r.x0, z3 = r.x0;      // any finite values: columns beyond the row's own meet zero weights
-        lds_v4_if(z0, r.pe + kRow * (4 * e4), 4 * e4, cnt);
-        lds_v4_if(z1, r.pe + kRow * (4 * e4 + 1), 4 * e4 + 1, cnt);
-        lds_v4_if(z2, r.pe + kRow * (4 * e4 + 2), 4 * e4 + 2, cnt);
-        lds_v4_if(z3, r.pe + kRow * (4 * e4 + 3), 4 * e4 + 3, cnt);
+        const unsigned pz = r.pe + kRow * (4 * e4);
+        lds_v4_if<0>(z0, pz, 4 * e4, cnt);
+        lds_v4_if<kRow>(z1, pz, 4 * e4 + 1, cnt);
+        lds_v4_if<2 * kRow>(z2, pz, 4 * e4 + 2, cnt);
+        lds_v4_if<3 * kRow>(z3, pz, 4 * e4 + 3, cnt);
         lo = cfma2(bc2(we.x), make_float2(z0.x, z0.y), lo); hi = cfma2(bc2(we.x), make_float2(z0.z, z0.w), hi);
         lo = cfma2(bc2(we.y), make_float2(z1.x, z1.y), lo); hi = cfma2(bc2(we.y), make_float2(z1.z, z1.w), hi);
         lo = cfma2(bc2(we.z), make_float2(z2.x, z2.y), lo); hi = cfma2(bc2(we.z), make_float2(z2.z, z2.w), hi);
@@ -246,7 +254,7 @@ __device__ __forceinline__ void sparse_quads_pipelined_impl(const KParams &p, co
     char *ob = reinterpret_cast<char *>(out_clip_frame) + 4 * j;
     const int last = q1 - 1;
     QuadRegs A, B;
-    A.x0 = A.x1 = A.x2 = A.x3 = B.x0 = B.x1 = B.x2 = B.x3 = make_float4(0.f, 0.f, 0.f, 0.f);
+    A.x1 = A.x2 = A.x3 = B.x1 = B.x2 = B.x3 = make_float4(0.f, 0.f, 0.f, 0.f);
     quad_fetch(A, lds_v4(qbase + 64u * q0), pbase);
     float4 dn = lds_v4(qbase + 64u * (q0 + 1 < q1 ? q0 + 1 : last));      // descriptor one quad ahead of the fetches
 #pragma unroll 1
