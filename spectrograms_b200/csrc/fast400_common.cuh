@@ -205,7 +205,7 @@ __device__ __forceinline__ void quad_fetch(QuadRegs &r, float4 d, unsigned pbase
     lds_v4_if<3 * kRow>(r.x3, r.pe, 3, cnt);
 }
 template <int AMP, bool FULL>
-__device__ __forceinline__ void quad_finish(const QuadRegs &r, float eps, char *ob, unsigned ors4, int j, int nf) {
+__device__ __forceinline__ void quad_finish(QuadRegs &r, float eps, char *ob, unsigned ors4, int j, int nf) {
     constexpr unsigned kRow = kFT * 4u;
     float2 lo = make_float2(0.f, 0.f), hi = lo;        // frames (j, j+8) and (j+16, j+24)
     lo = cfma2(bc2(r.w.x), make_float2(r.x0.x, r.x0.y), lo); hi = cfma2(bc2(r.w.x), make_float2(r.x0.z, r.x0.w), hi);
@@ -216,7 +216,8 @@ __device__ __forceinline__ void quad_finish(const QuadRegs &r, float eps, char *
 #pragma unroll 1
     for (int e4 = 1; e4 < steps; ++e4) {               // rows longer than four columns (warp-uniform count)
         const float4 we = lds_v4(__float_as_uint(r.d.z) + 16u * e4);
-        float4 z0 = r.x0, z1 = r.x0, z2 = r.x0, z3 = r.x0;      // any finite values: columns beyond the row's own meet zero weights
+        // into the (consumed) registers of the first step: whatever finite values a skipped read leaves there meet zero weights
+        float4 &z0 = r.x0, &z1 = r.x1, &z2 = r.x2, &z3 = r.x3;
         const unsigned pz = r.pe + kRow * (4 * e4);
         lds_v4_if<0>(z0, pz, 4 * e4, cnt);
         lds_v4_if<kRow>(z1, pz, 4 * e4 + 1, cnt);
