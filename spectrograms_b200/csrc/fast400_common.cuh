@@ -253,18 +253,20 @@ __device__ __forceinline__ void sparse_quads_pipelined_impl(const KParams &p, co
     const unsigned qbase = smem_u32(s_quads) + 16u * s;
     const unsigned ors4 = 4u * static_cast<unsigned>(p.out_row_stride);
     char *ob = reinterpret_cast<char *>(out_clip_frame) + 4 * j;
-    const int last = q1 - 1;
+    // The descriptor table is followed by three more valid quads (the next warp's, or the copies the kernel appends behind the
+    // last one), so the look-ahead reads below need no clamping: a quad fetched beyond q1 is simply never finished.
     QuadRegs A, B;
     A.x1 = A.x2 = A.x3 = B.x1 = B.x2 = B.x3 = make_float4(0.f, 0.f, 0.f, 0.f);
-    quad_fetch(A, lds_v4(qbase + 64u * q0), pbase);
-    float4 dn = lds_v4(qbase + 64u * (q0 + 1 < q1 ? q0 + 1 : last));      // descriptor one quad ahead of the fetches
+    unsigned qa = qbase + 64u * q0;
+    quad_fetch(A, lds_v4(qa), pbase);
+    float4 dn = lds_v4(qa + 64u);                                  // descriptor one quad ahead of the fetches
 #pragma unroll 1
-    for (int qi = q0; qi < q1; qi += 2) {
-        quad_fetch(B, dn, pbase);                                  // quad qi + 1 (or a harmless re-read of the last one)
-        dn = lds_v4(qbase + 64u * (qi + 2 < q1 ? qi + 2 : last));
+    for (int qi = q0; qi < q1; qi += 2, qa += 128u) {
+        quad_fetch(B, dn, pbase);                                  // quad qi + 1
+        dn = lds_v4(qa + 128u);
         quad_finish<AMP, FULL>(A, eps, ob, ors4, j, nf);
         quad_fetch(A, dn, pbase);                                  // quad qi + 2
-        dn = lds_v4(qbase + 64u * (qi + 3 < q1 ? qi + 3 : last));
+        dn = lds_v4(qa + 192u);
         if (qi + 1 < q1) quad_finish<AMP, FULL>(B, eps, ob, ors4, j, nf);
     }
 }

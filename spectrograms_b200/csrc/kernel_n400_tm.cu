@@ -66,7 +66,7 @@ struct TmSmem {
 };
 
 __host__ __device__ inline size_t tm_smem_bytes(int n_quads, int padded_weights) {
-    return sizeof(float) * (kGroups * (kSigWordsTm + kPWordsTm) + kN) + sizeof(int4) * 4 * static_cast<size_t>(n_quads) +
+    return sizeof(float) * (kGroups * (kSigWordsTm + kPWordsTm) + kN) + sizeof(int4) * 4 * static_cast<size_t>(n_quads + 3) +
            sizeof(int) * 12 + sizeof(float) * static_cast<size_t>(padded_weights + 8) + 8 + sizeof(uint64_t) * kGroups + 16;
 }
 
@@ -75,7 +75,7 @@ __device__ __forceinline__ TmSmem carve(unsigned char *base, int n_quads, int pa
     size_t o = 0;
     s.sig = reinterpret_cast<float *>(base + o);        o += sizeof(float) * kGroups * kSigWordsTm;
     s.ptile = reinterpret_cast<float *>(base + o);      o += sizeof(float) * kGroups * kPWordsTm;
-    s.quads = reinterpret_cast<int4 *>(base + o);       o += sizeof(int4) * 4 * static_cast<size_t>(n_quads);
+    s.quads = reinterpret_cast<int4 *>(base + o);       o += sizeof(int4) * 4 * static_cast<size_t>(n_quads + 3);    // + 3 look-ahead copies
     s.win = reinterpret_cast<float *>(base + o);        o += sizeof(float) * kN;
     s.qrange = reinterpret_cast<int *>(base + o);       o += sizeof(int) * 12;
     s.w = reinterpret_cast<float *>(base + o);          o += sizeof(float) * static_cast<size_t>(padded_weights + 8);
@@ -349,7 +349,9 @@ __global__ void __launch_bounds__(kGroups * GW * 32, 1) k_r2c_fused_n400_tm(cons
             const int e0 = e.w >= 0 ? __ldg(p.row_ptr + e.w) : 0;
             const int cnt = e.w >= 0 ? __ldg(p.row_ptr + e.w + 1) - e0 : 0;
             // .y: the quad's padded (warp-uniform) column count, and above it the row's own count (tile reads beyond it are skipped)
-            S.quads[i] = make_int4(e.x * (kFT * 4), e.y | (cnt << 16), static_cast<int>(wbase + 4u * e.z), e.w);
+            const int4 q4 = make_int4(e.x * (kFT * 4), e.y | (cnt << 16), static_cast<int>(wbase + 4u * e.z), e.w);
+            S.quads[i] = q4;
+            if (i >= 4 * (nq - 1)) S.quads[i + 4] = S.quads[i + 8] = S.quads[i + 12] = q4;      // the rows' look-ahead reads stay on valid quads
             for (int k = 0; k < ((e.y + 3) & ~3); ++k) S.w[e.z + k] = k < cnt ? __ldg(val + e0 + k) : 0.f;
         }
         if (SIG && tid < kGroups) tc::mbar_init(S.bars + tid, 1);
