@@ -19,6 +19,7 @@
 //   out      four more warps (one per sub-partition) wait for a tile's MMAs, tcgen05.ld the frame's coefficients (two D buffers:
 //            tile t-1 is drained while tile t multiplies), add the two column halves, apply the lifter and store one 128-byte
 //            run of frames per coefficient row; the conversion warps never wait for an MMA to complete
+#include "kparams.cuh"
 #include "launch.hpp"
 #include "tcgen05.cuh"
 
@@ -39,7 +40,12 @@ struct DctParams {
     float *out;                // [n_clips][rows][n_frames]
     const float *blob;         // per 8-mel K step: N x 8 hi tile then lo tile (K-major core matrices), then lifter[n_mfcc]
     long long n_frames, in_row_stride;
+    long long out_clip_stride;  // floats between clips of the output
     int n_clips, n_mels, kp, n_mfcc, row0, N, tiles_per_clip;
+    int out_row_base;           // output row of coefficient row0 (dense filterbank passes write row blocks of a wider output)
+    int mode;                   // 0: coefficient * lifter (MFCC); 1: amplitude scaling of a filterbank row (amp / apply_db / eps)
+    int amp, apply_db;
+    float eps;
 };
 
 __global__ void __launch_bounds__(kAllThreads, 1) k_dct2_lifter_tc(const __grid_constant__ DctParams p) {
@@ -102,7 +108,7 @@ __global__ void __launch_bounds__(kAllThreads, 1) k_dct2_lifter_tc(const __grid_
         const long long t = blockIdx.x + it * gridDim.x;
         const long long clip = t / p.tiles_per_clip, tile = t - clip * p.tiles_per_clip;
         const long long f = tile * kTile + frame_in_tile;
-        float *o = p.out + clip * (p.n_mfcc - p.row0) * p.n_frames + f;
+        float *o = p.out + clip * p.out_clip_stride + static_cast<long long>(p.out_row_base) * p.n_frames + f;
         for (int c0 = 0; c0 < p.N; c0 += 16) {
             uint32_t v[16];
             uint32_t u[16];
@@ -113,7 +119,10 @@ __global__ void __launch_bounds__(kAllThreads, 1) k_dct2_lifter_tc(const __grid_
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const int c = c0 + i;
-                    if (c >= p.row0 && c < p.n_mfcc) o[static_cast<long long>(c - p.row0) * p.n_frames] = (__uint_as_float(v[i]) + __uint_as_float(u[i])) * sLift[c];
+                    if (c >= p.row0 && c < p.n_mfcc) {
+                        const float acc = __uint_as_float(v[i]) + __uint_as_float(u[i]);
+                        o[static_cast<long long>(c - p.row0) * p.n_frames] = p.mode == 0 ? acc * sLift[c] : amp_scale<float>(acc, p.amp, p.apply_db, p.eps);
+                    }
                 }
             }
         }
@@ -237,9 +246,28 @@ size_t mfcc_tc_blob_floats(int n_mels, int n_mfcc) {
     return static_cast<size_t>(mfcc_tc_padded_mels(n_mels) / 8) * 2 * mfcc_tc_padded_coeffs(n_mfcc) * 8 + static_cast<size_t>(n_mfcc);
 }
 
+namespace {
+cudaError_t launch_gemm_tc(DctParams p, int sm_count, cudaStream_t stream) {
+    p.kp = mfcc_tc_padded_mels(p.n_mels);
+    p.N = mfcc_tc_padded_coeffs(p.n_mfcc);
+    p.tiles_per_clip = static_cast<int>((p.n_frames + kTile - 1) / kTile);
+    const long long total = static_cast<long long>(p.n_clips) * p.tiles_per_clip;
+    if (total <= 0) return cudaSuccess;
+    const size_t b_floats = static_cast<size_t>(p.kp / 8) * 2 * p.N * 8;
+    size_t smem = sizeof(float) * (b_floats + 64) + sizeof(uint64_t) * 8 + 16;
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    smem = std::max<size_t>(smem, 120 * 1024);          // one CTA per SM: it owns all 512 TMEM columns
+    cudaError_t e = cudaFuncSetAttribute(k_dct2_lifter_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    const long long grid = std::min<long long>(total, sm_count);
+    k_dct2_lifter_tc<<<static_cast<unsigned>(grid), kAllThreads, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+}  // namespace
+
 cudaError_t launch_mfcc_tc(const float *log_mel, long long in_row_stride, float *out, long long n_clips, int n_mels, long long n_frames, int n_mfcc,
                            int row0, const float *blob, int sm_count, cudaStream_t stream) {
-    DctParams p;
+    DctParams p{};
     p.log_mel = log_mel;
     p.in_row_stride = in_row_stride;
     p.out = out;
@@ -247,21 +275,44 @@ cudaError_t launch_mfcc_tc(const float *log_mel, long long in_row_stride, float 
     p.n_frames = n_frames;
     p.n_clips = static_cast<int>(n_clips);
     p.n_mels = n_mels;
-    p.kp = mfcc_tc_padded_mels(n_mels);
     p.n_mfcc = n_mfcc;
     p.row0 = row0;
-    p.N = mfcc_tc_padded_coeffs(n_mfcc);
-    p.tiles_per_clip = static_cast<int>((n_frames + kTile - 1) / kTile);
-    const long long total = n_clips * p.tiles_per_clip;
-    if (total <= 0) return cudaSuccess;
-    const size_t b_floats = static_cast<size_t>(p.kp / 8) * 2 * p.N * 8;
-    size_t smem = sizeof(float) * (b_floats + 64) + sizeof(uint64_t) * 8 + 16;
-    smem = std::max<size_t>(smem, 120 * 1024);          // one CTA per SM: it owns all 512 TMEM columns
-    cudaError_t e = cudaFuncSetAttribute(k_dct2_lifter_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess) return e;
-    const long long grid = std::min<long long>(total, sm_count);
-    k_dct2_lifter_tc<<<static_cast<unsigned>(grid), kAllThreads, smem, stream>>>(p);
-    return cudaGetLastError();
+    p.out_clip_stride = static_cast<long long>(n_mfcc - row0) * n_frames;
+    p.out_row_base = 0;
+    p.mode = 0;
+    return launch_gemm_tc(p, sm_count, stream);
+}
+
+// One row block of a dense filterbank (ERB, src/erb.rs:374-402) applied to a linear power spectrogram as the same GEMM:
+// power [n_clips][n_cols][n_frames] (rows in_row_stride apart) -> rows [row_base, row_base + n_rows) of out [n_clips][.][n_frames]
+// (clips out_clip_stride floats apart), followed by the amplitude scaling. n_rows <= dense_tc_max_rows(n_cols); blob as for
+// dct2_lifter_tc with the block's weights as the "basis" (no lifter section needed).
+int dense_tc_max_rows(int n_cols) {
+    const size_t steps = static_cast<size_t>(mfcc_tc_padded_mels(n_cols) / 8);
+    const size_t budget = (size_t(200) * 1024) / (steps * 2 * 8 * sizeof(float));      // rows whose hi + lo tiles fit beside the barriers
+    const int rows = static_cast<int>(std::min<size_t>(64, budget)) & ~15;
+    return rows;
+}
+cudaError_t launch_dense_tc(const float *power, long long in_row_stride, float *out, long long out_clip_stride, long long n_clips, int n_cols,
+                            long long n_frames, int row_base, int n_rows, const float *blob, int amp, int apply_db, float eps, int sm_count,
+                            cudaStream_t stream) {
+    DctParams p{};
+    p.log_mel = power;
+    p.in_row_stride = in_row_stride;
+    p.out = out;
+    p.blob = blob;
+    p.n_frames = n_frames;
+    p.n_clips = static_cast<int>(n_clips);
+    p.n_mels = n_cols;
+    p.n_mfcc = n_rows;
+    p.row0 = 0;
+    p.out_clip_stride = out_clip_stride;
+    p.out_row_base = row_base;
+    p.mode = 1;
+    p.amp = amp;
+    p.apply_db = apply_db;
+    p.eps = eps;
+    return launch_gemm_tc(p, sm_count, stream);
 }
 
 }  // namespace sgx

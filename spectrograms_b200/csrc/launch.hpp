@@ -78,6 +78,14 @@ size_t mfcc_tc_blob_floats(int n_mels, int n_mfcc);
 cudaError_t launch_mfcc_tc(const float *log_mel, long long in_row_stride, float *out, long long n_clips, int n_mels, long long n_frames, int n_mfcc,
                            int row0, const float *blob, int sm_count, cudaStream_t stream);
 
+// the same kernel as a dense filterbank row block (ERB): linear power spectrogram [n_clips][n_cols][n_frames] -> rows [row_base,
+// row_base + n_rows) of out, amplitude scaling fused; n_rows <= dense_tc_max_rows(n_cols) (0: the column count does not fit).
+// blob: build as for dct2_lifter_tc with the block's weights as the basis.
+int dense_tc_max_rows(int n_cols);
+cudaError_t launch_dense_tc(const float *power, long long in_row_stride, float *out, long long out_clip_stride, long long n_clips, int n_cols,
+                            long long n_frames, int row_base, int n_rows, const float *blob, int amp, int apply_db, float eps, int sm_count,
+                            cudaStream_t stream);
+
 // standalone chromagram_from_spectrogram (kernel_chroma.cu): spec [n_clips][n_bins][n_frames] -> out [n_clips][12][n_frames];
 // w_transposed is the chroma filterbank as T[n_bins][12], non-zero only for bins in [k0, k1)
 cudaError_t launch_chroma(bool f64, const void *spec, void *out, long long n_clips, int n_bins, long long n_frames,

@@ -201,6 +201,11 @@ struct sgx_plan {
     void *d_frames = nullptr;               // istft: windowed time frames of a chunk of clips
     bool mfcc_split = false;                // n400 f32 mfcc(): log-mel by r2c_fused_n400_tm, DCT-II by dct2_lifter_tc (tcgen05)
     float *d_dct_tc = nullptr;              // ... basis blob of dct2_lifter_tc
+    // dense (ERB) f32 spectrogram plans outside the n400_tc kernel: linear power spectrogram of a chunk of clips into plan scratch by
+    // the plan's FFT family, then the filterbank as row blocks of the tcgen05 GEMM (dense_rows_tc = the dct2_lifter_tc kernel)
+    bool dense_split = false;
+    int dense_block_rows = 0;               // rows per GEMM pass
+    std::vector<float *> d_dense_tc;        // one B-operand blob per row block
     void *d_logmel = nullptr;               // ... log-mel scratch of a chunk of clips
     size_t logmel_cap = 0;
     size_t frames_cap = 0;
@@ -240,6 +245,7 @@ struct sgx_plan {
         for (void *q : d_pair) if (q) cudaFree(q);
         if (d_frames) cudaFree(d_frames);
         if (d_dct_tc) cudaFree(d_dct_tc);
+        for (float *q : d_dense_tc) if (q) cudaFree(q);
         if (d_logmel) cudaFree(d_logmel);
         if (scratch_done) cudaEventDestroy(scratch_done);
         for (auto &s : slot) {
@@ -620,6 +626,13 @@ void select_family(sgx_plan &pl) {
     pl.fast400_sparse = pl.fast400 && csr && contiguous && fast400_sparse_fits(pl.sparse_quads, pl.sparse_weights);
     build_tc_blob(pl);
     pl.fast400_tc = pl.tc_steps > 0;
+    {
+        static const bool dense_tc_off = std::getenv("SGX_DENSE_TC") && std::atoi(std::getenv("SGX_DENSE_TC")) == 0;
+        const int rows = dense_tc_max_rows(static_cast<int>(pl.tab.out_len));
+        pl.dense_block_rows = rows;
+        pl.dense_split = !dense_tc_off && !pl.f64 && d.mapping == SGX_MAP_ERB && d.output == SGX_OUT_SPECTROGRAM && rows >= 16 &&
+                         !pl.fast400_tc && !pl.tab.dense.empty();
+    }
     pl.fast400_tm = pl.fast400 && csr && contiguous && d.output == SGX_OUT_SPECTROGRAM && !pl.wofs_tm.empty() &&
                     fast400_tm_fits(pl.sparse_quads, pl.tm_weights);
     // fused mfcc() on the n400 family: the log-mel spectrogram by the TMEM-exchange kernel, the DCT-II on the tensor cores
@@ -701,6 +714,14 @@ void ensure_device(sgx_plan &pl) {
     pl.d_lifter = upload(pl.tab.lifter, pl.f64);
     pl.d_dct_folded = upload(pl.dct_folded, pl.f64);
     if (pl.mfcc_split) pl.d_dct_tc = upload_floats(build_dct_tc_blob(pl.tab.n_bins, pl.desc.n_mfcc, pl.tab.dct, pl.tab.lifter));
+    if (pl.dense_split) {
+        const size_t nb = pl.tab.n_bins, ol = pl.tab.out_len;
+        for (size_t r0 = 0; r0 < nb; r0 += static_cast<size_t>(pl.dense_block_rows)) {
+            const size_t nr = std::min<size_t>(static_cast<size_t>(pl.dense_block_rows), nb - r0);
+            const std::vector<double> block(pl.tab.dense.begin() + static_cast<std::ptrdiff_t>(r0 * ol), pl.tab.dense.begin() + static_cast<std::ptrdiff_t>((r0 + nr) * ol));
+            pl.d_dense_tc.push_back(upload_floats(build_dct_tc_blob(ol, nr, block, std::vector<double>(nr, 1.0))));
+        }
+    }
     cudaDeviceProp prop;
     ck(cudaGetDeviceProperties(&prop, dev), "cudaGetDeviceProperties");
     pl.sm_count = prop.multiProcessorCount;
@@ -757,10 +778,20 @@ void fill_params(const sgx_plan &pl, KParams &p) {
 // run frames [frame_begin, frame_begin+frames_todo) of n_clips device-resident clips
 void run_device(sgx_plan &pl, const void *d_samples, size_t n_clips, size_t n_samples, size_t clip_stride, void *d_out,
                 long long out_row_stride, long long out_clip_stride, long long frame_begin, long long frames_todo,
-                cudaStream_t stream, long long pad_override = -1) {
+                cudaStream_t stream, long long pad_override = -1, bool as_linear_power = false) {
     KParams p;
     fill_params(pl, p);
     if (pad_override >= 0) p.pad = static_cast<int>(pad_override);
+    if (as_linear_power) {
+        // the plan's FFT family with the identity mapping and no scaling: |X|^2 [out_len][frames] (first half of a dense split)
+        p.mapping = SGX_MAP_LINEAR;
+        p.n_bins = static_cast<int>(pl.tab.out_len);
+        p.amp = SGX_AMP_POWER;
+        p.apply_db = 0;
+        p.output = SGX_OUT_SPECTROGRAM;
+        p.n_lane_slots = 0;
+        p.rows_contig = 0;
+    }
     p.samples = d_samples;
     p.n_samples = static_cast<long long>(n_samples);
     p.clip_stride = static_cast<long long>(clip_stride);
@@ -776,7 +807,36 @@ void run_device(sgx_plan &pl, const void *d_samples, size_t n_clips, size_t n_sa
     // then the DCT-II + lifter as a tcgen05 GEMM (dct2_lifter_tc). Two launches; only the log-mel tile (a sixth of the input's
     // bytes) makes a round trip through HBM / L2.
     const long long mfcc_rows = static_cast<long long>(pl.desc.n_mfcc) - p.mfcc_row0;
-    if (pl.mfcc_split && !pl.force_generic && pl.tm_mode != 0 && out_row_stride == frames_todo && out_clip_stride == mfcc_rows * frames_todo) {
+    if (pl.dense_split && !as_linear_power && !pl.force_generic && pl.tc_mode != 0 && out_row_stride == frames_todo &&
+        out_clip_stride == static_cast<long long>(pl.tab.n_bins) * frames_todo) {
+        const size_t ol = pl.tab.out_len, nb = pl.tab.n_bins;
+        const size_t per_clip = ol * static_cast<size_t>(frames_todo) * sizeof(float);
+        size_t chunk = std::max<size_t>(1, (size_t(1) << 30) / per_clip);
+        chunk = std::min(chunk, n_clips);
+        if (pl.logmel_cap < chunk * per_clip) {
+            if (pl.d_logmel) { ck(cudaDeviceSynchronize(), "sync"); cudaFree(pl.d_logmel); pl.d_logmel = nullptr; pl.logmel_cap = 0; }
+            ck(cudaMalloc(&pl.d_logmel, chunk * per_clip), "cudaMalloc(power scratch)");
+            pl.logmel_cap = chunk * per_clip;
+        }
+        pl.scratch_acquire(stream);
+        for (size_t c0 = 0; c0 < n_clips; c0 += chunk) {
+            const size_t nc = std::min(chunk, n_clips - c0);
+            run_device(pl, static_cast<const char *>(d_samples) + c0 * clip_stride * pl.esize, nc, n_samples, clip_stride, pl.d_logmel, frames_todo,
+                       static_cast<long long>(ol) * frames_todo, frame_begin, frames_todo, stream, pad_override, true);
+            size_t blk = 0;
+            for (size_t r0 = 0; r0 < nb; r0 += static_cast<size_t>(pl.dense_block_rows), ++blk) {
+                const size_t nr = std::min<size_t>(static_cast<size_t>(pl.dense_block_rows), nb - r0);
+                ck(launch_dense_tc(static_cast<const float *>(pl.d_logmel), frames_todo, static_cast<float *>(d_out) + c0 * static_cast<size_t>(out_clip_stride),
+                                   out_clip_stride, static_cast<long long>(nc), static_cast<int>(ol), frames_todo, static_cast<int>(r0), static_cast<int>(nr),
+                                   pl.d_dense_tc[blk], p.amp, p.apply_db, static_cast<float>(p.eps), pl.sm_count, stream),
+                   "kernel launch (dense_rows_tc)");
+                pl.last_launches += 1;
+            }
+        }
+        pl.scratch_release(stream);
+        return;
+    }
+    if (pl.mfcc_split && !as_linear_power && !pl.force_generic && pl.tm_mode != 0 && out_row_stride == frames_todo && out_clip_stride == mfcc_rows * frames_todo) {
         const size_t nb = pl.tab.n_bins;
         const size_t per_clip = nb * static_cast<size_t>(frames_todo) * sizeof(float);
         size_t chunk = std::max<size_t>(1, (size_t(1) << 30) / per_clip);
@@ -819,20 +879,21 @@ void run_device(sgx_plan &pl, const void *d_samples, size_t n_clips, size_t n_sa
         if (pl.fast400 && !pl.force_generic) {
             // 8-byte vector loads need an 8-byte aligned base and an even clip stride
             q.vec_ok = (reinterpret_cast<uintptr_t>(q.samples) % 8 == 0 && clip_stride % 2 == 0) ? 1 : 0;
-            if (use_tm(pl)) {
+            if (use_tm(pl) && !as_linear_power) {
                 q.sched = pl.d_wofs_tm;
                 ck(launch_fast400_tm(q, pl.window_f32.data(), pl.sparse_quads, pl.tm_weights, pl.tm_warps, pl.sm_count, stream), "kernel launch (r2c_fused_n400_tm)");
                 pl.last_launches += 1;
                 continue;
             }
-            if (use_tc(pl)) {
+            if (use_tc(pl) && !as_linear_power) {
                 q.sched = pl.d_tc_blob;
                 ck(launch_fast400_tc(q, pl.window_f32.data(), pl.tc_steps, pl.tc_rounds, pl.tc_b_floats, pl.sm_count, stream), "kernel launch (r2c_fused_n400_tc)");
                 pl.last_launches += 1;
                 continue;
             }
-            q.sched = pl.fast400_sparse ? pl.d_wofs : nullptr;
-            ck(launch_fast400(q, pl.window_f32.data(), pl.fast400_sparse, pl.sparse_quads, pl.sparse_weights, pl.sm_count, stream), "kernel launch (r2c_fused_n400)");
+            const bool sparse = pl.fast400_sparse && !as_linear_power;
+            q.sched = sparse ? pl.d_wofs : nullptr;
+            ck(launch_fast400(q, pl.window_f32.data(), sparse, pl.sparse_quads, pl.sparse_weights, pl.sm_count, stream), "kernel launch (r2c_fused_n400)");
         } else if (pl.pow2 && !pl.force_generic) {
             q.FT = pl.pow2_ft;
             q.fd_FT = make_fastdiv(static_cast<unsigned>(q.FT));
@@ -1000,6 +1061,11 @@ const char *sgx_plan_kernel_name(const sgx_plan *plan) {
     if (!plan) return "";
     if (plan->force_generic) return "r2c_fused_generic";
     if (plan->mfcc_split && plan->tm_mode != 0) return "r2c_fused_n400_tm+dct2_lifter_tc";
+    if (plan->dense_split && plan->tc_mode != 0) {
+        static thread_local std::string name;
+        name = plan->kernel_name + "+dense_rows_tc";
+        return name.c_str();
+    }
     if (use_tm(*plan)) return "r2c_fused_n400_tm";
     if (use_tc(*plan)) return "r2c_fused_n400_tc";
     return plan->kernel_name.c_str();

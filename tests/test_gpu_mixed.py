@@ -77,7 +77,7 @@ def test_mixed_all_mappings(n_fft, hop, amp, dtype):
         (pl.log_hz_plan(P(n_fft, hop), sg.LogHzParams(60, 60.0, 7000.0), db, amp, dtype), od(n_fft, hop, dtype, mapping="loghz", n_bands=60, f_min=60.0, f_max=7000.0, **okw)),
     ]
     for plan, odesc in cases:
-        assert plan.kernel_name() == "r2c_fused_mixed"
+        assert plan.kernel_name() in ("r2c_fused_mixed", "r2c_fused_mixed+dense_rows_tc")    # f32 ERB: FFT family + tcgen05 row blocks
         got = plan.compute(t).data.cpu().numpy()
         ref = oracle.Plan(odesc).compute(x.astype(np.float64))
         assert got.shape == ref.shape

@@ -151,6 +151,8 @@ def test_tc_selection_rule():
     assert pl.mel_plan(P(), sg.MelParams(128, 0.0, 8000.0), None, "power", "float32").kernel_name() == "r2c_fused_n400_tm"     # banded: CUDA cores, TMEM exchange
     big = pl.erb_plan(P(), sg.ErbParams(128, 50.0, 8000.0), None, "power", "float32")            # filterbank tiles exceed shared memory
     big.set_tensor_cores(True)
+    assert big.kernel_name() == "r2c_fused_n400+dense_rows_tc"           # ... so: linear power by the family, row blocks by the tcgen05 GEMM
+    big.set_tensor_cores(False)
     assert big.kernel_name() == "r2c_fused_n400"
     lin = pl.linear_plan(P(), None, "power", "float32")
     lin.set_tensor_cores(True)
