@@ -153,7 +153,8 @@ sgx_status sgx_plan_window(const sgx_plan *plan, void *out_host);
  * or ERB response matrix (src/erb.rs:261); *nnz = stored non-zeros (sparse mappings) or n_bins*out_len (dense). */
 sgx_status sgx_plan_filterbank(const sgx_plan *plan, double *dense_out_host, size_t *nnz);
 
-/* Name of the CUDA kernel family the plan dispatches to (e.g. "r2c_fused_generic", "r2c_fused_n400"). */
+/* Name of the CUDA kernel family the plan dispatches to (e.g. "r2c_fused_generic", "r2c_fused_n400_tm"); two-kernel paths are
+ * joined with '+' ("r2c_fused_n400_tm+dct2_lifter_tc" for mfcc(), "r2c_fused_pow2+dense_rows_tc" for a dense ERB plan). */
 const char *sgx_plan_kernel_name(const sgx_plan *plan);
 
 /* Number of kernel launches issued by the last compute call on this plan. */
@@ -165,7 +166,9 @@ sgx_status sgx_plan_force_generic(sgx_plan *plan, int force);
 /* TMEM / tcgen05 kernel variant of a family (r2c_fused_n400_tc: the FFT exchange lives in tensor memory and the filterbank
  * projection -- FrequencyMapping::apply, src/spectrogram.rs:1822-1881 -- runs as 3xTF32 MMAs): -1 = automatic (default:
  * used where it is measured faster, i.e. the dense ERB projection), 0 = never, 1 = whenever the plan supports it.
- * Test / measurement hook. */
+ * The same switch governs the split path of dense f32 (ERB) plans that the fused kernel does not cover (other n_fft, more than
+ * 64 bands): linear power spectrogram by the plan's FFT family, then the filterbank (src/erb.rs:374-402) as row blocks of the
+ * tcgen05 GEMM kernel ("...+dense_rows_tc"); 0 keeps the CUDA-core dense rows. Test / measurement hook. */
 sgx_status sgx_plan_set_tensor_cores(sgx_plan *plan, int enable);
 
 /* Tensor memory as the exchange medium between the two FFT passes of the n_fft = 400 / hop = 160 f32 family
