@@ -19,6 +19,8 @@
 //   out      four more warps (one per sub-partition) wait for a tile's MMAs, tcgen05.ld the frame's coefficients (two D buffers:
 //            tile t-1 is drained while tile t multiplies), add the two column halves, apply the lifter and store one 128-byte
 //            run of frames per coefficient row; the conversion warps never wait for an MMA to complete
+#include <type_traits>
+
 #include "kparams.cuh"
 #include "launch.hpp"
 #include "tcgen05.cuh"
@@ -87,21 +89,34 @@ __global__ void __launch_bounds__(kAllThreads, 1) k_dct2_lifter_tc(const __grid_
     const long long my_tiles = blockIdx.x < total ? (total - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const long long n_jobs = my_tiles * n_halves;              // job g = (tile g / n_halves of this CTA, half g % n_halves)
 
-    // the 32 values of this thread's frame for job g (zeros past the clip's last frame / the last mel)
-    auto load_job = [&](float (&v)[kPart], long long g) {
-        const long long it = g / n_halves;
-        const int h = static_cast<int>(g - it * n_halves);
-        const long long t = blockIdx.x + it * gridDim.x;
-        const long long clip = t / p.tiles_per_clip, tile = t - clip * p.tiles_per_clip;
-        const long long f = tile * kTile + frame_in_tile;
-        const int m0 = h * kHalf + hp * kPart;
+    // Job g of this CTA = (its tile g / n_halves, half g % n_halves). The conversion warps walk the jobs in order and keep the job
+    // coordinates as counters -- (tile, clip) of the tile advance by carry, no division per job -- once for the job being loaded
+    // (one ahead) and implicitly (g) for the job being converted.
+    const int step_clip = static_cast<int>(gridDim.x / p.tiles_per_clip), step_tile = static_cast<int>(gridDim.x % p.tiles_per_clip);
+    int ld_h = 0, ld_clip = static_cast<int>(blockIdx.x / p.tiles_per_clip), ld_tile = static_cast<int>(blockIdx.x % p.tiles_per_clip);
+    const unsigned row_bytes = static_cast<unsigned>(p.in_row_stride * static_cast<long long>(sizeof(float)));   // < 4 GB (checked by the host)
+    // the 32 values of this thread's frame for the next job in order (zeros past the clip's last frame / the last mel)
+    auto load_next = [&](float (&v)[kPart]) {
+        const long long f = static_cast<long long>(ld_tile) * kTile + frame_in_tile;
+        const int m0 = ld_h * kHalf + hp * kPart;
         const bool live = f < p.n_frames;
-        const float *src = p.log_mel + (clip * p.n_mels + m0) * p.in_row_stride + (live ? f : 0);
+        const char *src = reinterpret_cast<const char *>(p.log_mel + (static_cast<long long>(ld_clip) * p.n_mels + m0) * p.in_row_stride + (live ? f : 0));
+        const int nvalid = live ? p.n_mels - m0 : 0;
+        // independent addresses (one 32 x 32 -> 64-bit multiply-add each: every load can issue at once); rows beyond the last get zeros
 #pragma unroll
-        for (int i = 0; i < kPart; ++i) v[i] = (live && m0 + i < p.n_mels) ? __ldg(src + static_cast<long long>(i) * p.in_row_stride) : 0.f;
+        for (int i = 0; i < kPart; ++i)
+            v[i] = i < nvalid ? __ldg(reinterpret_cast<const float *>(src + static_cast<size_t>(static_cast<unsigned>(i) * static_cast<unsigned long long>(row_bytes)))) : 0.f;
+        if (++ld_h == n_halves) {
+            ld_h = 0;
+            ld_clip += step_clip;
+            ld_tile += step_tile;
+            if (ld_tile >= p.tiles_per_clip) { ld_tile -= p.tiles_per_clip; ++ld_clip; }
+        }
     };
     // coefficients of tile `it` of this CTA: D buffer it & 1 -> lifter -> rows of the output (drain warps)
-    auto drain = [&](long long it, uint32_t parity) {
+    // (two instantiations, chosen once per kernel: the MFCC loop stays as tight as it was before the kernel learnt the scalings)
+    auto drain = [&](auto mode_tag, long long it, uint32_t parity) {
+        constexpr int MODE = decltype(mode_tag)::value;
         const int pb = static_cast<int>(it & 1);
         tc::mbar_wait(&bars[2 + pb], parity);
         tc::fence_after_sync();
@@ -121,7 +136,7 @@ __global__ void __launch_bounds__(kAllThreads, 1) k_dct2_lifter_tc(const __grid_
                     const int c = c0 + i;
                     if (c >= p.row0 && c < p.n_mfcc) {
                         const float acc = __uint_as_float(v[i]) + __uint_as_float(u[i]);
-                        o[static_cast<long long>(c - p.row0) * p.n_frames] = p.mode == 0 ? acc * sLift[c] : amp_scale<float>(acc, p.amp, p.apply_db, p.eps);
+                        o[static_cast<long long>(c - p.row0) * p.n_frames] = MODE == 0 ? acc * sLift[c] : amp_scale<float>(acc, p.amp, p.apply_db, p.eps);
                     }
                 }
             }
@@ -131,12 +146,10 @@ __global__ void __launch_bounds__(kAllThreads, 1) k_dct2_lifter_tc(const __grid_
         if (lane == 0) tc::mbar_arrive(&bars[6 + pb]);         // this sub-partition's quarter of the D buffer is free again
     };
     uint32_t a_uses[2] = {0, 0};          // MMA groups committed on each A buffer so far (mbarrier parity)
-    uint32_t d_done = 0;                  // tiles whose MMAs have been committed
     // one job: job g + 1 is requested into `nxt`, job g is converted from `cur` into A buffer g & 1 and multiplied
     auto step = [&](float (&cur)[kPart], float (&nxt)[kPart], long long g) {
-        const long long it = g / n_halves;
-        const int h = static_cast<int>(g - it * n_halves), b = static_cast<int>(g & 1);
-        if (g + 1 < n_jobs) load_job(nxt, g + 1);
+        const int b = static_cast<int>(g & 1);
+        if (g + 1 < n_jobs) load_next(nxt);
         if (a_uses[b] > 0) {                                   // the MMAs that last read this A buffer are done
             tc::mbar_wait(&bars[b], (a_uses[b] - 1) & 1);
             tc::fence_after_sync();
@@ -163,7 +176,6 @@ __global__ void __launch_bounds__(kAllThreads, 1) k_dct2_lifter_tc(const __grid_
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&bars[4 + b]);          // this warp's 32 rows x 32 mels of the half are in TMEM
         a_uses[b] += 1;
-        if (h == n_halves - 1) d_done += 1;
     };
 
     if (__shfl_sync(0xffffffffu, warp, 0) == kThreads / 32) {
@@ -194,9 +206,10 @@ __global__ void __launch_bounds__(kAllThreads, 1) k_dct2_lifter_tc(const __grid_
                     "}\n" ::"r"(tc::smem_addr(bar))
                     : "memory");
             };
-            for (long long g = 0; g < n_jobs; ++g) {
-                const long long it = g / n_halves;
-                const int h = static_cast<int>(g - it * n_halves), b = static_cast<int>(g & 1);
+            long long it = 0;
+            int h = 0;
+            for (long long g = 0; g < n_jobs; ++g, h = h + 1 == n_halves ? 0 : h + 1, it += h == 0 ? 1 : 0) {
+                const int b = static_cast<int>(g & 1);
                 tc::mbar_wait(&bars[4 + b], static_cast<uint32_t>((g >> 1) & 1));
                 if (h == 0 && it >= 2) tc::mbar_wait(&bars[6 + (it & 1)], static_cast<uint32_t>(((it - 2) >> 1) & 1));   // tile it - 2 has left this D buffer
                 tc::fence_after_sync();
@@ -220,16 +233,16 @@ __global__ void __launch_bounds__(kAllThreads, 1) k_dct2_lifter_tc(const __grid_
         }
     } else if (warp > kThreads / 32) {
         // ---- drain warps (one per sub-partition: warp_id % 4 selects the TMEM lanes): tile after tile as the MMAs complete
-        for (long long it = 0; it < my_tiles; ++it) drain(it, static_cast<uint32_t>((it >> 1) & 1));
+        if (p.mode == 0) for (long long it = 0; it < my_tiles; ++it) drain(std::integral_constant<int, 0>{}, it, static_cast<uint32_t>((it >> 1) & 1));
+        else for (long long it = 0; it < my_tiles; ++it) drain(std::integral_constant<int, 1>{}, it, static_cast<uint32_t>((it >> 1) & 1));
     } else {
         float va[kPart], vb[kPart];
-        if (n_jobs > 0) load_job(va, 0);
+        if (n_jobs > 0) load_next(va);
         for (long long g = 0; g < n_jobs; g += 2) {
             step(va, vb, g);
             if (g + 1 < n_jobs) step(vb, va, g + 1);
         }
     }
-    (void)d_done;
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::dealloc(tm, kTmemCols);
@@ -255,7 +268,7 @@ cudaError_t launch_gemm_tc(DctParams p, int sm_count, cudaStream_t stream) {
     if (total <= 0) return cudaSuccess;
     const size_t b_floats = static_cast<size_t>(p.kp / 8) * 2 * p.N * 8;
     size_t smem = sizeof(float) * (b_floats + 64) + sizeof(uint64_t) * 8 + 16;
-    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    if (smem > 227 * 1024 || p.in_row_stride * static_cast<long long>(sizeof(float)) >= (1LL << 32)) return cudaErrorInvalidValue;
     smem = std::max<size_t>(smem, 120 * 1024);          // one CTA per SM: it owns all 512 TMEM columns
     cudaError_t e = cudaFuncSetAttribute(k_dct2_lifter_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
