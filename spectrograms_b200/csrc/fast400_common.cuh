@@ -106,7 +106,7 @@ __device__ __forceinline__ float4 lds_v4(unsigned a) {
 // frame order as the power tile) for the fused DCT.
 template <int AMP, bool TO_SMEM, bool FULL>
 __device__ __forceinline__ void sparse_quads_epilogue_impl(const KParams &p, const float *ptile, const int4 *s_quads, int q0, int q1, int qstep,
-                                                           float *out_clip_frame, float *mtile, int nf, int lane) {
+                                                           float *out_clip_frame, float *mtile, int nf, int lane, unsigned wrel = 0u) {
     const float eps = static_cast<float>(p.eps);
     const int s = lane >> 3, j = lane & 7;
     const unsigned pbase = smem_u32(ptile) + 16u * j;             // columns 4j..4j+3 = frames j, j+8, j+16, j+24
@@ -118,7 +118,7 @@ __device__ __forceinline__ void sparse_quads_epilogue_impl(const KParams &p, con
         const float4 rf = lds_v4(qbase + 16u * (4 * qi + s));      // {byte offset of P[c0], cnt, weights address, row}
         const int cnt = __float_as_int(rf.y);
         const unsigned pe = pbase + __float_as_uint(rf.x);
-        const unsigned wa = __float_as_uint(rf.z);
+        const unsigned wa = __float_as_uint(rf.z) + wrel;      // wrel: base of the weights when the table holds relative addresses
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
         // per-lane trip count: the divergent loop branch masks finished rows, no predicate inside the body. Four columns per
         // step: the row's weights are padded to a multiple of 4, so one 16-byte broadcast load serves four columns; the
@@ -280,9 +280,9 @@ __device__ __forceinline__ void sparse_quads_pipelined(const KParams &p, const f
 
 template <int AMP, bool TO_SMEM>
 __device__ __forceinline__ void sparse_quads_epilogue(const KParams &p, const float *ptile, const int4 *s_quads, int q0, int q1, int qstep,
-                                                      float *out_clip_frame, float *mtile, int nf, int lane) {
-    if (nf == kFT) sparse_quads_epilogue_impl<AMP, TO_SMEM, true>(p, ptile, s_quads, q0, q1, qstep, out_clip_frame, mtile, nf, lane);
-    else sparse_quads_epilogue_impl<AMP, TO_SMEM, false>(p, ptile, s_quads, q0, q1, qstep, out_clip_frame, mtile, nf, lane);
+                                                      float *out_clip_frame, float *mtile, int nf, int lane, unsigned wrel = 0u) {
+    if (nf == kFT) sparse_quads_epilogue_impl<AMP, TO_SMEM, true>(p, ptile, s_quads, q0, q1, qstep, out_clip_frame, mtile, nf, lane, wrel);
+    else sparse_quads_epilogue_impl<AMP, TO_SMEM, false>(p, ptile, s_quads, q0, q1, qstep, out_clip_frame, mtile, nf, lane, wrel);
 }
 
 }  // namespace f400

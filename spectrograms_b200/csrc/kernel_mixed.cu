@@ -21,6 +21,7 @@
 //            and then written in NATURAL order over the (now dead) spectrum tile: P[bin][frame]
 //   epilogue the lane = frame epilogue (epilogue.cuh): any mapping, scaling, fused DCT; 128-byte row stores
 #include "epilogue.cuh"
+#include "fast400_common.cuh"
 #include "launch.hpp"
 #include "mixed_dft.cuh"
 
@@ -86,6 +87,17 @@ __global__ void __launch_bounds__(32 * W, (32 * W <= 320 && sizeof(T) == 4) ? 2 
     const int nf = rem < kFrames ? static_cast<int>(rem) : kFrames;
     const T *x = static_cast<const T *>(p.samples) + static_cast<long long>(clip) * p.clip_stride;
     const T *win = static_cast<const T *>(p.window);
+    // Quad epilogue (f32 mel / loghz spectrogram plans; the sparse-row schedule of the n400 family, fast400_common.cuh): its table --
+    // int4 {byte offset of P[c0], cnt, weight byte offset, row}[4 n_quads] + zero-padded weights, built by the host -- starts its
+    // way into the shared memory behind the tile now (cp.async, nothing held) and is complete long before the epilogue.
+    const bool quads = sizeof(T) == 4 && p.lane_w_smem != 0;
+    if (quads) {
+        const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(smem_raw + p.lane_w_smem));
+        const char *src = static_cast<const char *>(p.sched);
+        for (int o = 16 * static_cast<int>(threadIdx.x); o < p.lane_w_bytes; o += 16 * 32 * W)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + o), "l"(src + o) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
 
     // ---- load + window: warp = frame (strided), lanes along the packed elements n (samples 2n, 2n+1). The window pairs of a
     //      lane's elements are loaded once; interior frames are taken two at a time up to n_fft 512 (one at a time above: two
@@ -221,22 +233,41 @@ __global__ void __launch_bounds__(32 * W, (32 * W <= 320 && sizeof(T) == 4) ? 2 
     }
     __syncthreads();
     T *P = reinterpret_cast<T *>(smem_raw);                     // P[bin][32 frames], then the scratch rows of the fused MFCC
+    // quad epilogue: frames permuted inside a row so that one 16-byte read returns frames j, j+8, j+16, j+24 (f400::frame_col)
+    const int pcol = quads ? f400::frame_col(lane) : lane;
 #pragma unroll
     for (int i = 0; i < KPW; ++i) {
         const int k = warp + W * i;
         if (k <= L / 2) {
-            P[k * 32 + lane] = pa[i];
-            P[(L - k) * 32 + lane] = pb[i];
+            P[k * 32 + pcol] = pa[i];
+            P[(L - k) * 32 + pcol] = pb[i];
         }
     }
+    if (quads) asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
+    if constexpr (sizeof(T) == 4) {
+        if (quads) {
+            // 4 rows x 32 frames per warp step, rows dealt to the warps quad by quad (longest first); ascending columns, one fused
+            // rounding per term (never further from the exact sum than SparseMatrix::multiply_vec, src/spectrogram.rs:102-117)
+            const int4 *tab = reinterpret_cast<const int4 *>(smem_raw + p.lane_w_smem);
+            const int nq = tab[0].x;
+            const unsigned wrel = static_cast<unsigned>(__cvta_generic_to_shared(tab + 1 + 4 * nq));
+            float *ocf = reinterpret_cast<float *>(p.out) + static_cast<long long>(clip) * p.out_clip_stride + (f0 - p.out_frame_origin);
+            const float *Pf = reinterpret_cast<const float *>(P);
+            if (p.apply_db) f400::sparse_quads_epilogue<2, false>(p, Pf, tab + 1, warp, nq, W, ocf, nullptr, nf, lane, wrel);
+            else if (p.amp == SGX_AMP_MAGNITUDE) f400::sparse_quads_epilogue<1, false>(p, Pf, tab + 1, warp, nq, W, ocf, nullptr, nf, lane, wrel);
+            else f400::sparse_quads_epilogue<0, false>(p, Pf, tab + 1, warp, nq, W, ocf, nullptr, nf, lane, wrel);
+            return;
+        }
+    }
     epilogue_lane_frames<T>(p, P, P + (L + 1) * 32, clip, f0, nf, lane);
 }
 
 template <typename T, int R1, int R2, int R3, int W>
 cudaError_t launch_one(const KParams &p, cudaStream_t stream) {
     constexpr int L = R1 * R2 * R3;
-    const size_t smem = sizeof(Cx<T>) * static_cast<size_t>(L + 1) * kRow;
+    size_t smem = sizeof(Cx<T>) * static_cast<size_t>(L + 1) * kRow;
+    if (p.lane_w_smem) smem = static_cast<size_t>(p.lane_w_smem) + static_cast<size_t>(p.lane_w_bytes);     // + the quad epilogue's table
     const long long grid = static_cast<long long>(p.n_clips) * p.tiles_per_clip;
     if (grid <= 0) return cudaSuccess;
     if (grid > 2147483647LL) return cudaErrorInvalidConfiguration;

@@ -203,6 +203,9 @@ struct sgx_plan {
     float *d_dct_tc = nullptr;              // ... basis blob of dct2_lifter_tc
     // dense (ERB) f32 spectrogram plans outside the n400_tc kernel: linear power spectrogram of a chunk of clips into plan scratch by
     // the plan's FFT family, then the filterbank as row blocks of the tcgen05 GEMM (dense_rows_tc = the dct2_lifter_tc kernel)
+    std::vector<int> mixed_q;               // r2c_fused_mixed quad epilogue: {n_quads,0,0,0} + int4 entries + zero-padded f32 weights (bit patterns)
+    int *d_mixed_q = nullptr;
+    bool eps_denormal = false;              // dB floor below the f32 normal range: kernels that take lg2.approx.ftz are not used
     bool dense_split = false;
     int dense_block_rows = 0;               // rows per GEMM pass
     std::vector<float *> d_dense_tc;        // one B-operand blob per row block
@@ -246,6 +249,7 @@ struct sgx_plan {
         if (d_frames) cudaFree(d_frames);
         if (d_dct_tc) cudaFree(d_dct_tc);
         for (float *q : d_dense_tc) if (q) cudaFree(q);
+        if (d_mixed_q) cudaFree(d_mixed_q);
         if (d_logmel) cudaFree(d_logmel);
         if (scratch_done) cudaEventDestroy(scratch_done);
         for (auto &s : slot) {
@@ -445,6 +449,7 @@ void select_family(sgx_plan &pl) {
     // flushed to zero and silent bins would come out as -inf instead of the floor, so such plans stay on the other families
     const bool eps_denormal = d.amp == SGX_AMP_DECIBELS && d.has_floor_db &&
                               static_cast<float>(std::pow(10.0, d.floor_db / 10.0)) < 1.17549435e-38f;
+    pl.eps_denormal = eps_denormal;
     pl.fast400 = !pl.f64 && !eps_denormal && d.n_fft == 400 && d.hop_size == 160 && d.output != SGX_OUT_COMPLEX_STFT &&
                  (d.output != SGX_OUT_MFCC || static_cast<int>(pl.tab.n_bins) <= fast400_max_scratch_rows());
     if (pl.fast400) {
@@ -506,6 +511,32 @@ void select_family(sgx_plan &pl) {
         for (int q = 0; q < nq; ++q)
             for (int k = 0; k < 4; ++k)
                 if (order[4 * q + k] >= 0) qmax[q] = std::max(qmax[q], cnt[order[4 * q + k]]);
+        // r2c_fused_mixed, f32: the same rows as one flat table for the quad epilogue (quads longest first, dealt to the warps round
+        // robin): {n_quads, 0, 0, 0}, int4 {byte offset of P[c0], cnt, byte offset of the row's weights, row}[4 n_quads], then the
+        // weights, every row zero-padded to a multiple of four
+        pl.mixed_q.clear();
+        if (contiguous && !pl.f64 && nq > 0) {
+            std::vector<int> tq(4 + 16 * static_cast<size_t>(nq), 0);
+            std::vector<float> wq;
+            tq[0] = nq;
+            for (int q = 0; q < nq; ++q)
+                for (int k = 0; k < 4; ++k) {
+                    const int r = order[4 * q + k];
+                    int *e = &tq[4 + 4 * (4 * static_cast<size_t>(q) + k)];
+                    e[0] = (r >= 0 && cnt[r]) ? pl.tab.col[pl.tab.row_ptr[r]] * 128 : 0;
+                    e[1] = r >= 0 ? cnt[r] : 0;
+                    e[2] = static_cast<int>(wq.size() * sizeof(float));
+                    e[3] = r;
+                    if (r < 0) continue;
+                    for (int i = 0; i < cnt[r]; ++i) wq.push_back(static_cast<float>(pl.tab.val[pl.tab.row_ptr[r] + i]));
+                    while (wq.size() % 4) wq.push_back(0.0f);
+                }
+            if (wq.empty()) wq.assign(4, 0.0f);
+            const size_t at = tq.size();
+            tq.resize(at + wq.size());
+            std::memcpy(&tq[at], wq.data(), wq.size() * sizeof(float));
+            pl.mixed_q = tq;
+        }
         auto make_blob = [&](int W) {
             std::vector<std::vector<int>> per_warp(W);
             std::vector<long> load(W, 0);
@@ -703,6 +734,7 @@ void ensure_device(sgx_plan &pl) {
     pl.d_col = upload_int(pl.tab.col);
     pl.d_wofs = upload_int(pl.wofs);
     pl.d_wofs_tm = upload_int(pl.wofs_tm);
+    if (pl.mixed && !pl.f64) pl.d_mixed_q = upload_int(pl.mixed_q);
     pl.d_tc_blob = upload_int(pl.tc_blob);
     pl.d_lane_rows = upload_int(pl.lane_rows);
     pl.d_row_desc = upload_int(pl.row_desc);
@@ -940,6 +972,22 @@ void run_device(sgx_plan &pl, const void *d_samples, size_t n_clips, size_t n_sa
             q.fd_FT = make_fastdiv(static_cast<unsigned>(q.FT));
             q.vec_ok = (reinterpret_cast<uintptr_t>(q.samples) % (2 * pl.esize) == 0 && clip_stride % 2 == 0 &&
                            pl.desc.hop_size % 2 == 0 && q.pad % 2 == 0) ? 1 : 0;
+            // quad epilogue (sparse rows of the n400 family) for f32 mel / loghz spectrogram outputs when its table fits behind the tile
+            // without costing the second resident CTA; SGX_MIXED_QUADS=0 keeps the lane = frame epilogue
+            static const bool quads_off = std::getenv("SGX_MIXED_QUADS") && std::atoi(std::getenv("SGX_MIXED_QUADS")) == 0;
+            q.lane_w_smem = 0;
+            q.lane_w_bytes = 0;
+            q.sched = nullptr;
+            if (!quads_off && !as_linear_power && pl.d_mixed_q && !pl.f64 && !pl.eps_denormal && pl.desc.output == SGX_OUT_SPECTROGRAM &&
+                (pl.desc.mapping == SGX_MAP_MEL || pl.desc.mapping == SGX_MAP_LOGHZ) && pl.rows_contig) {
+                const size_t base = (mixed_smem_bytes(pl.desc.n_fft, false) + 15) & ~size_t(15), bytes = pl.mixed_q.size() * sizeof(int);
+                const size_t ctas = (base + 1024) * 2 <= size_t(228) * 1024 ? 2 : 1;
+                if ((base + bytes + 1024) * ctas <= size_t(228) * 1024) {
+                    q.lane_w_smem = static_cast<int>(base);
+                    q.lane_w_bytes = static_cast<int>(bytes);
+                    q.sched = pl.d_mixed_q;
+                }
+            }
             ck(launch_mixed(q, pl.f64, stream), "kernel launch (r2c_fused_mixed)");
         } else {
             ck(launch_generic(q, pl.f64, pl.smem_bytes, stream), "kernel launch (r2c_fused_generic)");
