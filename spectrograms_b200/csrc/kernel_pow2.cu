@@ -649,27 +649,37 @@ k_r2c_fused_pow2(const __grid_constant__ KParams p) {
         pf[M - k] = pb[u];
     }
     if (t == 0) pf[M / 2] = pm;
+    if (!PAIR && p.lane_w_smem) asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     if (FT >= 16 && p.output == SGX_OUT_SPECTROGRAM && p.rows_contig && (p.mapping == SGX_MAP_MEL || p.mapping == SGX_MAP_LOGHZ)) {
         // Wide tiles (n_fft 256 / 512), sparse rows: lane = frame, FT consecutive lanes share a row, so the row's extent
         // and every weight are one broadcast load and the store is a run of FT frames; all index math is compile time.
         // Ascending-column, un-fused accumulation as in SparseMatrix::multiply_vec (src/spectrogram.rs:102-117).
+        // STAGED: the row descriptors and the weights were copied into shared memory by cp.async at kernel start (the block
+        // p.lane_w: int4 {first entry, count, first column}[n_bins], then the CSR values): every broadcast read is then a
+        // shared-memory read instead of an exposed global / L1 round trip (73 % of the 512 / 160 / 80 kernel's stall samples sat here).
         constexpr int NT = FT * TPF, GROUPS = NT / FT;
         const int f = tid % FT, g = tid / FT;
         const T eps = static_cast<T>(p.eps);
-        const T *val = static_cast<const T *>(p.val);
         const T *px = P + f * p.tile_stride;
         T *out = static_cast<T *>(p.out) + static_cast<long long>(clip) * p.out_clip_stride + (f0 - p.out_frame_origin) + f;
-        for (int row = g; row < p.n_bins; row += GROUPS) {
-            const int4 d = __ldg(p.row_desc + row);              // {first entry, count, first column}
-            const int cnt = d.y;
-            const T *w = val + d.x;
-            const T *pc = px + d.z;
-            T acc = T(0);
+        auto rows = [&](auto staged) {
+            constexpr bool STAGED = decltype(staged)::value;
+            const int4 *sdesc = reinterpret_cast<const int4 *>(smem_raw + p.lane_w_smem);
+            const T *val = STAGED ? reinterpret_cast<const T *>(sdesc + p.n_bins) : static_cast<const T *>(p.val);
+            for (int row = g; row < p.n_bins; row += GROUPS) {
+                const int4 d = STAGED ? sdesc[row] : __ldg(p.row_desc + row);              // {first entry, count, first column}
+                const int cnt = d.y;
+                const T *w = val + d.x;
+                const T *pc = px + d.z;
+                T acc = T(0);
 #pragma unroll 4
-            for (int i = 0; i < cnt; ++i) acc = t_add_rn(acc, t_mul_rn(__ldg(w + i), pc[i]));
-            if (f < nf) out[static_cast<long long>(row) * p.out_row_stride] = amp_scale<T>(acc, p.amp, p.apply_db, eps);
-        }
+                for (int i = 0; i < cnt; ++i) acc = t_add_rn(acc, t_mul_rn(STAGED ? w[i] : __ldg(w + i), pc[i]));
+                if (f < nf) out[static_cast<long long>(row) * p.out_row_stride] = amp_scale<T>(acc, p.amp, p.apply_db, eps);
+            }
+        };
+        if (!PAIR && p.lane_w_smem != 0) rows(std::true_type{});
+        else rows(std::false_type{});
         return;
     }
     // scratch for the fused-MFCC log-mel tile sits behind the power tile (host sizes the buffer for it)

@@ -203,6 +203,8 @@ struct sgx_plan {
     float *d_dct_tc = nullptr;              // ... basis blob of dct2_lifter_tc
     // dense (ERB) f32 spectrogram plans outside the n400_tc kernel: linear power spectrogram of a chunk of clips into plan scratch by
     // the plan's FFT family, then the filterbank as row blocks of the tcgen05 GEMM (dense_rows_tc = the dct2_lifter_tc kernel)
+    std::vector<int> wide_rows;             // r2c_fused_pow2 wide tiles (FT >= 16): int4 row descriptors + CSR values (bit patterns of T), staged into shared memory
+    void *d_wide_rows = nullptr;
     std::vector<int> mixed_q;               // r2c_fused_mixed quad epilogue: {n_quads,0,0,0} + int4 entries + zero-padded f32 weights (bit patterns)
     int *d_mixed_q = nullptr;
     bool eps_denormal = false;              // dB floor below the f32 normal range: kernels that take lg2.approx.ftz are not used
@@ -250,6 +252,7 @@ struct sgx_plan {
         if (d_dct_tc) cudaFree(d_dct_tc);
         for (float *q : d_dense_tc) if (q) cudaFree(q);
         if (d_mixed_q) cudaFree(d_mixed_q);
+        if (d_wide_rows) cudaFree(d_wide_rows);
         if (d_logmel) cudaFree(d_logmel);
         if (scratch_done) cudaEventDestroy(scratch_done);
         for (auto &s : slot) {
@@ -734,6 +737,17 @@ void ensure_device(sgx_plan &pl) {
     pl.d_col = upload_int(pl.tab.col);
     pl.d_wofs = upload_int(pl.wofs);
     pl.d_wofs_tm = upload_int(pl.wofs_tm);
+    pl.wide_rows.clear();
+    if (pl.pow2 && pl.pow2_ft >= 16 && pl.rows_contig && !pl.row_desc.empty() && pl.desc.output == SGX_OUT_SPECTROGRAM &&
+        (pl.desc.mapping == SGX_MAP_MEL || pl.desc.mapping == SGX_MAP_LOGHZ)) {
+        pl.wide_rows = pl.row_desc;                             // int4 {first entry, count, first column, 0} per row
+        const size_t at = pl.wide_rows.size(), nnz = pl.tab.val.size();
+        const size_t words = (nnz * pl.esize + 15) / 16 * 4;   // CSR values as T, padded to 16 bytes
+        pl.wide_rows.resize(at + words, 0);
+        if (pl.f64) for (size_t i = 0; i < nnz; ++i) std::memcpy(reinterpret_cast<char *>(&pl.wide_rows[at]) + 8 * i, &pl.tab.val[i], 8);
+        else for (size_t i = 0; i < nnz; ++i) { const float v = static_cast<float>(pl.tab.val[i]); std::memcpy(&pl.wide_rows[at + i], &v, 4); }
+        pl.d_wide_rows = upload_int(pl.wide_rows);
+    }
     if (pl.mixed && !pl.f64) pl.d_mixed_q = upload_int(pl.mixed_q);
     pl.d_tc_blob = upload_int(pl.tc_blob);
     pl.d_lane_rows = upload_int(pl.lane_rows);
@@ -949,6 +963,17 @@ void run_device(sgx_plan &pl, const void *d_samples, size_t n_clips, size_t n_sa
             q.lane_w_smem = 0;
             q.lane_w_bytes = 0;
             // (measured: n_fft 2048 -9 .. -11 %, n_fft 1024 +1.7 % -- its rows are half as long -- so from 2048 points on)
+            if (!stage_w_off && !(q.vec_ok & 2) && !as_linear_power && pl.d_wide_rows) {
+                // wide tiles (n_fft 256 / 512): row descriptors + CSR values of the lane = frame sparse rows
+                const size_t wbytes = pl.wide_rows.size() * sizeof(int), base = (smem + 15) & ~size_t(15);
+                const size_t budget = size_t(227) * 1024 / static_cast<size_t>(std::max(1, pow2_min_blocks(pl.desc.n_fft, pl.f64))) - 1024;
+                if (base + wbytes <= budget) {
+                    q.lane_w = pl.d_wide_rows;
+                    q.lane_w_smem = static_cast<int>(base);
+                    q.lane_w_bytes = static_cast<int>(wbytes);
+                    smem = base + wbytes;
+                }
+            } else
             if (!stage_w_off && !(q.vec_ok & 2) && q.FT <= 8 && pl.desc.n_fft >= 2048 && pl.desc.output == SGX_OUT_SPECTROGRAM && pl.desc.mapping != SGX_MAP_LINEAR &&
                 q.n_lane_slots > 0 && !pl.lane_w.empty()) {
                 const size_t wbytes = pl.lane_w.size() * pl.esize, base = (smem + 15) & ~size_t(15);
