@@ -322,17 +322,38 @@ void build_lane_rows(sgx_plan &pl) {
         }
         int maxc = 0;
         for (int r : arranged) if (r >= 0) maxc = std::max(maxc, cnt[r]);
+        // A warp runs as long as its longest row, so a shorter row may start up to (maxc - cnt) columns early on zero weights at no
+        // cost (acc = 0 + 0 * x stays 0: results unchanged bit for bit). The slack is used to give the 8 lanes of every quarter warp
+        // distinct (first column mod 8): their 16-byte tile reads then hit 8 different bank groups at every step of the walk.
+        std::vector<int> shift(32, 0);
+        if (!dense)
+            for (int g0 = 0; g0 < 32; g0 += 8) {
+                bool used[8] = {false, false, false, false, false, false, false, false};
+                std::vector<int> lanes;
+                for (int l = g0; l < g0 + 8; ++l) if (arranged[l] >= 0 && cnt[arranged[l]] > 0) lanes.push_back(l);
+                std::stable_sort(lanes.begin(), lanes.end(), [&](int a, int b) {       // least slack first
+                    return std::min(maxc - cnt[arranged[a]], c0[arranged[a]]) < std::min(maxc - cnt[arranged[b]], c0[arranged[b]]);
+                });
+                for (int l : lanes) {
+                    const int r = arranged[l], slack = std::min(maxc - cnt[r], c0[r]);
+                    int pick = 0;
+                    for (int dlt = 0; dlt <= std::min(slack, 7); ++dlt)
+                        if (!used[(c0[r] - dlt) & 7]) { pick = dlt; break; }
+                    shift[l] = pick;
+                    used[(c0[r] - pick) & 7] = true;
+                }
+            }
         const size_t wofs = pl.lane_w.size();
         pl.lane_w.resize(wofs + static_cast<size_t>(maxc) * 32, 0.0);
         for (int lane = 0; lane < 32; ++lane) {
-            const int r = arranged[lane];
+            const int r = arranged[lane], sh = shift[lane];
             pl.lane_rows.push_back(r);
-            pl.lane_rows.push_back(r >= 0 ? c0[r] : 0);
-            pl.lane_rows.push_back(r >= 0 ? cnt[r] : 0);
+            pl.lane_rows.push_back(r >= 0 ? c0[r] - sh : 0);
+            pl.lane_rows.push_back(r >= 0 ? cnt[r] + sh : 0);
             pl.lane_rows.push_back(static_cast<int>(wofs));
             if (r < 0) continue;
             for (int i = 0; i < cnt[r]; ++i)
-                pl.lane_w[wofs + static_cast<size_t>(i) * 32 + lane] =
+                pl.lane_w[wofs + static_cast<size_t>(i + sh) * 32 + lane] =
                     dense ? pl.tab.dense[static_cast<size_t>(r) * ol + i] : pl.tab.val[pl.tab.row_ptr[r] + i];
         }
     }
