@@ -35,6 +35,7 @@ __device__ __forceinline__ Cx<float> mul2(Cx<float> a, Cx<float> b) { unsigned l
 __device__ __forceinline__ Cx<float> fma2(Cx<float> a, Cx<float> b, Cx<float> c) { unsigned long long r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pk2(a)), "l"(pk2(b)), "l"(pk2(c))); return upk2(r); }
 // a * b = a.x * (b.x, b.y) + a.y * (-b.y, b.x)
 __device__ __forceinline__ Cx<float> operator*(Cx<float> a, Cx<float> b) { return fma2(Cx<float>{a.y, a.y}, Cx<float>{-b.y, b.x}, mul2(Cx<float>{a.x, a.x}, b)); }
+__device__ __forceinline__ Cx<double> mul2(Cx<double> a, Cx<double> b) { return {a.x * b.x, a.y * b.y}; }
 __device__ __forceinline__ Cx<double> operator+(Cx<double> a, Cx<double> b) { return {a.x + b.x, a.y + b.y}; }
 __device__ __forceinline__ Cx<double> operator-(Cx<double> a, Cx<double> b) { return {a.x - b.x, a.y - b.y}; }
 __device__ __forceinline__ Cx<double> operator*(Cx<double> a, Cx<double> b) { return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
@@ -423,6 +424,11 @@ k_r2c_fused_pow2(const __grid_constant__ KParams p) {
     // ---- post pass: X[k] = E + W_N^k O, X[M-k] = conj(E - W_N^k O); thread owns k = t + TPF*u (u < RPT/2), plus k = M/2
     //      and k = 0 / M on thread 0. Values are held in registers across the barrier because the tile may alias z.
     const C *post = static_cast<const C *>(p.post);
+    // k = t + TPF u and M - k walk the padded buffer with constant strides when TPF is a multiple of 16 (pad16 is linear on such
+    // steps): two base addresses per thread, immediate offsets per u. The halvings of the split are taken once on the sums --
+    // 0.5 (E' + W O') instead of 0.5 E' + W (0.5 O'): scaling by a power of two commutes with every rounding, the bits are the same.
+    constexpr int PSTEP = TPF + TPF / 16;
+    const int pa0 = pad16(t), pb0 = pad16(M - t);
     auto post_pair = [&](int u, C &xa, C &xb) {
         const int k = t + TPF * u;                 // 0 .. M/2 - 1
         if (k == 0) {
@@ -430,13 +436,13 @@ k_r2c_fused_pow2(const __grid_constant__ KParams p) {
             xa = {z0.x + z0.y, T(0)};              // bin 0
             xb = {z0.x - z0.y, T(0)};              // bin M
         } else {
-            const C a = z[pad16(k)], b = z[pad16(M - k)];
-            const C ev = {T(0.5) * (a.x + b.x), T(0.5) * (a.y - b.y)};
-            const C od = {T(0.5) * (a.y + b.y), T(0.5) * (b.x - a.x)};
+            const C a = TPF % 16 == 0 ? z[pa0 + PSTEP * u] : z[pad16(k)], b = TPF % 16 == 0 ? z[pb0 - PSTEP * u] : z[pad16(M - k)];
+            const C ev = a + C{b.x, -b.y};         // 2 E
+            const C od = C{a.y, -a.x} + C{b.y, b.x};   // 2 O
             const C wo = od * ldg_cx<T>(post + k);
-            xa = ev + wo;                          // bin k
-            const C d = ev - wo;
-            xb = {d.x, -d.y};                      // bin M - k
+            const C s = ev + wo, d = ev - wo;
+            xa = mul2(C{T(0.5), T(0.5)}, s);       // bin k
+            xb = mul2(C{T(0.5), T(-0.5)}, d);      // bin M - k
         }
     };
     if (p.output == SGX_OUT_COMPLEX_STFT) {
