@@ -351,7 +351,7 @@ k_r2c_fused_pow2(const __grid_constant__ KParams p) {
 #pragma unroll
                 for (int j = 0; j < R; ++j) {
                     const C w = ldg_cx<T>(wf + j * B);
-                    v[j] = {v[j].x * w.x, v[j].y * w.y};
+                    v[j] = mul2(v[j], w);                  // sample * window[i] (src/spectrogram.rs:1319), both halves in one instruction
                 }
             }
         }
@@ -365,7 +365,7 @@ k_r2c_fused_pow2(const __grid_constant__ KParams p) {
 #pragma unroll
             for (int j = 0; j < R; ++j) {
                 const C w = ldg_cx<T>(wf + j * B);
-                v[j] = {v[j].x * w.x, v[j].y * w.y};
+                v[j] = mul2(v[j], w);                  // sample * window[i] (src/spectrogram.rs:1319), both halves in one instruction
             }
         } else {
 #pragma unroll                      // (static indices only: a rolled loop would push v[] into local memory)
