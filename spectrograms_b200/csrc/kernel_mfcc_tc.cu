@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(kAllThreads, 1) k_dct2_lifter_tc(const __grid_
                     const int c = c0 + i;
                     if (c >= p.row0 && c < p.n_mfcc) {
                         const float acc = __uint_as_float(v[i]) + __uint_as_float(u[i]);
-                        o[static_cast<long long>(c - p.row0) * p.n_frames] = MODE == 0 ? acc * sLift[c] : amp_scale<float>(acc, p.amp, p.apply_db, p.eps);
+                        o[static_cast<long long>(c - p.row0) * p.n_frames] = MODE == 0 ? acc * sLift[c] : amp_scale_fast(acc, p.amp, p.apply_db, p.eps, p.eps >= 1.17549435e-38f);
                     }
                 }
             }

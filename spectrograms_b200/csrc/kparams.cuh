@@ -122,6 +122,24 @@ template <typename T> __device__ __forceinline__ T amp_scale(T v, int amp, int a
     return v;
 }
 
+// The same for loops that scale many values: when the dB floor eps is a normal f32 (all but floors below about -379 dB), max(v, eps)
+// is normal too and lg2.approx.ftz returns exactly what __log2f returns -- without its per-call denormal fix-up (a scale, a
+// select and an add around the MUFU). fast_db is that launch-uniform condition; f64 has no such short cut.
+__device__ __forceinline__ float amp_scale_fast(float v, int amp, int apply_db, float eps, bool fast_db) {
+    if (amp == 1) v = sqrtf(v);
+    if (apply_db) {
+        if (fast_db) {
+            float r;
+            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaxf(v, eps)));
+            v = 3.01029995663981195f * r;
+        } else {
+            v = t_ten_log10(fmaxf(v, eps));
+        }
+    }
+    return v;
+}
+__device__ __forceinline__ double amp_scale_fast(double v, int amp, int apply_db, double eps, bool) { return amp_scale<double>(v, amp, apply_db, eps); }
+
 // apply_chroma_normalization (src/chroma.rs:406-453) on one frame's 12 pitch classes, in the reference's fold order
 template <typename T> __device__ __forceinline__ void chroma_normalise(T (&c)[12], int norm) {
     T d = T(0);
