@@ -121,6 +121,19 @@ def test_tm_batches_short_long_unaligned_and_host_pointers():
         host = view.cpu().numpy()
         for i in (0, 5):
             assert np.abs(got[i] - ref.compute(host[i].astype(np.float64))).max() <= TOL_DB
+    base2 = torch.randn((6, 30002), generator=g, device="cuda")
+    for view in (base2[:, 2:], base2[:, 2:29002]):         # 8-byte but not 16-byte aligned: cp.async (not bulk-copy) staged instantiation
+        got = plan.compute_batch(view).cpu().numpy()
+        host = view.cpu().numpy()
+        for i in (0, 5):
+            assert np.abs(got[i] - ref.compute(host[i].astype(np.float64))).max() <= TOL_DB
+    two = torch.randn((700, 8000), generator=g, device="cuda")                       # 51 frames = 2 tiles per clip, both edge tiles, 1400 tiles
+    out = plan.compute_batch(two)
+    smem = sg.SpectrogramPlanner().mel_plan(P(), sg.MelParams(128, 0.0, 8000.0), sg.LogParams(-80.0), "db", "float32")
+    smem.set_tmem_exchange(False)
+    assert torch.equal(out, smem.compute_batch(two))       # contiguous tile runs / bulk-staged edge tiles: same bits as the shared-memory kernel
+    for i in (0, 350, 699):
+        assert np.abs(out[i].cpu().numpy() - ref.compute(two[i].cpu().numpy().astype(np.float64))).max() <= TOL_DB
     hx = np.random.default_rng(5).standard_normal((7, 33333)).astype(np.float32)     # host pointers through the staging pipeline
     got = plan.compute_batch(hx)
     assert isinstance(got, np.ndarray)
