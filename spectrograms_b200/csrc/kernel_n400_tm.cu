@@ -16,8 +16,8 @@
 //   phase A   the filterbank rows of tile t (sparse mel / loghz rows from the power tile, the quad schedule of
 //             kernel_fast400.cu -> sqrt / dB -> row stores) AND pass 1 of tile t+1 (window + 20-point real-pair DFT in
 //             registers -> Y[k1][n2] into TMEM columns 0..399 of the thread's own lane, tcgen05.st / STTM) share one
-//             phase: half the warps start with their rows, the other half with their FFT tasks, so the load/store-bound
-//             rows of one warp fill the issue slots the FP32-bound butterflies of another leave free.
+//             phase with no barrier between them: every warp runs its rows, then its FFT tasks (the warps drift apart by the
+//             different lengths of their row lists, which is what mixes load/store-bound and FP32-bound work on a scheduler).
 //
 // Arithmetic is the arithmetic of kernel_fast400.cu (same task functions, same epilogue); only where Y travels differs.
 // Measured steps of this design (dedicated filterbank warps behind full / free barriers lost: one or two such warps per
@@ -463,9 +463,15 @@ __global__ void __launch_bounds__(kGroups * GW * 32, 1) k_r2c_fused_n400_tm(cons
         const long long rem = p.frame_begin + p.frames_todo - f0;
         const int nf = rem < kFT ? static_cast<int>(rem) : kFT;
         float *ocf = static_cast<float *>(p.out) + static_cast<long long>(clip) * p.out_clip_stride + (f0 - p.out_frame_origin);
-        if (wl & 1) rows_epilogue(p, ptile, S.quads, q0, q1, ocf, nf, lane);
+#ifndef SGX_TM_ORDER
+#define SGX_TM_ORDER 4
+#endif
+        // which warps take their rows before their FFT tasks (measured, same box, alternating: every warp rows first 1.020 ms, odd
+        // warps first 1.046, even warps first 1.046, warps 2 / 3 first 1.054, none first 1.073 -- profiles/r2_n400_tm_experiments.md)
+        const bool rows_first = SGX_TM_ORDER == 0 ? (wl & 1) != 0 : SGX_TM_ORDER == 1 ? (wl & 1) == 0 : SGX_TM_ORDER == 2 ? wl >= 2 : SGX_TM_ORDER == 3 ? wl < 2 : SGX_TM_ORDER == 4;
+        if (rows_first) rows_epilogue(p, ptile, S.quads, q0, q1, ocf, nf, lane);
         if (has_next) pass1_all(sig, S.win, lane, wl, lane_base);
-        if (!(wl & 1)) rows_epilogue(p, ptile, S.quads, q0, q1, ocf, nf, lane);
+        if (!rows_first) rows_epilogue(p, ptile, S.quads, q0, q1, ocf, nf, lane);
         tc::wait_st();
         tc::fence_before_sync();
         tc::bar_sync(bar, kGroupThreads);                    // Y(next) complete; the power tile and the samples are free again
