@@ -174,6 +174,18 @@ SGX_HD void pass2_load(const float *__restrict__ ybuf, const float2 *__restrict_
     }
 }
 
+// norm_sqr (src/spectrogram.rs:1332-1334) as FMUL + FFMA: one rounding fewer than the reference's re*re + im*im (the contraction
+// nvcc applies by itself in the generic / mixed / pow2 families), two FMA-pipe cycles per bin instead of three (packed multiply +
+// add). SGX_NORM_UNFUSED keeps the two-rounding form for A/B runs.
+SGX_HD float norm_sqr(float2 X) {
+#ifdef SGX_NORM_UNFUSED
+    const float2 sq = cmul2(X, X);
+    return sq.x + sq.y;
+#else
+    return fmaf(X.x, X.x, X.y * X.y);
+#endif
+}
+
 // writes |X[bin]|^2 for the bins this butterfly owns into P[bin][f]
 SGX_HD void pass2_finish(float2 (&v)[20], float *__restrict__ ptile, int f, int k1) {
     dft20(v);
@@ -181,8 +193,7 @@ SGX_HD void pass2_finish(float2 (&v)[20], float *__restrict__ ptile, int f, int 
 #pragma unroll
     for (int k2 = 0; k2 < 20; ++k2) {
         const float2 X = v[reg_of_bin(k2)];
-        const float2 sq = cmul2(X, X);
-        const float pw = sq.x + sq.y;                 // norm_sqr = re*re + im*im (src/spectrogram.rs:1332-1334)
+        const float pw = norm_sqr(X);                 // norm_sqr = re*re + im*im (src/spectrogram.rs:1332-1334)
         if (k2 < 10) {
             p[kFT * (k1 + 20 * k2)] = pw;             // bin k1 + 20 k2
         } else if (k2 == 10) {

@@ -120,8 +120,7 @@ __device__ __forceinline__ void pass2_tc(uint32_t ybase, const float2 *__restric
 #pragma unroll
     for (int k2 = 0; k2 < 20; ++k2) {
         const float2 X = v[reg_of_bin(k2)];
-        const float2 sq = cmul2(X, X);
-        pw[k2] = sq.x + sq.y;                         // norm_sqr (src/spectrogram.rs:1332-1334)
+        pw[k2] = norm_sqr(X);                         // norm_sqr (src/spectrogram.rs:1332-1334)
     }
 }
 

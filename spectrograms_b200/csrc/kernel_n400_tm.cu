@@ -277,8 +277,7 @@ __device__ __forceinline__ void pass2_finish_tm(float2 (&v)[20], float *__restri
 #pragma unroll
     for (int k2 = 0; k2 < 20; ++k2) {
         const float2 X = v[reg_of_bin(k2)];
-        const float2 sq = cmul2(X, X);
-        pw[k2] = sq.x + sq.y;                         // norm_sqr = re*re + im*im (src/spectrogram.rs:1332-1334)
+        pw[k2] = norm_sqr(X);                         // norm_sqr = re*re + im*im (src/spectrogram.rs:1332-1334)
     }
     float *up = ptile + frame_col(f) + kFT * k1;
     float *down = ptile + frame_col(f) + kFT * (200 - k1);
@@ -352,8 +351,17 @@ __global__ void __launch_bounds__(kGroups * GW * 32, 1) k_r2c_fused_n400_tm(cons
             const int4 q4 = make_int4(e.x * (kFT * 4), e.y | (cnt << 16), static_cast<int>(wbase + 4u * e.z), e.w);
             S.quads[i] = q4;
             if (i >= 4 * (nq - 1)) S.quads[i + 4] = S.quads[i + 8] = S.quads[i + 12] = q4;      // the rows' look-ahead reads stay on valid quads
+#ifdef SGX_TM_DEVW
             for (int k = 0; k < ((e.y + 3) & ~3); ++k) S.w[e.z + k] = k < cnt ? __ldg(val + e0 + k) : 0.f;
+#endif
         }
+#ifndef SGX_TM_DEVW
+        {   // the padded weights, laid out by the host behind the quad table (sgx_api.cu): one coalesced copy
+            const float *hw = reinterpret_cast<const float *>(blob + hdr + 16 * nq);
+            for (int i = tid; i < padded_weights; i += kTmThreads) S.w[i] = __ldg(hw + i);
+            (void)val;
+        }
+#endif
         if (SIG && tid < kGroups) tc::mbar_init(S.bars + tid, 1);
         if (SIG && tid == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if (warp == 0) tc::alloc(S.tmem_ptr, kTmemCols);

@@ -643,6 +643,22 @@ void select_family(sgx_plan &pl) {
                 }
             }
             tb[1 + Wt] = idx;
+            // behind the table: the rows' weights as f32 bit patterns in the kernel's padded layout (row k of quad q at woq[4 q + k], zeros
+            // up to the quad's padded count), so that a CTA stages them with one coalesced copy instead of a serial gather per row
+            {
+                const size_t wat = tb.size();
+                tb.resize(wat + static_cast<size_t>(std::max(padded_tm, 4)), 0);
+                for (int q = 0; q < nq && ok; ++q)
+                    for (int k = 0; k < 4; ++k) {
+                        const int r = order[4 * q + k] >= 0 ? order[4 * q + k] : order[4 * q];
+                        if (r < 0) continue;
+                        const int e0 = pl.tab.row_ptr[r], n = pl.tab.row_ptr[r + 1] - e0;
+                        for (int j = 0; j < n && j < cntU[q]; ++j) {
+                            const float v = static_cast<float>(pl.tab.val[static_cast<size_t>(e0 + j)]);
+                            std::memcpy(&tb[wat + static_cast<size_t>(woq[4 * static_cast<size_t>(q) + k] + j)], &v, 4);
+                        }
+                    }
+            }
             if (ok) {
                 pl.wofs_tm = tb;
                 pl.tm_weights = std::max(padded_tm, 4);
