@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_PKG, "lib", "libsgx_b200.so")
 
 SGX_OK, SGX_INVALID_INPUT, SGX_DIMENSION_MISMATCH, SGX_BACKEND_ERROR, SGX_INTERNAL_ERROR = range(5)
 
-# every symbol include/sgx_b200.h declares (tests/test_boundary.py checks the header against this list)
+# every symbol include/sgx_b200.h declares (tests/test_host_api.py checks the header against this list)
 EXPORTS = [
     "sgx_last_error_message", "sgx_last_dimension_mismatch", "sgx_version", "sgx_plan_create", "sgx_plan_destroy",
     "sgx_plan_output_shape", "sgx_plan_axes", "sgx_plan_window", "sgx_plan_filterbank", "sgx_plan_kernel_name",
